@@ -1,0 +1,207 @@
+/* sunet_b200.h — C ABI of libsunet_b200.so
+ *
+ * The drop-in boundary of the B200-native SelectiveUNet hot path.  The reference
+ * (yellofi/SelectiveNet_for_semantic_segmentation_binary) has no FFI layer of its own: every
+ * op below replaces a stock-PyTorch dispatch made from the reference's Python, cited per entry
+ * point as file:line into /root/reference.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error (sunet_last_error() explains);
+ *     nothing throws, exits or allocates device memory: the caller owns every buffer,
+ *     including workspaces;
+ *   - all work is enqueued on the stream passed in (a cudaStream_t / CUstream); no implicit
+ *     synchronisation, so every call is CUDA-graph capturable;
+ *   - activations are NHWC bf16 ("pix_stride" = elements between consecutive pixels, which
+ *     lets a tensor be a channel slice of a wider buffer); parameters, statistics, logits and
+ *     gradients of parameters are fp32 in the reference's own layouts;
+ *   - functions are re-entrant and may be called from any host thread (PyTorch's autograd
+ *     worker threads included); one process drives one GPU.
+ */
+#ifndef SUNET_B200_H_
+#define SUNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* sunet_stream_t;
+
+#define SUNET_ABI_VERSION 1
+/* workspace every reduce-type call may use (bytes); callers pass one buffer of at least this size */
+#define SUNET_WORKSPACE_BYTES (8u << 20)
+
+int sunet_abi_version(void);
+const char* sunet_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * G1: tensor-core implicit GEMM  D[pixel, n] = sum_{tap,c} A_tap[pixel, c] * W[n, tap*C + c] (+bias)
+ * tcgen05.mma / TMEM / TMA.  Replaces nn.Conv2d(k3,p1) forward + backward-data and
+ * nn.ConvTranspose2d(k2,s2) forward + backward-data (model.py:11, :44-45, :51-52, :57-58;
+ * backward via train.py:208).
+ * ---------------------------------------------------------------------------------------- */
+enum { SUNET_A_CONV3X3 = 0, SUNET_A_PLAIN = 1, SUNET_A_GATHER2X2 = 2 };
+enum { SUNET_D_NHWC = 0, SUNET_D_SCATTER2X2 = 1 };
+
+typedef struct sunet_conv_gemm_args {
+  int batch, height, width;    /* the pixel grid that is the GEMM M dimension                    */
+  int a_mode;                  /* CONV3X3: 9 taps, zero pad 1; PLAIN: 1 tap;                     */
+                               /* GATHER2X2: src0 is [batch][2*height][2*width][..], 4 taps (a,b) */
+  const void* src0;            /* NHWC bf16                                                       */
+  int src0_channels, src0_pix_stride;
+  const void* src1;            /* optional second source, concatenated after src0 along C (NULL)  */
+  int src1_channels, src1_pix_stride;
+  const void* weights;         /* bf16 [n_total][k_total], k = tap*(C0+C1) + c                    */
+  int n_total, k_total;
+  const float* bias;           /* optional fp32 [n_total]                                         */
+  void* dst;                   /* NHWC bf16; SCATTER2X2: [batch][2*height][2*width][n_total/4],   */
+  int dst_pix_stride;          /*   column n = (a*2+b)*C' + co goes to pixel (2y+a, 2x+b), chan co */
+  int d_mode;
+  float* stats;                /* optional fp32 [sunet_conv_gemm_stat_rows()][n_total][2]:        */
+                               /*   per-CTA partial (sum, sum of squares) of the bf16 outputs     */
+} sunet_conv_gemm_args;
+
+int sunet_conv_gemm(const sunet_conv_gemm_args* args, sunet_stream_t stream);
+int sunet_conv_gemm_stat_rows(int batch, int height, int width, int n_total);
+
+/* ------------------------------------------------------------------------------------------
+ * G2: weight-gradient GEMM over pixels, split-K with fp32 partials.
+ *   P[split][tap][m][n] = sum_p A[p, m] * B[p (+) tap, n]
+ * Replaces the backward-weight half of conv2d / conv_transpose2d (train.py:208).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sunet_wgrad_gemm_args {
+  int batch, height, width;    /* pixel grid of A (the reduction dimension)                       */
+  const void* a;               /* NHWC bf16, never shifted                                         */
+  int a_channels, a_pix_stride;
+  int b_mode;                  /* SUNET_A_CONV3X3 (9 shifted taps), _PLAIN (1), _GATHER2X2 (4)     */
+  const void* b0;
+  int b0_channels, b0_pix_stride;
+  const void* b1;              /* optional second B source (concat), NULL otherwise                */
+  int b1_channels, b1_pix_stride;
+  float* partials;             /* fp32 [splits][taps][a_channels][b0+b1 channels]                  */
+  size_t partials_bytes;
+} sunet_wgrad_gemm_args;
+
+int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* args, sunet_stream_t stream);
+int sunet_wgrad_gemm_splits(const sunet_wgrad_gemm_args* args); /* how many splits it will write */
+
+/* sum the split-K partials into the reference's parameter-gradient layout.
+ *   layout 0: conv3x3  grad[co][ci][3][3]   from P[s][r*3+q][co][ci]
+ *   layout 1: convT    grad[ci][co][2][2]   from P[s][a*2+b][ci][co]
+ *   layout 2: first conv (im2col'ed input)  grad[co][cin][3][3] from P[s][0][co][(r*3+q)*cin+ci] */
+int sunet_wgrad_reduce(const float* partials, int splits, int taps, int a_channels, int b_channels, int layout,
+                       int real_cin, float* grad, sunet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / packing (fp32 reference layouts -> bf16 kernel layouts)
+ * ---------------------------------------------------------------------------------------- */
+/* x: fp32 NCHW [B][cin][H][W] (cin*9 <= 64) -> bf16 [B][H][W][64], channel tap*cin+ci = x[.., y+r-1, x+q-1] */
+int sunet_pack_input_im2col(const float* x, void* out, int batch, int cin, int height, int width,
+                            sunet_stream_t stream);
+/* Conv2d weight [co][ci][3][3] -> wf [co][9*ci] (k = tap*ci_total + ci) and, if wd != NULL,
+ * the dgrad operand wd [ci][9*co] (k = flipped_tap*co_total + co) */
+int sunet_pack_conv3x3_weights(const float* w, void* wf, void* wd, int cout, int cin, sunet_stream_t stream);
+/* first conv: [co][cin][3][3] -> [co][64] with k = tap*cin + ci, zero padded */
+int sunet_pack_conv1_weights(const float* w, void* wf, int cout, int cin, sunet_stream_t stream);
+/* ConvTranspose2d weight [ci][co][2][2] -> wf [4*co][ci] (row (a*2+b)*co_total+co), wd [ci][4*co];
+ * bias [co] -> bias4 [4*co] */
+int sunet_pack_convT_weights(const float* w, const float* bias, void* wf, void* wd, float* bias4, int cin, int cout,
+                             sunet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm2d + ReLU (+ MaxPool2d(2)), model.py:12-13,31,35,39
+ * ---------------------------------------------------------------------------------------- */
+/* training: fold per-CTA partials into batch statistics, produce the per-channel affine
+ * (scale, shift) applied to the bias-free conv output, and update the running statistics
+ * (momentum 0.1, unbiased variance; the conv bias only shifts running_mean). */
+int sunet_bn_finalize(const float* stats, int rows, int channels, long long count, const float* gamma,
+                      const float* beta, const float* conv_bias, float* running_mean, float* running_var,
+                      long long* num_batches_tracked, float momentum, float eps, float* scale, float* shift,
+                      float* mean, float* invstd, sunet_stream_t stream);
+/* eval: affine from running statistics */
+int sunet_bn_eval_affine(const float* gamma, const float* beta, const float* conv_bias, const float* running_mean,
+                         const float* running_var, float eps, float* scale, float* shift, int channels,
+                         sunet_stream_t stream);
+/* a = relu(y*scale + shift) -> bf16; pooled (optional) = 2x2/stride-2 max of a */
+int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
+                       int a_pix_stride, void* pooled, int pooled_pix_stride, int batch, int height, int width,
+                       int channels, sunet_stream_t stream);
+/* backward of [BN(train) -> ReLU -> (skip + MaxPool)]:
+ *   g = (dA [+ dPool routed to the first maximum of each 2x2 window]) * (a > 0)
+ *   dgamma = sum g*xhat, dbeta = sum g, dy = scale*(g - dbeta/n - xhat*dgamma/n)  -> bf16
+ * dA may be NULL when only the pooled branch carries gradient. */
+int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const void* dPool, int dPool_pix_stride, const void* y,
+                           int y_pix_stride, const float* scale, const float* shift, const float* mean,
+                           const float* invstd, const float* gamma, float* dgamma, float* dbeta, void* dy,
+                           int dy_pix_stride, int batch, int height, int width, int channels, void* workspace,
+                           size_t workspace_bytes, sunet_stream_t stream);
+/* out[c] = sum_rows stats[row][col_offset + c][0]  (column sums from the G1 epilogue; ConvT bias grad) */
+int sunet_colsum_finalize(const float* stats, int rows, int n_total, int col_offset, int channels, float* out,
+                          sunet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Heads: three 1x1 convs 64 -> 1 (model.py:62,65-66,96,99-101)
+ * ---------------------------------------------------------------------------------------- */
+/* logits[h][p] = b_h + sum_c a[p][c] * w_h[c];  nheads = 1 or 3; planar fp32 == the [N,H,W] tensors */
+int sunet_heads_fwd(const void* a, int a_pix_stride, const float* w0, const float* b0, const float* w1,
+                    const float* b1, const float* w2, const float* b2, int nheads, float* logits, long long pixels,
+                    sunet_stream_t stream);
+/* dA[p][c] = sum_h dl[h][p]*w_h[c] (bf16);  dw_h[c] = sum_p dl[h][p]*a[p][c];  db_h = sum_p dl[h][p] */
+int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,
+                    const float* w2, int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0, float* dw1,
+                    float* db1, float* dw2, float* db2, long long pixels, void* workspace, size_t workspace_bytes,
+                    sunet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses: BCEWithLogitsLoss (train.py:78,195) and calc_selective_risk_image_b
+ * (selective_loss.py:58-85), in two phases so that a data-parallel job can all-reduce the
+ * three sums in between (the reference computes the loss on the gathered global batch).
+ * ---------------------------------------------------------------------------------------- */
+/* sums[0] = sum sigmoid(sel), sums[1] = sum bce(out,t)*sigmoid(sel), sums[2] = sum bce(aux,t)   (fp64)
+ * any of out/sel/aux may be NULL (its sums stay 0) */
+int sunet_loss_sums(const float* out, const float* sel, const float* aux, const float* target, long long pixels,
+                    double* sums, void* workspace, size_t workspace_bytes, sunet_stream_t stream);
+/* results[0] = selective loss (risk + lamb*max(0, cov_target - c)^2), [1] = coverage c,
+ * [2] = aux BCE mean, [3] = total;  P = global pixel count */
+int sunet_loss_finalize(const double* sums, long long global_pixels, float lamb, float target_coverage,
+                        float* results, sunet_stream_t stream);
+/* per-pixel gradients given the (global) sums; g_sel / g_aux = upstream grads of the two losses
+ * (device scalars, NULL = 1.0).  Outputs may be NULL. */
+int sunet_loss_bwd(const float* out, const float* sel, const float* aux, const float* target, long long pixels,
+                   const double* sums, long long global_pixels, float lamb, float target_coverage,
+                   const float* g_sel, const float* g_aux, float* d_out, float* d_sel, float* d_aux,
+                   sunet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Metrics: thresholding + Evaluator confusion matrix (train.py:211-239, eval.py:228-251,
+ * utils/compute_metric.py:10-26).  Exact integer counts.
+ *   counts[0..3] = confusion matrix rows=label cols=pred (only selected pixels if sel != NULL
+ *                  and masked != 0), counts[4] = selected pixels, counts[5] = pixels seen
+ * pred = out >= thr_out, selected = sel >= thr_sel: thresholds in logit space, bisected on the
+ * host against numpy's float64 / float32 sigmoid so the masks are bit-identical.
+ * label_dtype: 0 uint8, 1 float32 (truncated to uint8 like .astype('uint8')), 2 int64.
+ * counts are ACCUMULATED (caller zeroes them at reset()). */
+int sunet_metric_hist(const float* out, const float* sel, const void* label, int label_dtype, long long pixels,
+                      float thr_out, float thr_sel, int masked, unsigned long long* counts, sunet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer: Adam over a table of tensors in one launch (train.py:88-92,209)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sunet_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long numel;
+} sunet_adam_tensor;
+/* table: DEVICE array of n_tensors entries */
+int sunet_adam_step(const sunet_adam_tensor* table, int n_tensors, long long max_numel, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, sunet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUNET_B200_H_ */

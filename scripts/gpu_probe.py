@@ -1,0 +1,394 @@
+"""Kernel-by-kernel bring-up probe (run on a B200 through gpurun).
+
+Each group runs in its own process (a trapped kernel poisons its CUDA context) and compares one
+C-ABI entry point against plain PyTorch on the same bf16-rounded inputs.  This is a development
+aid; the graded parity tests live in tests/.
+
+    python scripts/gpu_probe.py            # run every group, each in a subprocess
+    python scripts/gpu_probe.py g1_plain   # run one group in-process
+"""
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.nn.functional as F
+
+
+def rel_err(got, ref):
+    got = got.float()
+    ref = ref.float()
+    denom = ref.abs().max().clamp_min(1e-6)
+    return ((got - ref).abs().max() / denom).item()
+
+
+def report(name, got, ref, tol=2e-2):
+    e = rel_err(got, ref)
+    ok = e <= tol and torch.isfinite(got.float()).all().item()
+    print(f"  [{'OK ' if ok else 'BAD'}] {name}: max-rel-err {e:.3e} (ref max {ref.abs().max().item():.3e})", flush=True)
+    return ok
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(x):  # NHWC bf16 -> NCHW fp32
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def conv3x3_case(K, B, H, W, Cin, Cout, dual=False, stats=True):
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + H + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(dev)
+    xb = nhwc(x)
+    wf = torch.empty(Cout, 9 * Cin, dtype=torch.bfloat16, device=dev)
+    wd = torch.empty(Cin, 9 * Cout, dtype=torch.bfloat16, device=dev)
+    K.pack_conv3x3_weights(w, wf, wd)
+    y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
+    rows = K.conv_gemm_stat_rows(B, H, W, Cout)
+    st = torch.zeros(rows, Cout, 2, device=dev)
+    if dual:
+        c0 = Cin // 2
+        s0 = xb[..., :c0].contiguous()
+        s1 = xb[..., c0:].contiguous()
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), s0, wf, y, src1=s1, stats=st if stats else None)
+    else:
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), xb, wf, y, stats=st if stats else None)
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(xb), w.to(torch.bfloat16).float(), padding=1)
+    ok = report(f"conv3x3 fwd B{B} {H}x{W} {Cin}->{Cout}{' dual' if dual else ''}", nchw(y), ref)
+    if stats:
+        yb = y.float().reshape(-1, Cout)
+        ok &= report("   stats sum", st[..., 0].sum(0), yb.sum(0), 1e-3)
+        ok &= report("   stats sumsq", st[..., 1].sum(0), (yb * yb).sum(0), 1e-3)
+    # dgrad through the same kernel with the flipped/transposed pack
+    dy = torch.randn(B, Cout, H, W, generator=g).to(dev)
+    dyb = nhwc(dy)
+    dx = torch.full((B, H, W, Cin), float("nan"), dtype=torch.bfloat16, device=dev)
+    K.conv_gemm(K.A_CONV3X3, (B, H, W), dyb, wd, dx)
+    torch.cuda.synchronize()
+    ref_dx = F.conv_transpose2d(nchw(dyb), w.to(torch.bfloat16).float(), padding=1)
+    ok &= report("   dgrad", nchw(dx), ref_dx)
+    return ok
+
+
+def g1_plain(K):
+    dev = "cuda"
+    ok = True
+    for (B, H, W, Cin, N) in [(1, 16, 16, 64, 64), (2, 32, 32, 128, 128), (1, 16, 32, 64, 256), (3, 8, 8, 64, 64)]:
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(B, H, W, Cin, generator=g).to(dev).to(torch.bfloat16)
+        w = (torch.randn(N, Cin, generator=g) / Cin ** 0.5).to(dev).to(torch.bfloat16)
+        y = torch.full((B, H, W, N), float("nan"), dtype=torch.bfloat16, device=dev)
+        K.conv_gemm(K.A_PLAIN, (B, H, W), x, w, y)
+        torch.cuda.synchronize()
+        ref = x.float().reshape(-1, Cin) @ w.float().t()
+        ok &= report(f"plain gemm B{B} {H}x{W} K{Cin} N{N}", y.float().reshape(-1, N), ref)
+    return ok
+
+
+def g1_conv(K):
+    ok = True
+    ok &= conv3x3_case(K, 2, 32, 32, 64, 64)
+    ok &= conv3x3_case(K, 1, 16, 16, 128, 128)
+    ok &= conv3x3_case(K, 2, 8, 8, 256, 256)
+    ok &= conv3x3_case(K, 1, 8, 256, 64, 64)
+    ok &= conv3x3_case(K, 3, 4, 4, 64, 128)
+    ok &= conv3x3_case(K, 2, 16, 16, 128, 64, dual=True)
+    ok &= conv3x3_case(K, 2, 16, 16, 256, 512)
+    return ok
+
+
+def g1_big(K):
+    # many tiles per CTA: exercises the persistent schedule, phase wrap-around, TMEM double buffering
+    ok = conv3x3_case(K, 8, 128, 128, 64, 64)
+    ok &= conv3x3_case(K, 4, 64, 64, 128, 256)
+    return ok
+
+
+def g1_convT(K):
+    dev = "cuda"
+    ok = True
+    for (B, h, w_, Cin, Cout) in [(2, 8, 8, 128, 64), (1, 16, 16, 256, 128), (2, 4, 4, 512, 256)]:
+        g = torch.Generator().manual_seed(7)
+        x = torch.randn(B, Cin, h, w_, generator=g).to(dev)
+        wt = (torch.randn(Cin, Cout, 2, 2, generator=g) / Cin ** 0.5).to(dev)
+        bias = torch.randn(Cout, generator=g).to(dev)
+        xb = nhwc(x)
+        wf = torch.empty(4 * Cout, Cin, dtype=torch.bfloat16, device=dev)
+        wd = torch.empty(Cin, 4 * Cout, dtype=torch.bfloat16, device=dev)
+        b4 = torch.empty(4 * Cout, device=dev)
+        K.pack_convT_weights(wt, bias, wf, wd, b4)
+        # write into the first half of a 2*Cout-wide buffer (as the decoder concat would)
+        buf = torch.zeros(B, 2 * h, 2 * w_, 2 * Cout, dtype=torch.bfloat16, device=dev)
+        up = buf[..., :Cout]
+        K.conv_gemm(K.A_PLAIN, (B, h, w_), xb, wf, up, bias=b4, d_mode=K.D_SCATTER2X2)
+        torch.cuda.synchronize()
+        ref = F.conv_transpose2d(nchw(xb), wt.to(torch.bfloat16).float(), bias, stride=2)
+        ok &= report(f"convT fwd B{B} {h}x{w_} {Cin}->{Cout}", nchw(up), ref)
+        ok &= report("   untouched half", buf[..., Cout:].float(), torch.zeros_like(buf[..., Cout:]).float(), 0)
+        # dgrad: gather 2x2
+        dup = torch.randn(B, Cout, 2 * h, 2 * w_, generator=g).to(dev)
+        dbuf = torch.zeros(B, 2 * h, 2 * w_, 2 * Cout, dtype=torch.bfloat16, device=dev)
+        dbuf[..., :Cout] = nhwc(dup)
+        dx = torch.full((B, h, w_, Cin), float("nan"), dtype=torch.bfloat16, device=dev)
+        K.conv_gemm(K.A_GATHER2X2, (B, h, w_), dbuf[..., :Cout], wd, dx)
+        torch.cuda.synchronize()
+        ref_dx = F.conv2d(dbuf[..., :Cout].float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float().transpose(0, 1),
+                          stride=2)
+        ok &= report("   convT dgrad", nchw(dx), ref_dx)
+    return ok
+
+
+def g2_wgrad(K):
+    dev = "cuda"
+    ok = True
+    cases = [(2, 16, 16, 64, 64, False), (1, 32, 32, 128, 128, False), (2, 8, 8, 256, 128, False),
+             (2, 16, 16, 128, 64, True), (4, 64, 64, 64, 64, False), (2, 4, 4, 512, 256, False)]
+    for (B, H, W, Cin, Cout, dual) in cases:
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(B, Cin, H, W, generator=g).to(dev)
+        dy = torch.randn(B, Cout, H, W, generator=g).to(dev)
+        xb, dyb = nhwc(x), nhwc(dy)
+        if dual:
+            b0 = xb[..., :Cin // 2].contiguous()
+            b1 = xb[..., Cin // 2:].contiguous()
+        else:
+            b0, b1 = xb, None
+        splits = K.wgrad_splits((B, H, W), dyb, K.A_CONV3X3, b0, b1)
+        part = torch.full((splits, 9, Cout, Cin), float("nan"), device=dev)
+        K.wgrad_gemm((B, H, W), dyb, K.A_CONV3X3, b0, part, b1)
+        grad = torch.empty(Cout, Cin, 3, 3, device=dev)
+        K.wgrad_reduce(part, splits, 9, Cout, Cin, 0, grad)
+        torch.cuda.synchronize()
+        xr = nchw(xb).requires_grad_(False)
+        wref = torch.zeros(Cout, Cin, 3, 3, device=dev, requires_grad=True)
+        F.conv2d(xr, wref, padding=1).backward(nchw(dyb))
+        ok &= report(f"wgrad conv3x3 B{B} {H}x{W} {Cin}->{Cout}{' dual' if dual else ''} splits={splits}", grad,
+                     wref.grad, 1e-2)
+    # convT wgrad (gather): dW[ci][co][a][b]
+    for (B, h, w_, Cin, Cout) in [(2, 8, 8, 128, 64), (1, 16, 16, 256, 128)]:
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(B, Cin, h, w_, generator=g).to(dev)
+        dup = torch.randn(B, Cout, 2 * h, 2 * w_, generator=g).to(dev)
+        xb = nhwc(x)
+        dbuf = torch.zeros(B, 2 * h, 2 * w_, 2 * Cout, dtype=torch.bfloat16, device=dev)
+        dbuf[..., :Cout] = nhwc(dup)
+        dupv = dbuf[..., :Cout]
+        splits = K.wgrad_splits((B, h, w_), xb, K.A_GATHER2X2, dupv)
+        part = torch.full((splits, 4, Cin, Cout), float("nan"), device=dev)
+        K.wgrad_gemm((B, h, w_), xb, K.A_GATHER2X2, dupv, part)
+        grad = torch.empty(Cin, Cout, 2, 2, device=dev)
+        K.wgrad_reduce(part, splits, 4, Cin, Cout, 1, grad)
+        torch.cuda.synchronize()
+        wref = torch.zeros(Cin, Cout, 2, 2, device=dev, requires_grad=True)
+        F.conv_transpose2d(nchw(xb), wref, stride=2).backward(dupv.float().permute(0, 3, 1, 2))
+        ok &= report(f"wgrad convT B{B} {h}x{w_} {Cin}->{Cout} splits={splits}", grad, wref.grad, 1e-2)
+    # plain (first layer, im2col'ed input)
+    B, H, W, Cin, Cout = 2, 16, 16, 3, 64
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev)
+    dy = torch.randn(B, Cout, H, W, generator=g).to(dev)
+    dyb = nhwc(dy)
+    col = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=dev)
+    K.pack_input_im2col(x, col)
+    splits = K.wgrad_splits((B, H, W), dyb, K.A_PLAIN, col)
+    part = torch.full((splits, 1, Cout, 64), float("nan"), device=dev)
+    K.wgrad_gemm((B, H, W), dyb, K.A_PLAIN, col, part)
+    grad = torch.empty(Cout, Cin, 3, 3, device=dev)
+    K.wgrad_reduce(part, splits, 1, Cout, 64, 2, grad, real_cin=Cin)
+    torch.cuda.synchronize()
+    wref = torch.zeros(Cout, Cin, 3, 3, device=dev, requires_grad=True)
+    F.conv2d(x.to(torch.bfloat16).float(), wref, padding=1).backward(nchw(dyb))
+    ok &= report("wgrad first layer (im2col)", grad, wref.grad, 1e-2)
+    # first-layer forward through the im2col + plain GEMM
+    w1 = (torch.randn(Cout, Cin, 3, 3, generator=g) / 5).to(dev)
+    w1p = torch.empty(Cout, 64, dtype=torch.bfloat16, device=dev)
+    K.pack_conv1_weights(w1, w1p)
+    y = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    K.conv_gemm(K.A_PLAIN, (B, H, W), col, w1p, y)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w1.to(torch.bfloat16).float(), padding=1)
+    ok &= report("first layer fwd (im2col)", nchw(y), ref)
+    return ok
+
+
+def ew_bn(K):
+    dev = "cuda"
+    ok = True
+    ws = K.new_workspace(dev)
+    for (B, H, W, Cc, pool) in [(2, 16, 16, 64, True), (2, 8, 8, 128, False), (1, 32, 32, 256, True),
+                                (3, 4, 4, 512, False)]:
+        g = torch.Generator().manual_seed(11)
+        y = torch.randn(B, Cc, H, W, generator=g).to(dev) * 1.5 + 0.3
+        yb = nhwc(y)
+        gamma = (torch.rand(Cc, generator=g) + 0.5).to(dev)
+        beta = (torch.randn(Cc, generator=g) * 0.2).to(dev)
+        cbias = (torch.randn(Cc, generator=g) * 0.1).to(dev)
+        # statistics as G1 would produce them
+        yf = yb.float().reshape(-1, Cc)
+        st = torch.stack([yf.sum(0), (yf * yf).sum(0)], dim=-1).reshape(1, Cc, 2).contiguous()
+        rm = torch.zeros(Cc, device=dev)
+        rv = torch.ones(Cc, device=dev)
+        nbt = torch.zeros((), dtype=torch.int64, device=dev)
+        scale, shift, mean, invstd = (torch.empty(Cc, device=dev) for _ in range(4))
+        count = B * H * W
+        K.bn_finalize(st, 1, Cc, count, gamma, beta, cbias, rm, rv, nbt, 0.1, 1e-5, scale, shift, mean, invstd)
+        a = torch.empty(B, H, W, Cc, dtype=torch.bfloat16, device=dev)
+        pooled = torch.empty(B, H // 2, W // 2, Cc, dtype=torch.bfloat16, device=dev) if pool else None
+        K.bn_relu_pool(yb, scale, shift, a, pooled)
+        torch.cuda.synchronize()
+        # torch reference on the bf16-rounded conv output (+ bias, which BN must cancel)
+        yin = (nchw(yb) + cbias.view(1, -1, 1, 1)).requires_grad_(True)
+        bn = torch.nn.BatchNorm2d(Cc).to(dev)
+        with torch.no_grad():
+            bn.weight.copy_(gamma)
+            bn.bias.copy_(beta)
+        bn.train()
+        aref = F.relu(bn(yin))
+        ok &= report(f"bn+relu fwd B{B} {H}x{W} C{Cc}", nchw(a), aref, 1e-2)
+        ok &= report("   running_mean", rm, bn.running_mean, 1e-4)
+        ok &= report("   running_var", rv, bn.running_var, 1e-4)
+        ok &= (int(nbt.item()) == 1)
+        dA = torch.randn(B, Cc, H, W, generator=g).to(dev)
+        dAb = nhwc(dA)
+        if pool:
+            pref = F.max_pool2d(aref, 2)
+            ok &= report("   pooled", nchw(pooled), pref, 1e-2)
+            dP = torch.randn(B, Cc, H // 2, W // 2, generator=g).to(dev)
+            dPb = nhwc(dP)
+            # reference backward on bf16-rounded activations so the argmax agrees
+            a_round = aref.to(torch.bfloat16).float()
+            # straight-through: pool over rounded values, gradient routed to aref
+            pool_in = aref + (a_round - aref).detach()
+            total = (pool_in * nchw(dAb)).sum() + (F.max_pool2d(pool_in, 2) * nchw(dPb)).sum()
+            total.backward()
+        else:
+            dPb = None
+            (aref * nchw(dAb)).sum().backward()
+        dgamma, dbeta = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
+        dy = torch.empty(B, H, W, Cc, dtype=torch.bfloat16, device=dev)
+        K.bn_relu_pool_bwd(dAb, dPb, yb, scale, shift, mean, invstd, gamma, dgamma, dbeta, dy, ws)
+        torch.cuda.synchronize()
+        ok &= report("   bwd dy", nchw(dy), yin.grad, 2e-2)
+        ok &= report("   bwd dgamma", dgamma, bn.weight.grad, 1e-2)
+        ok &= report("   bwd dbeta", dbeta, bn.bias.grad, 1e-2)
+    return ok
+
+
+def ew_heads_loss(K):
+    dev = "cuda"
+    ok = True
+    ws = K.new_workspace(dev)
+    B, H, W = 2, 32, 32
+    P = B * H * W
+    g = torch.Generator().manual_seed(13)
+    a = torch.randn(B, H, W, 64, generator=g).to(dev).to(torch.bfloat16)
+    ws_ = [(torch.randn(1, 64, 1, 1, generator=g) * 0.2).to(dev) for _ in range(3)]
+    bs_ = [(torch.randn(1, generator=g) * 0.2).to(dev) for _ in range(3)]
+    logits = torch.empty(3, P, device=dev)
+    K.heads_fwd(a, ws_, bs_, logits)
+    torch.cuda.synchronize()
+    af = a.float().reshape(P, 64)
+    ref = torch.stack([af @ w.reshape(64) + b for w, b in zip(ws_, bs_)])
+    ok &= report("heads fwd", logits, ref, 1e-5)
+    # losses vs autograd of the reference formula (stable form)
+    tgt = (torch.rand(P, generator=g) < 0.4).float().to(dev)
+    lg = ref.clone().requires_grad_(True)
+    out, sel, aux = lg[0], lg[1], lg[2]
+    s = torch.sigmoid(sel)
+    cov = s.mean()
+    risk = (F.binary_cross_entropy_with_logits(out, tgt, reduction="none") * s).mean() / cov
+    pen = torch.clamp(0.8 - cov, min=0) ** 2
+    lamb = 2.0
+    sl = risk + lamb * pen
+    al = F.binary_cross_entropy_with_logits(aux, tgt)
+    (sl + al).backward()
+    sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    K.loss_sums(logits[0], logits[1], logits[2], tgt, sums, ws)
+    res = torch.empty(4, device=dev)
+    K.loss_finalize(sums, P, lamb, 0.8, res)
+    dl = torch.empty(3, P, device=dev)
+    K.loss_bwd(logits[0], logits[1], logits[2], tgt, sums, P, lamb, 0.8, None, None, dl[0], dl[1], dl[2])
+    torch.cuda.synchronize()
+    ok &= report("loss values", res, torch.stack([sl, cov, al, sl + al]).detach(), 1e-5)
+    ok &= report("loss grads", dl, lg.grad, 1e-4)
+    # heads bwd
+    dA = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=dev)
+    dws = [torch.empty_like(w) for w in ws_]
+    dbs = [torch.empty_like(b) for b in bs_]
+    K.heads_bwd(dl, a, ws_, dA, dws, dbs, ws)
+    torch.cuda.synchronize()
+    dref = sum(dl[h].reshape(P, 1) * ws_[h].reshape(1, 64) for h in range(3))
+    ok &= report("heads bwd dA", dA.float().reshape(P, 64), dref, 1e-2)
+    for h in range(3):
+        ok &= report(f"heads bwd dw{h}", dws[h].reshape(64), dl[h] @ af, 1e-4)
+        ok &= report(f"heads bwd db{h}", dbs[h], dl[h].sum().reshape(1), 1e-4)
+    # metric
+    counts = torch.zeros(6, dtype=torch.int64, device=dev)
+    K.metric_hist(logits[0], logits[1], tgt, 0.0, 0.0, True, counts)
+    torch.cuda.synchronize()
+    pred = (logits[0] >= 0).long()
+    selm = logits[1] >= 0
+    lab = tgt.long()
+    cm = torch.bincount((lab * 2 + pred)[selm], minlength=4)
+    exp = torch.cat([cm, selm.sum().reshape(1), torch.tensor([P], device=dev)])
+    good = bool((counts == exp).all().item())
+    print(f"  [{'OK ' if good else 'BAD'}] metric hist {counts.tolist()} vs {exp.tolist()}")
+    ok &= good
+    # adam
+    import ctypes as C
+    from selectivenet_for_semantic_segmentation_binary_b200 import _lib
+    ps = [torch.randn(n, generator=g).to(dev) for n in (1000, 7, 64 * 64 * 9)]
+    gs = [torch.randn(p.shape, generator=g).to(dev) for p in ps]
+    refp = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.Adam(refp, lr=1e-3)
+    ms = [torch.zeros_like(p) for p in ps]
+    vs = [torch.zeros_like(p) for p in ps]
+    tab = (_lib.AdamTensor * len(ps))()
+    for i, p in enumerate(ps):
+        tab[i].param, tab[i].grad, tab[i].exp_avg, tab[i].exp_avg_sq, tab[i].numel = (
+            p.data_ptr(), gs[i].data_ptr(), ms[i].data_ptr(), vs[i].data_ptr(), p.numel())
+    tab_dev = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(dev)
+    for step in (1, 2, 3):
+        for rp, gg in zip(refp, gs):
+            rp.grad = gg.clone()
+        opt.step()
+        K.adam_step(tab_dev, len(ps), max(p.numel() for p in ps), 1e-3, 0.9, 0.999, 1e-8, 0.0, step)
+    torch.cuda.synchronize()
+    for i in range(len(ps)):
+        ok &= report(f"adam tensor {i}", ps[i], refp[i].detach(), 1e-5)
+    return ok
+
+
+GROUPS = {"g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g2_wgrad": g2_wgrad,
+          "ew_bn": ew_bn, "ew_heads_loss": ew_heads_loss}
+
+
+def main():
+    if len(sys.argv) > 1:
+        from selectivenet_for_semantic_segmentation_binary_b200 import kernels as K
+        name = sys.argv[1]
+        print(f"== {name}", flush=True)
+        ok = GROUPS[name](K)
+        print(f"== {name}: {'PASS' if ok else 'FAIL'}", flush=True)
+        sys.exit(0 if ok else 1)
+    results = {}
+    for name in GROUPS:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=240)
+            results[name] = "PASS" if r.returncode == 0 else f"FAIL(rc={r.returncode})"
+        except subprocess.TimeoutExpired:
+            results[name] = "TIMEOUT"
+        print(f"-- {name}: {results[name]} ({time.time() - t0:.1f}s)", flush=True)
+    print("SUMMARY", results)
+
+
+if __name__ == "__main__":
+    main()

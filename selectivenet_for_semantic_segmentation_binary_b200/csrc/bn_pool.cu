@@ -1,0 +1,548 @@
+// HBM-bound kernels around the convolutions: layout packing, BatchNorm finalize,
+// BN+ReLU(+MaxPool) apply and its backward.  All activation traffic is 16-byte vectors of
+// 8 bf16 channels; reductions are two-stage and deterministic (per-block partial rows, then a
+// fixed-order sum) — no floating-point atomics anywhere.
+//
+// Reference semantics: /root/reference/model.py:9-15 (CBR_2D = Conv2d -> BatchNorm2d -> ReLU),
+// :31,35,39 (MaxPool2d(2), first-max tie break on backward).
+#include "common.h"
+#include "ptx.cuh"
+#include "../../include/sunet_b200.h"
+
+namespace sunet {
+
+static inline int ew_grid(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+struct alignas(16) bf16x8 {
+  uint32_t w[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& v, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = bf16lo(v.w[i]);
+    f[2 * i + 1] = bf16hi(v.w[i]);
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.w[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------ packing kernels
+__global__ void pack_input_im2col_kernel(const float* __restrict__ x, bf16x8* __restrict__ out, int B, int cin, int H,
+                                         int W) {
+  // one thread = one pixel x 8 output channels
+  const long long total = (long long)B * H * W * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float v = 0.f;
+      if (k < 9 * cin) {
+        const int tap = k / cin, ci = k - tap * cin;
+        const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = __ldg(x + (((long long)n * cin + ci) * H + sy) * W + sx);
+      }
+      f[j] = v;
+    }
+    out[i] = pack8(f);
+  }
+}
+
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                    __nv_bfloat16* __restrict__ wd, int co_n, int ci_n) {
+  const long long total = (long long)co_n * ci_n * 9;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the packed forward layout [co][tap][ci] so the bf16 writes are coalesced
+    const int ci = (int)(i % ci_n);
+    const int tap = (int)((i / ci_n) % 9);
+    const int co = (int)(i / ((long long)ci_n * 9));
+    const float v = w[((long long)co * ci_n + ci) * 9 + tap];
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    wf[i] = b;
+    if (wd) wd[((long long)ci * 9 + (8 - tap)) * co_n + co] = b;
+  }
+}
+
+__global__ void pack_conv1_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int co_n, int cin) {
+  const int total = co_n * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 63, co = i >> 6;
+    float v = 0.f;
+    if (k < 9 * cin) {
+      const int tap = k / cin, ci = k - tap * cin;
+      v = w[((long long)co * cin + ci) * 9 + tap];
+    }
+    wf[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void pack_convT_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                  __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
+                                  float* __restrict__ bias4, int ci_n, int co_n) {
+  const long long total = (long long)ci_n * co_n * 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes wf [(tap*co_n + co)][ci]
+    const int ci = (int)(i % ci_n);
+    const int row = (int)(i / ci_n);
+    const int co = row % co_n, tap = row / co_n;
+    const __nv_bfloat16 b = __float2bfloat16_rn(w[((long long)ci * co_n + co) * 4 + tap]);
+    wf[i] = b;
+    if (wd) wd[(long long)ci * (4 * co_n) + row] = b;
+    if (ci == 0 && bias4) bias4[row] = bias ? bias[co] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ BN finalize
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ conv_bias, float* running_mean, float* running_var,
+                                   long long* nbt, float momentum, float eps, float* scale, float* shift, float* mean,
+                                   float* invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s += (double)stats[((size_t)r * C + c) * 2];
+    q += (double)stats[((size_t)r * C + c) * 2 + 1];
+  }
+  const double m = s / count;
+  double var = q / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float istd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * istd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  mean[c] = (float)m;
+  invstd[c] = istd;
+  if (running_mean) {
+    const float b = conv_bias ? conv_bias[c] : 0.f;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)m + b);
+    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+__global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* conv_bias,
+                                      const float* rm, const float* rv, float eps, float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+}
+
+__global__ void colsum_finalize_kernel(const float* stats, int rows, int n_total, int col_offset, int C, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int r = 0; r < rows; ++r) s += (double)stats[((size_t)r * n_total + col_offset + c) * 2];
+  out[c] = (float)s;
+}
+
+// ------------------------------------------------------------------ BN + ReLU (+ pool) forward
+template <bool POOL>
+__global__ void __launch_bounds__(256)
+bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
+                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int as,
+                    __nv_bfloat16* __restrict__ pooled, int ps, int B, int H, int W, int C) {
+  const int G = C >> 3;
+  // POOL: one item = one 2x2 window x 8 channels; else one pixel x 8 channels
+  const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
+  const long long total = (long long)B * HW * WW * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const long long wpix = i / G;
+    const int wx = (int)(wpix % WW);
+    const int wy = (int)((wpix / WW) % HW);
+    const int n = (int)(wpix / ((long long)WW * HW));
+    float sc[8], sh[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
+    if (POOL) {
+      float mx[8];
+      bf16x8 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long pix = ((long long)n * H + (wy * 2 + (k >> 1))) * W + (wx * 2 + (k & 1));
+        v[k] = *reinterpret_cast<const bf16x8*>(y + pix * ys + g * 8);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long pix = ((long long)n * H + (wy * 2 + (k >> 1))) * W + (wx * 2 + (k & 1));
+        float f[8];
+        unpack8(v[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+          mx[j] = (k == 0) ? f[j] : fmaxf(mx[j], f[j]);
+        }
+        *reinterpret_cast<bf16x8*>(a + pix * as + g * 8) = pack8(f);
+      }
+      const long long ppix = ((long long)n * HW + wy) * WW + wx;
+      *reinterpret_cast<bf16x8*>(pooled + ppix * ps + g * 8) = pack8(mx);
+    } else {
+      const long long pix = wpix;
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(y + pix * ys + g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+      *reinterpret_cast<bf16x8*>(a + pix * as + g * 8) = pack8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ BN + ReLU (+ pool) backward
+// Shared gradient gather: g[k][j] for the 4 (POOL) or 1 pixels of this item, ReLU mask applied,
+// pooled gradient routed to the first maximum (row-major window order, computed on the same
+// bf16-rounded activations the forward pass pooled).
+template <bool POOL>
+struct BwdItem {
+  static constexpr int NP = POOL ? 4 : 1;
+  float g[NP][8];
+  float yv[NP][8];
+  long long pix[NP];
+};
+
+template <bool POOL>
+__device__ __forceinline__ void bwd_gather(BwdItem<POOL>& it, long long i, int G, const __nv_bfloat16* __restrict__ dA,
+                                           int das, const __nv_bfloat16* __restrict__ dP, int dps,
+                                           const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
+                                           const float* __restrict__ shift, int H, int W, int& g_out) {
+  constexpr int NP = BwdItem<POOL>::NP;
+  const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
+  const int g = (int)(i % G);
+  g_out = g;
+  const long long wpix = i / G;
+  const int wx = (int)(wpix % WW);
+  const int wy = (int)((wpix / WW) % HW);
+  const int n = (int)(wpix / ((long long)WW * HW));
+  float sc[8], sh[8];
+  *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
+  *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
+  *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
+  *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
+  float act[NP][8];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    it.pix[k] = POOL ? (((long long)n * H + (wy * 2 + (k >> 1))) * W + (wx * 2 + (k & 1))) : wpix;
+    unpack8(*reinterpret_cast<const bf16x8*>(y + it.pix[k] * ys + g * 8), it.yv[k]);
+    if (dA) {
+      unpack8(*reinterpret_cast<const bf16x8*>(dA + it.pix[k] * das + g * 8), it.g[k]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) it.g[k][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) act[k][j] = round_bf16(fmaxf(fmaf(it.yv[k][j], sc[j], sh[j]), 0.f));
+  }
+  if (POOL) {
+    float dp[8];
+    const long long ppix = ((long long)n * HW + wy) * WW + wx;
+    unpack8(*reinterpret_cast<const bf16x8*>(dP + ppix * dps + g * 8), dp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float bv = act[0][j];
+#pragma unroll
+      for (int k = 1; k < NP; ++k)
+        if (act[k][j] > bv) {
+          bv = act[k][j];
+          best = k;
+        }
+#pragma unroll
+      for (int k = 0; k < NP; ++k)
+        if (k == best) it.g[k][j] += dp[j];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NP; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(act[k][j] > 0.f)) it.g[k][j] = 0.f;
+}
+
+// stage 1: per-block partial (sum g, sum g*xhat) per channel -> partials[block][C][2]
+template <bool POOL>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ dP, int dps,
+                     const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, float* __restrict__ partials, int B, int H, int W, int C) {
+  __shared__ float red[256][17];
+  const int G = C >> 3;
+  const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
+  const long long total = (long long)B * HW * WW * G;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  // blockDim (256) is a multiple of G (8..64), and the grid stride too, so a thread keeps its
+  // channel group for the whole loop.
+  const int g = threadIdx.x % G;
+  float mu[8], is[8];
+  *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + g * 8));
+  *reinterpret_cast<float4*>(mu + 4) = __ldg(reinterpret_cast<const float4*>(mean + g * 8 + 4));
+  *reinterpret_cast<float4*>(is) = __ldg(reinterpret_cast<const float4*>(invstd + g * 8));
+  *reinterpret_cast<float4*>(is + 4) = __ldg(reinterpret_cast<const float4*>(invstd + g * 8 + 4));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    BwdItem<POOL> it;
+    int gg;
+    bwd_gather<POOL>(it, i, G, dA, das, dP, dps, y, ys, scale, shift, H, W, gg);
+#pragma unroll
+    for (int k = 0; k < BwdItem<POOL>::NP; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += it.g[k][j];
+        acc[8 + j] = fmaf(it.g[k][j], (it.yv[k][j] - mu[j]) * is[j], acc[8 + j]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  const int reps = 256 / G;
+  for (int o = threadIdx.x; o < G * 16; o += 256) {
+    const int og = o >> 4, oj = o & 15;
+    float s = 0.f;
+    for (int r = 0; r < reps; ++r) s += red[r * G + og][oj];
+    const int c = og * 8 + (oj & 7);
+    partials[((size_t)blockIdx.x * C + c) * 2 + (oj >> 3)] = s;
+  }
+}
+
+// stage 2: dgamma, dbeta and the three coefficients of dy = kg*g + k1*y + k0
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int C, double count,
+                                       const float* __restrict__ scale, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sg = 0.0, sgx = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    sg += (double)partials[((size_t)b * C + c) * 2];
+    sgx += (double)partials[((size_t)b * C + c) * 2 + 1];
+  }
+  if (dbeta) dbeta[c] = (float)sg;
+  if (dgamma) dgamma[c] = (float)sgx;
+  const double sc = scale[c];
+  const double k1 = -sc * (double)invstd[c] * sgx / count;
+  const double k0 = -sc * sg / count - k1 * (double)mean[c];
+  coef[c] = (float)sc;
+  coef[C + c] = (float)k1;
+  coef[2 * C + c] = (float)k0;
+}
+
+// stage 3: dy
+template <bool POOL>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ dP, int dps,
+                    const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
+                    int dys, int B, int H, int W, int C) {
+  const int G = C >> 3;
+  const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
+  const long long total = (long long)B * HW * WW * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    BwdItem<POOL> it;
+    int g;
+    bwd_gather<POOL>(it, i, G, dA, das, dP, dps, y, ys, scale, shift, H, W, g);
+    float kg[8], k1[8], k0[8];
+    *reinterpret_cast<float4*>(kg) = __ldg(reinterpret_cast<const float4*>(coef + g * 8));
+    *reinterpret_cast<float4*>(kg + 4) = __ldg(reinterpret_cast<const float4*>(coef + g * 8 + 4));
+    *reinterpret_cast<float4*>(k1) = __ldg(reinterpret_cast<const float4*>(coef + C + g * 8));
+    *reinterpret_cast<float4*>(k1 + 4) = __ldg(reinterpret_cast<const float4*>(coef + C + g * 8 + 4));
+    *reinterpret_cast<float4*>(k0) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + g * 8));
+    *reinterpret_cast<float4*>(k0 + 4) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + g * 8 + 4));
+#pragma unroll
+    for (int k = 0; k < BwdItem<POOL>::NP; ++k) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(kg[j], it.g[k][j], fmaf(k1[j], it.yv[k][j], k0[j]));
+      *reinterpret_cast<bf16x8*>(dy + it.pix[k] * dys + g * 8) = pack8(o);
+    }
+  }
+}
+
+}  // namespace sunet
+
+using namespace sunet;
+
+#define STREAM reinterpret_cast<cudaStream_t>(stream_)
+
+extern "C" int sunet_pack_input_im2col(const float* x, void* out, int batch, int cin, int height, int width,
+                                       sunet_stream_t stream_) {
+  if (!x || !out || batch <= 0 || cin <= 0 || cin * 9 > 64 || height <= 0 || width <= 0)
+    return set_error(SUNET_ERR_INVALID, "pack_input_im2col: bad arguments (cin=%d)", cin);
+  const long long total = (long long)batch * height * width * 8;
+  pack_input_im2col_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(x, reinterpret_cast<bf16x8*>(out), batch, cin,
+                                                                     height, width);
+  return check_launch("pack_input_im2col");
+}
+
+extern "C" int sunet_pack_conv3x3_weights(const float* w, void* wf, void* wd, int cout, int cin,
+                                          sunet_stream_t stream_) {
+  if (!w || !wf || cout <= 0 || cin <= 0) return set_error(SUNET_ERR_INVALID, "pack_conv3x3_weights: bad arguments");
+  const long long total = (long long)cout * cin * 9;
+  pack_conv3x3_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(w, reinterpret_cast<__nv_bfloat16*>(wf),
+                                                                reinterpret_cast<__nv_bfloat16*>(wd), cout, cin);
+  return check_launch("pack_conv3x3_weights");
+}
+
+extern "C" int sunet_pack_conv1_weights(const float* w, void* wf, int cout, int cin, sunet_stream_t stream_) {
+  if (!w || !wf || cout <= 0 || cin <= 0 || cin * 9 > 64)
+    return set_error(SUNET_ERR_INVALID, "pack_conv1_weights: bad arguments");
+  pack_conv1_kernel<<<ew_grid(cout * 64, 256), 256, 0, STREAM>>>(w, reinterpret_cast<__nv_bfloat16*>(wf), cout, cin);
+  return check_launch("pack_conv1_weights");
+}
+
+extern "C" int sunet_pack_convT_weights(const float* w, const float* bias, void* wf, void* wd, float* bias4, int cin,
+                                        int cout, sunet_stream_t stream_) {
+  if (!w || !wf || cin <= 0 || cout <= 0) return set_error(SUNET_ERR_INVALID, "pack_convT_weights: bad arguments");
+  const long long total = (long long)cin * cout * 4;
+  pack_convT_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(wf),
+                                                              reinterpret_cast<__nv_bfloat16*>(wd), bias4, cin, cout);
+  return check_launch("pack_convT_weights");
+}
+
+extern "C" int sunet_bn_finalize(const float* stats, int rows, int channels, long long count, const float* gamma,
+                                 const float* beta, const float* conv_bias, float* running_mean, float* running_var,
+                                 long long* num_batches_tracked, float momentum, float eps, float* scale, float* shift,
+                                 float* mean, float* invstd, sunet_stream_t stream_) {
+  if (!stats || rows <= 0 || channels <= 0 || count <= 0 || !gamma || !beta || !scale || !shift || !mean || !invstd)
+    return set_error(SUNET_ERR_INVALID, "bn_finalize: bad arguments");
+  if ((running_mean == nullptr) != (running_var == nullptr))
+    return set_error(SUNET_ERR_INVALID, "bn_finalize: running_mean/var must both be given or both NULL");
+  bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(stats, rows, channels, (double)count, gamma, beta,
+                                                                  conv_bias, running_mean, running_var,
+                                                                  num_batches_tracked, momentum, eps, scale, shift,
+                                                                  mean, invstd);
+  return check_launch("bn_finalize");
+}
+
+extern "C" int sunet_bn_eval_affine(const float* gamma, const float* beta, const float* conv_bias,
+                                    const float* running_mean, const float* running_var, float eps, float* scale,
+                                    float* shift, int channels, sunet_stream_t stream_) {
+  if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || channels <= 0)
+    return set_error(SUNET_ERR_INVALID, "bn_eval_affine: bad arguments");
+  bn_eval_affine_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(gamma, beta, conv_bias, running_mean, running_var,
+                                                                     eps, scale, shift, channels);
+  return check_launch("bn_eval_affine");
+}
+
+extern "C" int sunet_colsum_finalize(const float* stats, int rows, int n_total, int col_offset, int channels,
+                                     float* out, sunet_stream_t stream_) {
+  if (!stats || !out || rows <= 0 || channels <= 0 || col_offset < 0 || col_offset + channels > n_total)
+    return set_error(SUNET_ERR_INVALID, "colsum_finalize: bad arguments");
+  colsum_finalize_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(stats, rows, n_total, col_offset, channels, out);
+  return check_launch("colsum_finalize");
+}
+
+static int check_act(const char* what, int stride, int channels) {
+  if (channels <= 0 || channels % 8 || stride < channels || stride % 8)
+    return set_error(SUNET_ERR_INVALID, "%s: channels %d / pixel stride %d must be multiples of 8, stride >= channels",
+                     what, channels, stride);
+  return SUNET_OK;
+}
+
+extern "C" int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
+                                  int a_pix_stride, void* pooled, int pooled_pix_stride, int batch, int height,
+                                  int width, int channels, sunet_stream_t stream_) {
+  if (!y || !scale || !shift || !a || batch <= 0 || height <= 0 || width <= 0)
+    return set_error(SUNET_ERR_INVALID, "bn_relu_pool: bad arguments");
+  int e;
+  if ((e = check_act("bn_relu_pool(y)", y_pix_stride, channels))) return e;
+  if ((e = check_act("bn_relu_pool(a)", a_pix_stride, channels))) return e;
+  const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(y);
+  __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(a);
+  if (pooled) {
+    if ((height | width) & 1) return set_error(SUNET_ERR_INVALID, "bn_relu_pool: odd size %d x %d", height, width);
+    if ((e = check_act("bn_relu_pool(pooled)", pooled_pix_stride, channels))) return e;
+    const long long total = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
+    bn_relu_pool_kernel<true><<<ew_grid(total, 256), 256, 0, STREAM>>>(
+        yp, y_pix_stride, scale, shift, ap, a_pix_stride, reinterpret_cast<__nv_bfloat16*>(pooled), pooled_pix_stride,
+        batch, height, width, channels);
+  } else {
+    const long long total = (long long)batch * height * width * (channels / 8);
+    bn_relu_pool_kernel<false><<<ew_grid(total, 256), 256, 0, STREAM>>>(yp, y_pix_stride, scale, shift, ap,
+                                                                         a_pix_stride, nullptr, 0, batch, height,
+                                                                         width, channels);
+  }
+  return check_launch("bn_relu_pool");
+}
+
+extern "C" int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const void* dPool, int dPool_pix_stride,
+                                      const void* y, int y_pix_stride, const float* scale, const float* shift,
+                                      const float* mean, const float* invstd, const float* gamma, float* dgamma,
+                                      float* dbeta, void* dy, int dy_pix_stride, int batch, int height, int width,
+                                      int channels, void* workspace, size_t workspace_bytes, sunet_stream_t stream_) {
+  (void)gamma;
+  if ((!dA && !dPool) || !y || !scale || !shift || !mean || !invstd || !dy || !workspace)
+    return set_error(SUNET_ERR_INVALID, "bn_relu_pool_bwd: bad arguments");
+  int e;
+  if ((e = check_act("bn_relu_pool_bwd(y)", y_pix_stride, channels))) return e;
+  if ((e = check_act("bn_relu_pool_bwd(dy)", dy_pix_stride, channels))) return e;
+  if (dA && (e = check_act("bn_relu_pool_bwd(dA)", dA_pix_stride, channels))) return e;
+  if (dPool && (e = check_act("bn_relu_pool_bwd(dPool)", dPool_pix_stride, channels))) return e;
+  const int G = channels / 8;
+  if (256 % G) return set_error(SUNET_ERR_INVALID, "bn_relu_pool_bwd: channels %d unsupported", channels);
+  const bool pool = dPool != nullptr;
+  if (pool && ((height | width) & 1)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool_bwd: odd size");
+  const long long total = (long long)batch * (pool ? height / 2 : height) * (pool ? width / 2 : width) * G;
+  int blocks = ew_grid(total, 256);
+  const int max_blocks = num_sms() * 2;
+  if (blocks > max_blocks) blocks = max_blocks;
+  const size_t need = ((size_t)blocks * channels * 2 + 3 * (size_t)channels) * sizeof(float);
+  if (workspace_bytes < need)
+    return set_error(SUNET_ERR_WORKSPACE, "bn_relu_pool_bwd: workspace %zu < %zu", workspace_bytes, need);
+  float* partials = reinterpret_cast<float*>(workspace);
+  float* coef = partials + (size_t)blocks * channels * 2;
+  const __nv_bfloat16* dAp = reinterpret_cast<const __nv_bfloat16*>(dA);
+  const __nv_bfloat16* dPp = reinterpret_cast<const __nv_bfloat16*>(dPool);
+  const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(y);
+  __nv_bfloat16* dyp = reinterpret_cast<__nv_bfloat16*>(dy);
+  const double count = (double)batch * height * width;
+  if (pool)
+    bn_bwd_reduce_kernel<true><<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, dPp, dPool_pix_stride, yp,
+                                                            y_pix_stride, scale, shift, mean, invstd, partials, batch,
+                                                            height, width, channels);
+  else
+    bn_bwd_reduce_kernel<false><<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, nullptr, 0, yp, y_pix_stride, scale,
+                                                             shift, mean, invstd, partials, batch, height, width,
+                                                             channels);
+  if ((e = check_launch("bn_bwd_reduce"))) return e;
+  bn_bwd_finalize_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(partials, blocks, channels, count, scale, mean,
+                                                                      invstd, dgamma, dbeta, coef);
+  if ((e = check_launch("bn_bwd_finalize"))) return e;
+  const int ablocks = ew_grid(total, 256);
+  if (pool)
+    bn_bwd_apply_kernel<true><<<ablocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, dPp, dPool_pix_stride, yp, y_pix_stride,
+                                                            scale, shift, coef, dyp, dy_pix_stride, batch, height,
+                                                            width, channels);
+  else
+    bn_bwd_apply_kernel<false><<<ablocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, nullptr, 0, yp, y_pix_stride, scale,
+                                                             shift, coef, dyp, dy_pix_stride, batch, height, width,
+                                                             channels);
+  return check_launch("bn_bwd_apply");
+}

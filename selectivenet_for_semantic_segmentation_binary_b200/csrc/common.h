@@ -1,0 +1,35 @@
+// Host-side helpers shared by every translation unit of libsunet_b200.so:
+// error reporting (thread-local last-error string, integer return codes; nothing
+// here throws or exits) and TMA tensor-map construction through the driver entry
+// point (no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sunet {
+
+enum {
+  SUNET_OK = 0,
+  SUNET_ERR_INVALID = 1,   // bad argument / unsupported shape
+  SUNET_ERR_CUDA = 2,      // a CUDA runtime / driver call failed
+  SUNET_ERR_WORKSPACE = 3  // caller-provided workspace too small
+};
+
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+int check_cuda(cudaError_t e, const char* what);
+int check_launch(const char* what);
+
+// Rank-5 bf16 tensor map with 128-byte swizzle.  dims/strides are in elements /
+// bytes, innermost first; strides[0] is implied (2 bytes).  box[0] must be 64
+// (128 bytes = the swizzle span).
+int make_tmap_bf16_5d(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                      const uint32_t box[5]);
+// Rank-2 K-major bf16 matrix [rows][cols], box = 64 cols x box_rows rows.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                      uint32_t box_rows);
+
+int num_sms();
+
+}  // namespace sunet

@@ -1,0 +1,456 @@
+// G1 — the tensor-core implicit GEMM behind every "pixels x channels" contraction of
+// SUNet_B: conv3x3 forward and dgrad, ConvTranspose2d(k2,s2) forward and dgrad.
+//
+//   D[pixel, n] = sum_{tap, c} A_tap[pixel, c] * Wp[n, tap*C + c]      (+ bias[n])
+//
+// * A is never materialised: for every (tap, 64-channel chunk) the producer warp issues one
+//   TMA box load straight out of the NHWC bf16 activation tensor.  The 3x3 halo is a
+//   coordinate offset, zero padding is TMA out-of-bounds fill, the skip concat is a second
+//   tensor map (the decoder conv reads "up" and "skip" from their own buffers), and the 2x2
+//   gather of the transposed-conv dgrad is a rank-5 view of the high-resolution tensor.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16; bf16 x bf16 -> fp32 in TMEM).
+//   Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// * Epilogue warps: tcgen05.ld -> (+bias) -> bf16 -> 128B-swizzled staging tile -> TMA store
+//   (NHWC, or the 2x2 pixel-shuffle scatter of the transposed conv), and the per-channel
+//   sum / sum-of-squares BatchNorm needs, accumulated per CTA and written as one
+//   deterministic partial row per CTA (no atomics).
+//
+// Replaces: nn.Conv2d / nn.ConvTranspose2d forward+backward-data as dispatched by
+// /root/reference/model.py:11,44-45,51-52,57-58 (cuDNN in the reference).
+#include "common.h"
+#include "ptx.cuh"
+#include "../../include/sunet_b200.h"
+
+namespace sunet {
+
+struct ConvGemmParams {
+  int gs_load;      // 0: conv-type coords (c, x+dx, y+dy, n, 0); 1: gather coords (c, b, x, a, n*H+y)
+  int taps;         // 1, 4 or 9
+  int cpt0, cpt1;   // 64-channel chunks per tap coming from source 0 / source 1
+  int tw, th, nb;   // tile = nb images x th rows x tw pixels (= 128 GEMM rows)
+  int tiles_x, tiles_y;
+  int H;            // rows per image of the M grid
+  int m_tiles, n_tiles;
+  int gs_store;     // 0: NHWC store; 1: 2x2 scatter store
+  int out_cpt;      // scatter store: 64-channel chunks per (a,b) tap
+  const float* bias;
+  float* stats;     // [gridDim.x / n_tiles][n_total][2] or nullptr
+  int n_total;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 bf16
+  static constexpr int B_BYTES = BN * 128;       // BN rows x 64 bf16
+  static constexpr int STG_BYTES = 128 * 128;    // one 64-column output chunk
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 2 * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+constexpr int kThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
+                 const ConvGemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + C::STAGES * C::A_BYTES;
+  uint8_t* sStg = sB + C::STAGES * C::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * C::STG_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;     // [2]
+  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapD);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Static persistent schedule: CTA b owns N tile (b % n_tiles) and every
+  // (gridDim.x / n_tiles)-th M tile, so its BN-statistics accumulators stay on one
+  // channel range for the whole kernel.
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_first = blockIdx.x / p.n_tiles;
+  const int m_step = gridDim.x / p.n_tiles;
+  const int cpt = p.cpt0 + p.cpt1;
+  const int ksteps = p.taps * cpt;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
+        const int xt = mt % p.tiles_x;
+        const int yt = (mt / p.tiles_x) % p.tiles_y;
+        const int nt = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = xt * p.tw, y0 = yt * p.th, n0 = nt * p.nb;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int tap = ks / cpt;
+          int cc = ks - tap * cpt;
+          const CUtensorMap* mapA = &mapA0;
+          if (cc >= p.cpt0) {
+            cc -= p.cpt0;
+            mapA = &mapA1;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
+          if (p.gs_load) {
+            tma_load_5d(sA + stage * C::A_BYTES, mapA, &full_bar[stage], cc * 64, tap & 1, x0, tap >> 1,
+                        n0 * p.H + y0);
+          } else {
+            int dx = 0, dy = 0;
+            if (p.taps == 9) {
+              dy = tap / 3 - 1;
+              dx = tap - (tap / 3) * 3 - 1;
+            }
+            tma_load_5d(sA + stage * C::A_BYTES, mapA, &full_bar[stage], cc * 64, x0 + dx, y0 + dy, n0, 0);
+          }
+          tma_load_2d(sB + stage * C::B_BYTES, &mapB, &full_bar[stage], ks * 64, n_tile * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int mt = m_first; mt < p.m_tiles; mt += m_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * C::A_BYTES), 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * C::B_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // +32 bytes along K inside the 128B swizzle span = +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue (128 threads)
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;      // GEMM row (pixel) inside the tile
+    const bool issuer = (threadIdx.x == 64);
+    constexpr int NCHUNK = BN / 64;
+    float ssum[NCHUNK][2], ssq[NCHUNK][2];
+#pragma unroll
+    for (int q = 0; q < NCHUNK; ++q) ssum[q][0] = ssum[q][1] = ssq[q][0] = ssq[q][1] = 0.f;
+
+    int it = 0;
+    uint32_t chunk_ctr = 0;
+    for (int mt = m_first; mt < p.m_tiles; mt += m_step, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int xt = mt % p.tiles_x;
+      const int yt = (mt / p.tiles_x) % p.tiles_y;
+      const int nt = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = xt * p.tw, y0 = yt * p.th, n0 = nt * p.nb;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int q = 0; q < NCHUNK; ++q, ++chunk_ctr) {
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + q * 64;
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_32x32b_x32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        const int ncol0 = n_tile * BN + q * 64;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + ncol0 + j));
+        }
+        uint8_t* stg = sStg + (chunk_ctr & 1) * C::STG_BYTES;
+        // 128B-swizzled staging row (matches the TMA store map): 16B chunk j lands at j ^ (row & 7)
+        uint4* rowp = reinterpret_cast<uint4*>(stg + row * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+          w.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+          w.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+          w.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+          rowp[j ^ (row & 7)] = w;
+        }
+        fence_proxy_async_smem();
+        if (issuer) tma_store_wait_read<0>();  // previous chunk's store no longer reads the other buffer
+        named_bar_sync(1, 128);
+        if (issuer) {
+          if (p.gs_store) {
+            const int oc = (ncol0 >> 6);
+            const int tap = oc / p.out_cpt;
+            const int c0 = (oc - tap * p.out_cpt) * 64;
+            tma_store_5d(&mapD, stg, c0, tap & 1, x0, tap >> 1, n0 * p.H + y0);
+          } else {
+            tma_store_5d(&mapD, stg, ncol0, x0, y0, n0, 0);
+          }
+          tma_store_commit();
+        }
+        if (p.stats != nullptr) {
+          // Column statistics over this warp's own 32 rows (rows it wrote itself -> the
+          // named barrier above already ordered the writes).  Lane = channel pair.
+          const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int rr = quad * 32 + r;
+            const uint32_t w = words[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+            const float a = bf16lo(w), b = bf16hi(w);
+            s0 += a;
+            s1 += b;
+            q0 = fmaf(a, a, q0);
+            q1 = fmaf(b, b, q1);
+          }
+          ssum[q][0] += s0;
+          ssum[q][1] += s1;
+          ssq[q][0] += q0;
+          ssq[q][1] += q1;
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    if (issuer) tma_store_wait_all<0>();
+    if (p.stats != nullptr) {
+      // combine the 4 row-quadrants through (now idle) staging memory; one partial row per CTA
+      named_bar_sync(1, 128);
+      float* red = reinterpret_cast<float*>(sStg);  // [4][BN][2]
+#pragma unroll
+      for (int q = 0; q < NCHUNK; ++q) {
+        const int c = q * 64 + lane * 2;
+        red[(quad * BN + c) * 2 + 0] = ssum[q][0];
+        red[(quad * BN + c) * 2 + 1] = ssq[q][0];
+        red[(quad * BN + c + 1) * 2 + 0] = ssum[q][1];
+        red[(quad * BN + c + 1) * 2 + 1] = ssq[q][1];
+      }
+      named_bar_sync(1, 128);
+      const int t = threadIdx.x - 64;
+      float* dst = p.stats + (static_cast<size_t>(m_first) * p.n_total + n_tile * BN) * 2;
+      for (int i = t; i < BN * 2; i += 128) {
+        dst[i] = red[i] + red[BN * 2 + i] + red[2 * BN * 2 + i] + red[3 * BN * 2 + i];
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+
+static int pow2_floor_div(int v, int cap) {
+  // largest power of two that divides v, capped at cap
+  int t = 1;
+  while (t < cap && (v % (t * 2)) == 0) t *= 2;
+  return t;
+}
+
+struct TileGeom {
+  int tw, th, nb, tiles_x, tiles_y, tiles_n, m_tiles;
+};
+static TileGeom tile_geom(int B, int H, int W, int rows_per_tile) {
+  TileGeom g;
+  g.tw = pow2_floor_div(W, rows_per_tile);
+  g.th = pow2_floor_div(H, rows_per_tile / g.tw);
+  g.nb = rows_per_tile / (g.tw * g.th);
+  if (g.nb > 1 && g.th != H) {
+    // images may only be stacked when a tile covers whole images
+    g.nb = 1;
+  }
+  g.tiles_x = W / g.tw;
+  g.tiles_y = H / g.th;
+  g.tiles_n = (B + g.nb - 1) / g.nb;
+  g.m_tiles = g.tiles_x * g.tiles_y * g.tiles_n;
+  return g;
+}
+
+static int make_act_map(CUtensorMap* m, const void* base, int gs, int C, int S, int B, int H, int W, const TileGeom& g,
+                        int rows_per_tile) {
+  // gs == 0: NHWC tensor [B][H][W][S] viewed as (C, W, H, B, 1), box (64, tw, th, nb, 1)
+  // gs == 1: high-res tensor [B][2H][2W][S] viewed as (C, 2, W, 2, B*H), box (64, 1, tw, 1, th*nb)
+  uint64_t dims[5], str[4];
+  uint32_t box[5];
+  const uint64_t e = 2;
+  if (!gs) {
+    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = B; dims[4] = 1;
+    str[0] = (uint64_t)S * e;
+    str[1] = (uint64_t)W * S * e;
+    str[2] = (uint64_t)H * W * S * e;
+    str[3] = (uint64_t)B * H * W * S * e;
+    box[0] = 64; box[1] = g.tw; box[2] = g.th; box[3] = g.nb; box[4] = 1;
+  } else {
+    dims[0] = C; dims[1] = 2; dims[2] = W; dims[3] = 2; dims[4] = (uint64_t)B * H;
+    str[0] = (uint64_t)S * e;
+    str[1] = (uint64_t)2 * S * e;
+    str[2] = (uint64_t)2 * W * S * e;
+    str[3] = (uint64_t)4 * W * S * e;
+    box[0] = 64; box[1] = 1; box[2] = g.tw; box[3] = 1; box[4] = g.th * g.nb;
+  }
+  (void)rows_per_tile;
+  return make_tmap_bf16_5d(m, base, dims, str, box);
+}
+
+static int pick_bn(int n_total) {
+  if (n_total % 256 == 0) return 256;
+  if (n_total % 128 == 0) return 128;
+  return 64;
+}
+
+static int conv_gemm_grid(int m_tiles, int n_tiles) {
+  int slots = num_sms() / n_tiles;
+  if (slots < 1) slots = 1;
+  if (slots > m_tiles) slots = m_tiles;
+  return slots * n_tiles;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d,
+                  const ConvGemmParams& p, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int e = check_cuda(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg<BN>::SMEM),
+                       "cudaFuncSetAttribute(conv_gemm)");
+    if (e) return e;
+    attr_set = true;
+  }
+  conv_gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::SMEM, stream>>>(a0, a1, b, d, p);
+  return check_launch("conv_gemm_kernel");
+}
+
+}  // namespace sunet
+
+using namespace sunet;
+
+extern "C" int sunet_conv_gemm_stat_rows(int batch, int height, int width, int n_total) {
+  if (batch <= 0 || height <= 0 || width <= 0 || n_total <= 0 || n_total % 64) return -1;
+  TileGeom g = tile_geom(batch, height, width, 128);
+  const int bn = pick_bn(n_total);
+  const int n_tiles = n_total / bn;
+  return conv_gemm_grid(g.m_tiles, n_tiles) / n_tiles;
+}
+
+extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a) return set_error(SUNET_ERR_INVALID, "conv_gemm: null args");
+  const int B = a->batch, H = a->height, W = a->width;
+  if (B <= 0 || H <= 0 || W <= 0) return set_error(SUNET_ERR_INVALID, "conv_gemm: bad grid %d x %d x %d", B, H, W);
+  if (!a->src0 || !a->weights || !a->dst) return set_error(SUNET_ERR_INVALID, "conv_gemm: null tensor");
+  if (a->src0_channels <= 0 || a->src0_channels % 64 || a->src1_channels % 64 || a->n_total <= 0 || a->n_total % 64)
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: channel counts must be multiples of 64 (got %d,%d -> %d)",
+                     a->src0_channels, a->src1_channels, a->n_total);
+  if (a->src1 == nullptr && a->src1_channels != 0)
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: src1_channels without src1");
+  int taps;
+  switch (a->a_mode) {
+    case SUNET_A_CONV3X3: taps = 9; break;
+    case SUNET_A_PLAIN: taps = 1; break;
+    case SUNET_A_GATHER2X2: taps = 4; break;
+    default: return set_error(SUNET_ERR_INVALID, "conv_gemm: bad a_mode %d", a->a_mode);
+  }
+  if (a->a_mode == SUNET_A_GATHER2X2 && a->src1)
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: gather mode takes one source");
+  const int ctot = a->src0_channels + (a->src1 ? a->src1_channels : 0);
+  if (a->k_total != taps * ctot)
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: k_total %d != taps %d x channels %d", a->k_total, taps, ctot);
+  if (a->src0_pix_stride < a->src0_channels || (a->src0_pix_stride % 8) ||
+      (a->src1 && (a->src1_pix_stride < a->src1_channels || (a->src1_pix_stride % 8))) || (a->dst_pix_stride % 8))
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: pixel strides must be >= channels and multiples of 8");
+  if (a->d_mode == SUNET_D_SCATTER2X2 && (a->n_total % 4 || (a->n_total / 4) % 64))
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: scatter store needs n_total = 4 x (multiple of 64)");
+
+  TileGeom g = tile_geom(B, H, W, 128);
+  if (g.tw * g.th * g.nb != 128)
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: cannot tile %d x %d x %d into 128-pixel tiles", B, H, W);
+  const int bn = pick_bn(a->n_total);
+  const int n_tiles = a->n_total / bn;
+
+  CUtensorMap mA0, mA1, mB, mD;
+  int e;
+  const int gs_load = (a->a_mode == SUNET_A_GATHER2X2);
+  if ((e = make_act_map(&mA0, a->src0, gs_load, a->src0_channels, a->src0_pix_stride, B, H, W, g, 128))) return e;
+  if (a->src1) {
+    if ((e = make_act_map(&mA1, a->src1, 0, a->src1_channels, a->src1_pix_stride, B, H, W, g, 128))) return e;
+  } else {
+    mA1 = mA0;
+  }
+  if ((e = make_tmap_bf16_2d(&mB, a->weights, (uint64_t)a->k_total, (uint64_t)a->n_total, (uint64_t)a->k_total * 2,
+                             (uint32_t)bn)))
+    return e;
+  const int gs_store = (a->d_mode == SUNET_D_SCATTER2X2);
+  const int dst_c = gs_store ? a->n_total / 4 : a->n_total;
+  if (a->dst_pix_stride < dst_c) return set_error(SUNET_ERR_INVALID, "conv_gemm: dst_pix_stride < channels");
+  if ((e = make_act_map(&mD, a->dst, gs_store, dst_c, a->dst_pix_stride, B, H, W, g, 128))) return e;
+
+  ConvGemmParams p;
+  p.gs_load = gs_load;
+  p.taps = taps;
+  p.cpt0 = a->src0_channels / 64;
+  p.cpt1 = a->src1 ? a->src1_channels / 64 : 0;
+  p.tw = g.tw; p.th = g.th; p.nb = g.nb;
+  p.tiles_x = g.tiles_x; p.tiles_y = g.tiles_y;
+  p.H = H;
+  p.m_tiles = g.m_tiles;
+  p.n_tiles = n_tiles;
+  p.gs_store = gs_store;
+  p.out_cpt = dst_c / 64;
+  p.bias = a->bias;
+  p.stats = a->stats;
+  p.n_total = a->n_total;
+  const int grid = conv_gemm_grid(g.m_tiles, n_tiles);
+  switch (bn) {
+    case 256: return launch<256>(mA0, mA1, mB, mD, p, grid, stream);
+    case 128: return launch<128>(mA0, mA1, mB, mD, p, grid, stream);
+    default: return launch<64>(mA0, mA1, mB, mD, p, grid, stream);
+  }
+}

@@ -1,0 +1,430 @@
+// Heads (three 1x1 convs 64 -> 1), the SelectiveNet losses, the thresholding + confusion
+// matrix counters, and the Adam step.  HBM-bound or tiny; warp-shuffle reductions, two-stage
+// deterministic sums for floating point, integer atomics only for exact counts.
+//
+// Reference semantics:
+//   heads   /root/reference/model.py:62,65-66,96,99-101
+//   losses  /root/reference/selective_loss.py:58-85, train.py:78,195-201 (BCEWithLogitsLoss)
+//   metrics /root/reference/train.py:211-239, eval.py:228-251, utils/compute_metric.py:10-26
+//   Adam    /root/reference/train.py:88-92,209 (torch.optim.Adam defaults)
+#include "common.h"
+#include "ptx.cuh"
+#include "../../include/sunet_b200.h"
+
+namespace sunet {
+
+static inline int grid_for(long long items, int threads, int per_sm) {
+  long long b = (items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+struct alignas(16) bf16x8 {
+  uint32_t w[4];
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// stable BCE-with-logits: max(x,0) - x*t + log1p(exp(-|x|))   (== torch.nn.BCEWithLogitsLoss)
+__device__ __forceinline__ float bce_logits(float x, float t) {
+  return fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ------------------------------------------------------------------ heads forward
+struct HeadW {
+  const float* w[3];
+  const float* b[3];
+};
+
+__global__ void __launch_bounds__(256)
+heads_fwd_kernel(const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads, float* __restrict__ logits,
+                 long long P) {
+  // 8 lanes per pixel, 8 channels per lane
+  const int sub = threadIdx.x & 7;
+  float w[3][8];
+  float bias[3];
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    bias[h] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[h][j] = 0.f;
+    if (h < nheads) {
+      bias[h] = __ldg(hw.b[h]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[h][j] = __ldg(hw.w[h] + sub * 8 + j);
+    }
+  }
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+  // loop bound is warp-uniform (4 pixels per warp per trip) so the full-mask shuffles are legal
+  for (long long p0 = blockIdx.x * (long long)(blockDim.x >> 3) + ((threadIdx.x >> 5) << 2); p0 < P; p0 += stride) {
+    const long long p = p0 + ((threadIdx.x & 31) >> 3);
+    const bool valid = p < P;
+    bf16x8 v = {{0u, 0u, 0u, 0u}};
+    if (valid) v = *reinterpret_cast<const bf16x8*>(a + p * as + sub * 8);
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float lo = bf16lo(v.w[i]), hi = bf16hi(v.w[i]);
+#pragma unroll
+      for (int h = 0; h < 3; ++h) acc[h] = fmaf(lo, w[h][2 * i], fmaf(hi, w[h][2 * i + 1], acc[h]));
+    }
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+      acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 2);
+      acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 4);
+    }
+    if (valid && sub < nheads) {
+      const float r = sub == 0 ? acc[0] + bias[0] : (sub == 1 ? acc[1] + bias[1] : acc[2] + bias[2]);
+      logits[(long long)sub * P + p] = r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ heads backward
+__global__ void __launch_bounds__(256)
+heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
+                 __nv_bfloat16* __restrict__ dA, int das, float* __restrict__ partials, long long P) {
+  __shared__ float red[256][28];
+  const int sub = threadIdx.x & 7;
+  float w[3][8];
+#pragma unroll
+  for (int h = 0; h < 3; ++h)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[h][j] = (h < nheads) ? __ldg(hw.w[h] + sub * 8 + j) : 0.f;
+  float dw[3][8];
+  float db[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 3; ++h)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dw[h][j] = 0.f;
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+  for (long long p = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3); p < P; p += stride) {
+    float g[3];
+#pragma unroll
+    for (int h = 0; h < 3; ++h) g[h] = (h < nheads) ? __ldg(dl + (long long)h * P + p) : 0.f;
+    const bf16x8 v = *reinterpret_cast<const bf16x8*>(a + p * as + sub * 8);
+    float av[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      av[2 * i] = bf16lo(v.w[i]);
+      av[2 * i + 1] = bf16hi(v.w[i]);
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = g[0] * w[0][j] + g[1] * w[1][j] + g[2] * w[2][j];
+#pragma unroll
+      for (int h = 0; h < 3; ++h) dw[h][j] = fmaf(g[h], av[j], dw[h][j]);
+    }
+    bf16x8 ov;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ov.w[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<bf16x8*>(dA + p * das + sub * 8) = ov;
+    if (sub == 0) {
+#pragma unroll
+      for (int h = 0; h < 3; ++h) db[h] += g[h];
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][h * 8 + j] = dw[h][j];
+    red[threadIdx.x][24 + h] = db[h];
+  }
+  __syncthreads();
+  // partial row layout per block: [3][65] = 64 weight grads + bias grad
+  for (int o = threadIdx.x; o < 3 * 65; o += 256) {
+    const int h = o / 65, c = o % 65;
+    float s = 0.f;
+    if (c < 64) {
+      const int sb = c >> 3, j = c & 7;
+      for (int r = 0; r < 32; ++r) s += red[r * 8 + sb][h * 8 + j];
+    } else {
+      for (int r = 0; r < 32; ++r) s += red[r * 8][24 + h];
+    }
+    partials[(size_t)blockIdx.x * 195 + o] = s;
+  }
+}
+
+struct HeadG {
+  float* dw[3];
+  float* db[3];
+};
+__global__ void heads_bwd_reduce_kernel(const float* __restrict__ partials, int blocks, int nheads, HeadG hg) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= 3 * 65) return;
+  const int h = o / 65, c = o % 65;
+  if (h >= nheads) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += (double)partials[(size_t)b * 195 + o];
+  if (c < 64) {
+    if (hg.dw[h]) hg.dw[h][c] = (float)s;
+  } else {
+    if (hg.db[h]) hg.db[h][0] = (float)s;
+  }
+}
+
+// ------------------------------------------------------------------ losses
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ sel, const float* __restrict__ aux,
+                 const float* __restrict__ tgt, long long P, double* __restrict__ partials) {
+  __shared__ float red[8][3];
+  float S = 0.f, R = 0.f, A = 0.f;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const float t = __ldg(tgt + p);
+    if (sel) {
+      const float s = sigmoid_acc(__ldg(sel + p));
+      S += s;
+      if (out) R = fmaf(bce_logits(__ldg(out + p), t), s, R);
+    }
+    if (aux) A += bce_logits(__ldg(aux + p), t);
+  }
+  S = warp_sum(S);
+  R = warp_sum(R);
+  A = warp_sum(A);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp][0] = S;
+    red[warp][1] = R;
+    red[warp][2] = A;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += (double)red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+__global__ void loss_sums_final_kernel(const double* __restrict__ partials, int blocks, double* sums) {
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int b = 0; b < blocks; ++b) s += partials[(size_t)b * 3 + threadIdx.x];
+    sums[threadIdx.x] = s;
+  }
+}
+__global__ void loss_finalize_kernel(const double* sums, double P, float lamb, float tc, float* results) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double S = sums[0], R = sums[1], A = sums[2];
+    const double c = S / P;
+    const double risk = (S != 0.0) ? R / S : 0.0 / 0.0;
+    const double d = ((double)tc - c) > 0.0 ? ((double)tc - c) : 0.0;
+    const double sl = risk + (double)lamb * d * d;
+    const double al = A / P;
+    results[0] = (float)sl;
+    results[1] = (float)c;
+    results[2] = (float)al;
+    results[3] = (float)(sl + al);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ sel, const float* __restrict__ aux,
+                const float* __restrict__ tgt, long long P, const double* __restrict__ sums, double Pg, float lamb,
+                float tc, const float* __restrict__ g_sel, const float* __restrict__ g_aux, float* __restrict__ d_out,
+                float* __restrict__ d_sel, float* __restrict__ d_aux) {
+  const double S = sums[0], R = sums[1];
+  const float gs = g_sel ? *g_sel : 1.f;
+  const float ga = g_aux ? *g_aux : 1.f;
+  const double c = S / Pg;
+  const double d = ((double)tc - c) > 0.0 ? ((double)tc - c) : 0.0;
+  const float invS = (float)(1.0 / S);
+  const float k_const = (float)(-R / (S * S) - 2.0 * (double)lamb * d / Pg);  // dL/ds_i minus the l_i/S term
+  const float invP = (float)(1.0 / Pg);
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const float t = __ldg(tgt + p);
+    if (d_aux) d_aux[p] = ga * (sigmoid_acc(__ldg(aux + p)) - t) * invP;
+    if (d_out || d_sel) {
+      const float s = sigmoid_acc(__ldg(sel + p));
+      const float x = __ldg(out + p);
+      if (d_out) d_out[p] = gs * s * (sigmoid_acc(x) - t) * invS;
+      if (d_sel) d_sel[p] = gs * s * (1.f - s) * fmaf(bce_logits(x, t), invS, k_const);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ metrics
+template <int LT>
+__device__ __forceinline__ int load_label(const void* label, long long p) {
+  if (LT == 0) return (int)reinterpret_cast<const uint8_t*>(label)[p];
+  if (LT == 1) return (int)(uint8_t)(int)reinterpret_cast<const float*>(label)[p];  // .astype('uint8')
+  const long long v = reinterpret_cast<const long long*>(label)[p];
+  return (v >= 0 && v < 256) ? (int)v : 255;
+}
+
+template <int LT>
+__global__ void __launch_bounds__(256)
+metric_hist_kernel(const float* __restrict__ out, const float* __restrict__ sel, const void* __restrict__ label,
+                   long long P, float thr_out, float thr_sel, int masked, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int red[8][6];
+  unsigned int c[6] = {0, 0, 0, 0, 0, 0};
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int pred = __ldg(out + p) >= thr_out ? 1 : 0;
+    int selected = 1;
+    if (sel) selected = __ldg(sel + p) >= thr_sel ? 1 : 0;
+    const int lab = load_label<LT>(label, p);
+    c[5] += 1;
+    c[4] += selected;
+    const bool use = (lab >= 0 && lab < 2) && (!masked || selected);
+    if (use) c[lab * 2 + pred] += 1;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    unsigned int v = __reduce_add_sync(0xffffffffu, c[k]);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    unsigned long long s = 0;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    if (s) atomicAdd(counts + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------------ Adam
+__global__ void __launch_bounds__(256)
+adam_kernel(const sunet_adam_tensor* __restrict__ table, float lr, float b1, float b2, float eps, float wd,
+            float bc1, float bc2_sqrt) {
+  const sunet_adam_tensor t = table[blockIdx.y];
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.numel;
+       i += (long long)gridDim.x * blockDim.x) {
+    float g = t.grad[i];
+    float p = t.param[i];
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    const float m = b1 * t.exp_avg[i] + (1.f - b1) * g;
+    const float v = b2 * t.exp_avg_sq[i] + (1.f - b2) * g * g;
+    t.exp_avg[i] = m;
+    t.exp_avg_sq[i] = v;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    t.param[i] = p - step_size * (m / denom);
+  }
+}
+
+}  // namespace sunet
+
+using namespace sunet;
+#define STREAM reinterpret_cast<cudaStream_t>(stream_)
+
+extern "C" int sunet_heads_fwd(const void* a, int a_pix_stride, const float* w0, const float* b0, const float* w1,
+                               const float* b1, const float* w2, const float* b2, int nheads, float* logits,
+                               long long pixels, sunet_stream_t stream_) {
+  if (!a || !logits || pixels <= 0 || (nheads != 1 && nheads != 3) || a_pix_stride < 64 || a_pix_stride % 8)
+    return set_error(SUNET_ERR_INVALID, "heads_fwd: bad arguments");
+  HeadW hw = {{w0, w1, w2}, {b0, b1, b2}};
+  for (int h = 0; h < nheads; ++h)
+    if (!hw.w[h] || !hw.b[h]) return set_error(SUNET_ERR_INVALID, "heads_fwd: missing head %d parameters", h);
+  heads_fwd_kernel<<<grid_for(pixels * 8, 256, 8), 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                                      a_pix_stride, hw, nheads, logits, pixels);
+  return check_launch("heads_fwd");
+}
+
+extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,
+                               const float* w2, int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0,
+                               float* dw1, float* db1, float* dw2, float* db2, long long pixels, void* workspace,
+                               size_t workspace_bytes, sunet_stream_t stream_) {
+  if (!dlogits || !a || !dA || !workspace || pixels <= 0 || (nheads != 1 && nheads != 3) || a_pix_stride < 64 ||
+      a_pix_stride % 8 || dA_pix_stride < 64 || dA_pix_stride % 8)
+    return set_error(SUNET_ERR_INVALID, "heads_bwd: bad arguments");
+  HeadW hw = {{w0, w1, w2}, {nullptr, nullptr, nullptr}};
+  for (int h = 0; h < nheads; ++h)
+    if (!hw.w[h]) return set_error(SUNET_ERR_INVALID, "heads_bwd: missing head %d weights", h);
+  int blocks = grid_for(pixels * 8, 256, 4);
+  const size_t need = (size_t)blocks * 195 * sizeof(float);
+  if (workspace_bytes < need) return set_error(SUNET_ERR_WORKSPACE, "heads_bwd: workspace %zu < %zu", workspace_bytes, need);
+  float* partials = reinterpret_cast<float*>(workspace);
+  heads_bwd_kernel<<<blocks, 256, 0, STREAM>>>(dlogits, reinterpret_cast<const __nv_bfloat16*>(a), a_pix_stride, hw,
+                                               nheads, reinterpret_cast<__nv_bfloat16*>(dA), dA_pix_stride, partials,
+                                               pixels);
+  int e = check_launch("heads_bwd");
+  if (e) return e;
+  HeadG hg = {{dw0, dw1, dw2}, {db0, db1, db2}};
+  heads_bwd_reduce_kernel<<<1, 256, 0, STREAM>>>(partials, blocks, nheads, hg);
+  return check_launch("heads_bwd_reduce");
+}
+
+extern "C" int sunet_loss_sums(const float* out, const float* sel, const float* aux, const float* target,
+                               long long pixels, double* sums, void* workspace, size_t workspace_bytes,
+                               sunet_stream_t stream_) {
+  if (!target || !sums || !workspace || pixels <= 0) return set_error(SUNET_ERR_INVALID, "loss_sums: bad arguments");
+  if (out && !sel) return set_error(SUNET_ERR_INVALID, "loss_sums: out given without sel");
+  const int blocks = grid_for(pixels, 256, 8);
+  if (workspace_bytes < (size_t)blocks * 3 * sizeof(double))
+    return set_error(SUNET_ERR_WORKSPACE, "loss_sums: workspace too small");
+  double* partials = reinterpret_cast<double*>(workspace);
+  loss_sums_kernel<<<blocks, 256, 0, STREAM>>>(out, sel, aux, target, pixels, partials);
+  int e = check_launch("loss_sums");
+  if (e) return e;
+  loss_sums_final_kernel<<<1, 32, 0, STREAM>>>(partials, blocks, sums);
+  return check_launch("loss_sums_final");
+}
+
+extern "C" int sunet_loss_finalize(const double* sums, long long global_pixels, float lamb, float target_coverage,
+                                   float* results, sunet_stream_t stream_) {
+  if (!sums || !results || global_pixels <= 0) return set_error(SUNET_ERR_INVALID, "loss_finalize: bad arguments");
+  loss_finalize_kernel<<<1, 32, 0, STREAM>>>(sums, (double)global_pixels, lamb, target_coverage, results);
+  return check_launch("loss_finalize");
+}
+
+extern "C" int sunet_loss_bwd(const float* out, const float* sel, const float* aux, const float* target,
+                              long long pixels, const double* sums, long long global_pixels, float lamb,
+                              float target_coverage, const float* g_sel, const float* g_aux, float* d_out,
+                              float* d_sel, float* d_aux, sunet_stream_t stream_) {
+  if (!target || !sums || pixels <= 0 || global_pixels <= 0)
+    return set_error(SUNET_ERR_INVALID, "loss_bwd: bad arguments");
+  if ((d_out || d_sel) && (!out || !sel)) return set_error(SUNET_ERR_INVALID, "loss_bwd: d_out/d_sel need out and sel");
+  if (d_aux && !aux) return set_error(SUNET_ERR_INVALID, "loss_bwd: d_aux needs aux");
+  loss_bwd_kernel<<<grid_for(pixels, 256, 8), 256, 0, STREAM>>>(out, sel, aux, target, pixels, sums,
+                                                                 (double)global_pixels, lamb, target_coverage, g_sel,
+                                                                 g_aux, d_out, d_sel, d_aux);
+  return check_launch("loss_bwd");
+}
+
+extern "C" int sunet_metric_hist(const float* out, const float* sel, const void* label, int label_dtype,
+                                 long long pixels, float thr_out, float thr_sel, int masked,
+                                 unsigned long long* counts, sunet_stream_t stream_) {
+  if (!out || !label || !counts || pixels <= 0) return set_error(SUNET_ERR_INVALID, "metric_hist: bad arguments");
+  if (masked && !sel) return set_error(SUNET_ERR_INVALID, "metric_hist: masked counting needs a selection map");
+  const int blocks = grid_for(pixels, 256, 8);
+  switch (label_dtype) {
+    case 0:
+      metric_hist_kernel<0><<<blocks, 256, 0, STREAM>>>(out, sel, label, pixels, thr_out, thr_sel, masked, counts);
+      break;
+    case 1:
+      metric_hist_kernel<1><<<blocks, 256, 0, STREAM>>>(out, sel, label, pixels, thr_out, thr_sel, masked, counts);
+      break;
+    case 2:
+      metric_hist_kernel<2><<<blocks, 256, 0, STREAM>>>(out, sel, label, pixels, thr_out, thr_sel, masked, counts);
+      break;
+    default:
+      return set_error(SUNET_ERR_INVALID, "metric_hist: bad label dtype %d", label_dtype);
+  }
+  return check_launch("metric_hist");
+}
+
+extern "C" int sunet_adam_step(const sunet_adam_tensor* table, int n_tensors, long long max_numel, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step,
+                               sunet_stream_t stream_) {
+  if (!table || n_tensors <= 0 || max_numel <= 0 || step <= 0)
+    return set_error(SUNET_ERR_INVALID, "adam_step: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  long long bx = (max_numel + 256 * 8 - 1) / (256 * 8);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)n_tensors);
+  adam_kernel<<<grid, 256, 0, STREAM>>>(table, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  return check_launch("adam_step");
+}
+
+extern "C" int sunet_abi_version(void) { return SUNET_ABI_VERSION; }
+extern "C" const char* sunet_last_error(void) { return sunet::last_error(); }

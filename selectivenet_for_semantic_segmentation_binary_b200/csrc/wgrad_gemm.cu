@@ -1,0 +1,355 @@
+// G2 — weight-gradient GEMM: the contraction over PIXELS.
+//
+//   P[split][tap][m][n] = sum_{pixels p in split} A[p, m] * B[p (+) tap, n]        (fp32)
+//
+//   conv3x3 wgrad : A = dY (m = out channel), B = layer input shifted by the tap (n = in channel)
+//   convT   wgrad : A = layer input (m = in channel), B = 2x2-gathered dOut (n = out channel)
+//   plain         : one tap, no shift (the im2col'ed first layer)
+//
+// Both operands are read straight from NHWC bf16 tensors by TMA.  Because the reduction
+// dimension (pixels) is the slow axis of NHWC, both are "MN-major" tcgen05 operands: one
+// 128-byte swizzled row per pixel holding 64 channels.  Each CTA owns a 128(m) x BNW(n) block
+// of up to four taps (T*BNW <= 512 TMEM columns) and a slice of the pixel range (split-K);
+// partials are written as plain fp32 and summed deterministically by wgrad_reduce (no atomics).
+//
+// Replaces: the weight-gradient half of conv2d / conv_transpose2d backward as dispatched by
+// loss.backward() in /root/reference/train.py:208 (cuDNN wgrad in the reference).
+#include "common.h"
+#include "ptx.cuh"
+#include "../../include/sunet_b200.h"
+
+namespace sunet {
+
+constexpr int KP = 32;                 // pixels per pipeline stage (two K=16 MMA steps)
+constexpr int BOX_BYTES = KP * 128;    // one TMA box: KP pixels x 64 channels
+constexpr int WG_THREADS = 192;
+
+struct WgradParams {
+  int mode;        // SUNET_A_CONV3X3 / SUNET_A_PLAIN / SUNET_A_GATHER2X2 (how B is addressed)
+  int T;           // taps handled per CTA (3, 1 or 4)
+  int tap_groups;  // 3, 1, 1
+  int nb64;        // BNW / 64
+  int m_tiles, n_tiles, splits;
+  int kb_total, kb_per_split;
+  int tw, th, nb, tiles_x, tiles_y;
+  int H;
+  int c0_blocks;   // n tiles that come from B source 0 (rest from source 1)
+  int Ca, Nb;      // real A channels (rows written), total B channels
+  int taps_total;
+  int tmem_cols;   // power of two >= T * BNW
+  float* out;      // [splits][taps_total][Ca][Nb]
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
+                  const __grid_constant__ CUtensorMap mapB1, const WgradParams p, const int stage_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* done_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB0);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item
+  int item = blockIdx.x;
+  const int n_tile = item % p.n_tiles; item /= p.n_tiles;
+  const int m_tile = item % p.m_tiles; item /= p.m_tiles;
+  const int tg = item % p.tap_groups;  item /= p.tap_groups;
+  const int split = item;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  const int BNW = p.nb64 * 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mapB = (n_tile < p.c0_blocks) ? &mapB0 : &mapB1;
+      const int cB = ((n_tile < p.c0_blocks) ? n_tile : (n_tile - p.c0_blocks)) * BNW;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int xt = kb % p.tiles_x;
+        const int yt = (kb / p.tiles_x) % p.tiles_y;
+        const int nt = kb / (p.tiles_x * p.tiles_y);
+        const int x0 = xt * p.tw, y0 = yt * p.th, n0 = nt * p.nb;
+        uint8_t* st = smem + stage * stage_bytes;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        // A: two 64-channel boxes (the second may be fully out of range -> zeros)
+        tma_load_5d(st, &mapA, &full_bar[stage], m_tile * 128, x0, y0, n0, 0);
+        tma_load_5d(st + BOX_BYTES, &mapA, &full_bar[stage], m_tile * 128 + 64, x0, y0, n0, 0);
+        uint8_t* sb = st + 2 * BOX_BYTES;
+        for (int t = 0; t < p.T; ++t) {
+          for (int j = 0; j < p.nb64; ++j) {
+            uint8_t* dst = sb + (t * p.nb64 + j) * BOX_BYTES;
+            const int c = cB + j * 64;
+            if (p.mode == SUNET_A_GATHER2X2) {
+              tma_load_5d(dst, mapB, &full_bar[stage], c, t & 1, x0, t >> 1, n0 * p.H + y0);
+            } else if (p.mode == SUNET_A_CONV3X3) {
+              tma_load_5d(dst, mapB, &full_bar[stage], c, x0 + t - 1, y0 + tg - 1, n0, 0);
+            } else {
+              tma_load_5d(dst, mapB, &full_bar[stage], c, x0, y0, n0, 0);
+            }
+          }
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BNW, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sb = sa + 2 * BOX_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KP / 16; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(sa + kk * 2048, BOX_BYTES, 1024);
+          for (int t = 0; t < p.T; ++t) {
+            const uint64_t bdesc = make_smem_desc_sw128(sb + t * p.nb64 * BOX_BYTES + kk * 2048, BOX_BYTES, 1024);
+            umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int mrow = m_tile * 128 + quad * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after_sync();
+    for (int t = 0; t < p.T; ++t) {
+      const int tap = tg * p.T + t;
+      float* orow = p.out + ((static_cast<size_t>(split) * p.taps_total + tap) * p.Ca + mrow) * p.Nb + n_tile * BNW;
+      for (int c = 0; c < BNW; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + t * BNW + c, v);
+        tmem_ld_wait();
+        if (mrow < p.Ca) {
+          float4* o4 = reinterpret_cast<float4*>(orow + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static int pow2_div(int v, int cap) {
+  int t = 1;
+  while (t < cap && (v % (t * 2)) == 0) t *= 2;
+  return t;
+}
+
+struct WgPlan {
+  int T, tap_groups, taps_total, BNW, m_tiles, n_tiles, splits, kb_total, kb_per_split;
+  int tw, th, nb, tiles_x, tiles_y, tiles_n;
+  int Nb;
+};
+
+static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
+  switch (a->b_mode) {
+    case SUNET_A_CONV3X3: w->T = 3; w->tap_groups = 3; break;
+    case SUNET_A_PLAIN: w->T = 1; w->tap_groups = 1; break;
+    case SUNET_A_GATHER2X2: w->T = 4; w->tap_groups = 1; break;
+    default: return set_error(SUNET_ERR_INVALID, "wgrad_gemm: bad b_mode %d", a->b_mode);
+  }
+  w->taps_total = w->T * w->tap_groups;
+  w->Nb = a->b0_channels + (a->b1 ? a->b1_channels : 0);
+  if (a->a_channels <= 0 || a->a_channels % 64 || a->b0_channels <= 0 || a->b0_channels % 64 ||
+      (a->b1 && a->b1_channels % 64))
+    return set_error(SUNET_ERR_INVALID, "wgrad_gemm: channel counts must be multiples of 64");
+  w->BNW = (a->b0_channels % 128 == 0 && (!a->b1 || a->b1_channels % 128 == 0)) ? 128 : 64;
+  w->m_tiles = (a->a_channels + 127) / 128;
+  w->n_tiles = w->Nb / w->BNW;
+  const int B = a->batch, H = a->height, W = a->width;
+  w->tw = pow2_div(W, KP);
+  w->th = pow2_div(H, KP / w->tw);
+  w->nb = KP / (w->tw * w->th);
+  if (w->nb > 1 && w->th != H)
+    return set_error(SUNET_ERR_INVALID, "wgrad_gemm: cannot tile %d x %d x %d into %d-pixel blocks", B, H, W, KP);
+  w->tiles_x = W / w->tw;
+  w->tiles_y = H / w->th;
+  w->tiles_n = (B + w->nb - 1) / w->nb;
+  w->kb_total = w->tiles_x * w->tiles_y * w->tiles_n;
+  const int base_items = w->m_tiles * w->n_tiles * w->tap_groups;
+  int want = (2 * num_sms() + base_items - 1) / base_items;  // ~2 CTAs per SM worth of items
+  if (want < 1) want = 1;
+  int max_splits = (w->kb_total + 7) / 8;  // at least 8 k-blocks per CTA when possible
+  if (max_splits < 1) max_splits = 1;
+  if (want > max_splits) want = max_splits;
+  w->kb_per_split = (w->kb_total + want - 1) / want;
+  w->splits = (w->kb_total + w->kb_per_split - 1) / w->kb_per_split;
+  return SUNET_OK;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int gs, int C, int S, int B, int H, int W, const WgPlan& w) {
+  uint64_t dims[5], str[4];
+  uint32_t box[5];
+  const uint64_t e = 2;
+  if (!gs) {
+    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = B; dims[4] = 1;
+    str[0] = (uint64_t)S * e; str[1] = (uint64_t)W * S * e; str[2] = (uint64_t)H * W * S * e;
+    str[3] = (uint64_t)B * H * W * S * e;
+    box[0] = 64; box[1] = w.tw; box[2] = w.th; box[3] = w.nb; box[4] = 1;
+  } else {
+    dims[0] = C; dims[1] = 2; dims[2] = W; dims[3] = 2; dims[4] = (uint64_t)B * H;
+    str[0] = (uint64_t)S * e; str[1] = (uint64_t)2 * S * e; str[2] = (uint64_t)2 * W * S * e;
+    str[3] = (uint64_t)4 * W * S * e;
+    box[0] = 64; box[1] = 1; box[2] = w.tw; box[3] = 1; box[4] = w.th * w.nb;
+  }
+  return make_tmap_bf16_5d(m, base, dims, str, box);
+}
+
+}  // namespace sunet
+
+using namespace sunet;
+
+extern "C" int sunet_wgrad_gemm_splits(const sunet_wgrad_gemm_args* a) {
+  WgPlan w;
+  if (!a || plan_wgrad(a, &w)) return -1;
+  return w.splits;
+}
+
+extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: null args");
+  if (!a->a || !a->b0 || !a->partials) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: null tensor");
+  if (a->batch <= 0 || a->height <= 0 || a->width <= 0) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: bad grid");
+  if (a->b_mode == SUNET_A_GATHER2X2 && a->b1) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: gather takes one B");
+  WgPlan w;
+  int e = plan_wgrad(a, &w);
+  if (e) return e;
+  const size_t need = (size_t)w.splits * w.taps_total * a->a_channels * w.Nb * sizeof(float);
+  if (a->partials_bytes < need)
+    return set_error(SUNET_ERR_WORKSPACE, "wgrad_gemm: partials buffer %zu < %zu bytes", (size_t)a->partials_bytes, need);
+  if (a->b1 && (a->b0_channels % w.BNW)) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: b0 channels vs tile");
+
+  CUtensorMap mA, mB0, mB1;
+  const int B = a->batch, H = a->height, W = a->width;
+  if ((e = make_map(&mA, a->a, 0, a->a_channels, a->a_pix_stride, B, H, W, w))) return e;
+  if ((e = make_map(&mB0, a->b0, a->b_mode == SUNET_A_GATHER2X2, a->b0_channels, a->b0_pix_stride, B, H, W, w)))
+    return e;
+  if (a->b1) {
+    if ((e = make_map(&mB1, a->b1, 0, a->b1_channels, a->b1_pix_stride, B, H, W, w))) return e;
+  } else {
+    mB1 = mB0;
+  }
+  WgradParams p;
+  p.mode = a->b_mode;
+  p.T = w.T; p.tap_groups = w.tap_groups; p.nb64 = w.BNW / 64;
+  p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles; p.splits = w.splits;
+  p.kb_total = w.kb_total; p.kb_per_split = w.kb_per_split;
+  p.tw = w.tw; p.th = w.th; p.nb = w.nb; p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y;
+  p.H = H;
+  p.c0_blocks = a->b0_channels / w.BNW;
+  p.Ca = a->a_channels; p.Nb = w.Nb;
+  p.taps_total = w.taps_total;
+  p.out = a->partials;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < w.T * w.BNW) p.tmem_cols *= 2;
+  const int stage_bytes = BOX_BYTES * (2 + w.T * p.nb64);
+  constexpr int STAGES = 5;
+  const int smem = STAGES * stage_bytes + 1024 + 256;
+  if (smem > 227 * 1024) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: smem %d too large", smem);
+  static int max_set = 0;
+  if (smem > max_set) {
+    if ((e = check_cuda(cudaFuncSetAttribute(wgrad_gemm_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024),
+                        "cudaFuncSetAttribute(wgrad_gemm)")))
+      return e;
+    max_set = 227 * 1024;
+  }
+  const int grid = w.m_tiles * w.n_tiles * w.tap_groups * w.splits;
+  wgrad_gemm_kernel<STAGES><<<grid, WG_THREADS, smem, stream>>>(mA, mB0, mB1, p, stage_bytes);
+  return check_launch("wgrad_gemm_kernel");
+}
+
+// ------------------------------------------------------------------ split-K reduction
+namespace sunet {
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ P, int splits, int taps, int Ca, int Nb, int layout, int real_cin,
+                    float* __restrict__ grad, long long total) {
+  const long long slab = (long long)taps * Ca * Nb;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long src;
+    if (layout == 0) {        // grad[co][ci][tap], Ca = co, Nb = ci
+      const int tap = (int)(i % 9);
+      const int ci = (int)((i / 9) % Nb);
+      const int co = (int)(i / (9LL * Nb));
+      src = ((long long)tap * Ca + co) * Nb + ci;
+    } else if (layout == 1) { // grad[ci][co][tap], Ca = ci, Nb = co
+      const int tap = (int)(i % 4);
+      const int co = (int)((i / 4) % Nb);
+      const int ci = (int)(i / (4LL * Nb));
+      src = ((long long)tap * Ca + ci) * Nb + co;
+    } else {                  // grad[co][cin][tap] from P[0][co][tap*cin + ci]
+      const int tap = (int)(i % 9);
+      const int ci = (int)((i / 9) % real_cin);
+      const int co = (int)(i / (9LL * real_cin));
+      src = (long long)co * Nb + tap * real_cin + ci;
+    }
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += P[k * slab + src];
+    grad[i] = s;
+  }
+}
+}  // namespace sunet
+
+extern "C" int sunet_wgrad_reduce(const float* partials, int splits, int taps, int a_channels, int b_channels,
+                                  int layout, int real_cin, float* grad, sunet_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!partials || !grad || splits <= 0 || a_channels <= 0 || b_channels <= 0)
+    return set_error(SUNET_ERR_INVALID, "wgrad_reduce: bad arguments");
+  long long total;
+  if (layout == 0 && taps == 9) total = 9LL * a_channels * b_channels;
+  else if (layout == 1 && taps == 4) total = 4LL * a_channels * b_channels;
+  else if (layout == 2 && taps == 1 && real_cin > 0 && real_cin * 9 <= b_channels) total = 9LL * a_channels * real_cin;
+  else return set_error(SUNET_ERR_INVALID, "wgrad_reduce: layout %d / taps %d mismatch", layout, taps);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(partials, splits, taps, a_channels, b_channels, layout, real_cin,
+                                                       grad, total);
+  return check_launch("wgrad_reduce");
+}

@@ -1,0 +1,250 @@
+"""Typed torch-tensor wrappers over the C ABI (one Python function per entry point).
+
+PyTorch is plumbing here: it owns device memory and streams; every function below only
+extracts ``data_ptr()`` / strides and enqueues hand-written sm_100a kernels on the current
+stream.  Activations are NHWC bf16 tensors ``[B, H, W, C]`` and may be channel slices of a
+wider buffer (``stride(2)`` is the pixel stride).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import A_CONV3X3, A_GATHER2X2, A_PLAIN, D_NHWC, D_SCATTER2X2, WORKSPACE_BYTES  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _act(t: torch.Tensor):
+    """(ptr, channels, pix_stride) of an NHWC bf16 activation view."""
+    assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.is_cuda, (t.dtype, t.shape)
+    B, H, W, Cc = t.shape
+    assert t.stride(3) == 1
+    ps = t.stride(2)
+    assert t.stride(1) == W * ps and t.stride(0) == H * W * ps, "activation view must be pixel-contiguous"
+    return t.data_ptr(), Cc, ps
+
+
+def _f32(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous(), (t.dtype, t.shape)
+    return t.data_ptr()
+
+
+def new_workspace(device) -> torch.Tensor:
+    return torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------- G1
+def conv_gemm_stat_rows(batch: int, height: int, width: int, n_total: int) -> int:
+    r = _lib.load().sunet_conv_gemm_stat_rows(batch, height, width, n_total)
+    if r <= 0:
+        raise _lib.SunetError("conv_gemm_stat_rows: bad shape")
+    return r
+
+
+def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst: torch.Tensor, *,
+              src1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+              stats: Optional[torch.Tensor] = None, d_mode: int = D_NHWC) -> None:
+    """grid = (batch, height, width) of the GEMM-M pixel grid."""
+    lib = _lib.load()
+    a = _lib.ConvGemmArgs()
+    a.batch, a.height, a.width = grid
+    a.a_mode = a_mode
+    a.src0, a.src0_channels, a.src0_pix_stride = _act(src0)
+    if src1 is not None:
+        a.src1, a.src1_channels, a.src1_pix_stride = _act(src1)
+    assert weights.dtype == torch.bfloat16 and weights.dim() == 2 and weights.is_contiguous()
+    a.weights = weights.data_ptr()
+    a.n_total, a.k_total = weights.shape
+    a.bias = _f32(bias)
+    a.dst, _, a.dst_pix_stride = _act(dst)
+    a.d_mode = d_mode
+    if stats is not None:
+        rows = conv_gemm_stat_rows(a.batch, a.height, a.width, a.n_total)
+        assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= rows * a.n_total * 2
+        a.stats = stats.data_ptr()
+    _lib.check(lib.sunet_conv_gemm(C.byref(a), _stream()), "sunet_conv_gemm")
+
+
+# ----------------------------------------------------------------------------- G2
+def _wgrad_args(grid, a: torch.Tensor, b_mode: int, b0: torch.Tensor, b1: Optional[torch.Tensor],
+                partials: Optional[torch.Tensor]) -> _lib.WgradGemmArgs:
+    w = _lib.WgradGemmArgs()
+    w.batch, w.height, w.width = grid
+    w.a, w.a_channels, w.a_pix_stride = _act(a)
+    w.b_mode = b_mode
+    w.b0, w.b0_channels, w.b0_pix_stride = _act(b0)
+    if b1 is not None:
+        w.b1, w.b1_channels, w.b1_pix_stride = _act(b1)
+    if partials is not None:
+        w.partials = partials.data_ptr()
+        w.partials_bytes = partials.numel() * partials.element_size()
+    return w
+
+
+def wgrad_splits(grid, a, b_mode, b0, b1=None) -> int:
+    w = _wgrad_args(grid, a, b_mode, b0, b1, None)
+    r = _lib.load().sunet_wgrad_gemm_splits(C.byref(w))
+    if r <= 0:
+        raise _lib.SunetError("wgrad_gemm_splits: bad shape")
+    return r
+
+
+def wgrad_gemm(grid, a, b_mode, b0, partials, b1=None) -> int:
+    """Returns the number of split-K partial slabs written."""
+    w = _wgrad_args(grid, a, b_mode, b0, b1, partials)
+    lib = _lib.load()
+    splits = lib.sunet_wgrad_gemm_splits(C.byref(w))
+    _lib.check(lib.sunet_wgrad_gemm(C.byref(w), _stream()), "sunet_wgrad_gemm")
+    return splits
+
+
+def wgrad_reduce(partials, splits, taps, a_channels, b_channels, layout, grad, real_cin=0) -> None:
+    _lib.check(_lib.load().sunet_wgrad_reduce(partials.data_ptr(), splits, taps, a_channels, b_channels, layout,
+                                              real_cin, _f32(grad), _stream()), "sunet_wgrad_reduce")
+
+
+# ----------------------------------------------------------------------------- packing
+def pack_input_im2col(x: torch.Tensor, out: torch.Tensor) -> None:
+    B, Cin, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16
+    assert out.shape == (B, H, W, 64) and out.is_contiguous()
+    _lib.check(_lib.load().sunet_pack_input_im2col(x.data_ptr(), out.data_ptr(), B, Cin, H, W, _stream()),
+               "sunet_pack_input_im2col")
+
+
+def pack_conv3x3_weights(w, wf, wd=None) -> None:
+    co, ci = w.shape[0], w.shape[1]
+    _lib.check(_lib.load().sunet_pack_conv3x3_weights(_f32(w), wf.data_ptr(), _ptr(wd), co, ci, _stream()),
+               "sunet_pack_conv3x3_weights")
+
+
+def pack_conv1_weights(w, wf) -> None:
+    co, ci = w.shape[0], w.shape[1]
+    _lib.check(_lib.load().sunet_pack_conv1_weights(_f32(w), wf.data_ptr(), co, ci, _stream()),
+               "sunet_pack_conv1_weights")
+
+
+def pack_convT_weights(w, bias, wf, wd, bias4) -> None:
+    ci, co = w.shape[0], w.shape[1]
+    _lib.check(_lib.load().sunet_pack_convT_weights(_f32(w), _f32(bias), wf.data_ptr(), _ptr(wd), _f32(bias4), ci, co,
+                                                    _stream()), "sunet_pack_convT_weights")
+
+
+# ----------------------------------------------------------------------------- BN / pool
+def bn_finalize(stats, rows, channels, count, gamma, beta, conv_bias, running_mean, running_var, nbt, momentum, eps,
+                scale, shift, mean, invstd) -> None:
+    _lib.check(_lib.load().sunet_bn_finalize(_f32(stats), rows, channels, count, _f32(gamma), _f32(beta),
+                                             _f32(conv_bias), _f32(running_mean), _f32(running_var), _ptr(nbt),
+                                             momentum, eps, _f32(scale), _f32(shift), _f32(mean), _f32(invstd),
+                                             _stream()), "sunet_bn_finalize")
+
+
+def bn_eval_affine(gamma, beta, conv_bias, running_mean, running_var, eps, scale, shift) -> None:
+    _lib.check(_lib.load().sunet_bn_eval_affine(_f32(gamma), _f32(beta), _f32(conv_bias), _f32(running_mean),
+                                                _f32(running_var), eps, _f32(scale), _f32(shift), gamma.numel(),
+                                                _stream()), "sunet_bn_eval_affine")
+
+
+def bn_relu_pool(y, scale, shift, a, pooled=None) -> None:
+    B, H, W, Cc = y.shape
+    yp, _, ys = _act(y)
+    ap, _, as_ = _act(a)
+    pp, ps = (None, 0)
+    if pooled is not None:
+        pp, _, ps = _act(pooled)
+    _lib.check(_lib.load().sunet_bn_relu_pool(yp, ys, _f32(scale), _f32(shift), ap, as_, pp, ps, B, H, W, Cc,
+                                              _stream()), "sunet_bn_relu_pool")
+
+
+def bn_relu_pool_bwd(dA, dPool, y, scale, shift, mean, invstd, gamma, dgamma, dbeta, dy, workspace) -> None:
+    B, H, W, Cc = y.shape
+    yp, _, ys = _act(y)
+    dyp, _, dys = _act(dy)
+    dAp, das = (None, 0) if dA is None else _act(dA)[::2]
+    dPp, dps = (None, 0) if dPool is None else _act(dPool)[::2]
+    _lib.check(_lib.load().sunet_bn_relu_pool_bwd(dAp, das, dPp, dps, yp, ys, _f32(scale), _f32(shift), _f32(mean),
+                                                  _f32(invstd), _f32(gamma), _f32(dgamma), _f32(dbeta), dyp, dys, B,
+                                                  H, W, Cc, workspace.data_ptr(), workspace.numel(), _stream()),
+               "sunet_bn_relu_pool_bwd")
+
+
+def colsum_finalize(stats, rows, n_total, col_offset, channels, out) -> None:
+    _lib.check(_lib.load().sunet_colsum_finalize(_f32(stats), rows, n_total, col_offset, channels, _f32(out),
+                                                 _stream()), "sunet_colsum_finalize")
+
+
+# ----------------------------------------------------------------------------- heads / loss / metric / adam
+def heads_fwd(a, weights, biases, logits) -> None:
+    """weights/biases: lists (1 or 3) of fp32 tensors; logits: fp32 [nheads, P]."""
+    ap, _, as_ = _act(a)
+    n = len(weights)
+    w = [_f32(t.reshape(-1)) for t in weights] + [None] * (3 - n)
+    b = [_f32(t.reshape(-1)) for t in biases] + [None] * (3 - n)
+    P = a.shape[0] * a.shape[1] * a.shape[2]
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.numel() == n * P
+    _lib.check(_lib.load().sunet_heads_fwd(ap, as_, w[0], b[0], w[1], b[1], w[2], b[2], n, logits.data_ptr(), P,
+                                           _stream()), "sunet_heads_fwd")
+
+
+def heads_bwd(dlogits, a, weights, dA, dws, dbs, workspace) -> None:
+    ap, _, as_ = _act(a)
+    dp, _, ds = _act(dA)
+    n = len(weights)
+    w = [_f32(t.reshape(-1)) for t in weights] + [None] * (3 - n)
+    dw = [_f32(t.reshape(-1)) for t in dws] + [None] * (3 - n)
+    db = [_f32(t.reshape(-1)) for t in dbs] + [None] * (3 - n)
+    P = a.shape[0] * a.shape[1] * a.shape[2]
+    assert dlogits.dtype == torch.float32 and dlogits.is_contiguous() and dlogits.numel() == n * P
+    _lib.check(_lib.load().sunet_heads_bwd(dlogits.data_ptr(), ap, as_, w[0], w[1], w[2], n, dp, ds, dw[0], db[0],
+                                           dw[1], db[1], dw[2], db[2], P, workspace.data_ptr(), workspace.numel(),
+                                           _stream()), "sunet_heads_bwd")
+
+
+def loss_sums(out, sel, aux, target, sums, workspace) -> None:
+    P = target.numel()
+    _lib.check(_lib.load().sunet_loss_sums(_f32(out), _f32(sel), _f32(aux), _f32(target), P, sums.data_ptr(),
+                                           workspace.data_ptr(), workspace.numel(), _stream()), "sunet_loss_sums")
+
+
+def loss_finalize(sums, global_pixels, lamb, target_coverage, results) -> None:
+    _lib.check(_lib.load().sunet_loss_finalize(sums.data_ptr(), global_pixels, float(lamb), float(target_coverage),
+                                               _f32(results), _stream()), "sunet_loss_finalize")
+
+
+def loss_bwd(out, sel, aux, target, sums, global_pixels, lamb, target_coverage, g_sel, g_aux, d_out, d_sel,
+             d_aux) -> None:
+    P = target.numel()
+    _lib.check(_lib.load().sunet_loss_bwd(_f32(out), _f32(sel), _f32(aux), _f32(target), P, sums.data_ptr(),
+                                          global_pixels, float(lamb), float(target_coverage), _f32(g_sel),
+                                          _f32(g_aux), _f32(d_out), _f32(d_sel), _f32(d_aux), _stream()),
+               "sunet_loss_bwd")
+
+
+_LABEL_DTYPES = {torch.uint8: 0, torch.float32: 1, torch.int64: 2}
+
+
+def metric_hist(out, sel, label, thr_out, thr_sel, masked, counts) -> None:
+    assert label.is_contiguous() and label.dtype in _LABEL_DTYPES, label.dtype
+    assert counts.dtype == torch.int64 and counts.numel() >= 6
+    P = out.numel()
+    assert label.numel() == P
+    _lib.check(_lib.load().sunet_metric_hist(_f32(out), _f32(sel), label.data_ptr(), _LABEL_DTYPES[label.dtype], P,
+                                             float(thr_out), float(thr_sel), int(bool(masked)), counts.data_ptr(),
+                                             _stream()), "sunet_metric_hist")
+
+
+def adam_step(table_dev, n_tensors, max_numel, lr, beta1, beta2, eps, weight_decay, step) -> None:
+    _lib.check(_lib.load().sunet_adam_step(table_dev.data_ptr(), n_tensors, max_numel, lr, beta1, beta2, eps,
+                                           weight_decay, step, _stream()), "sunet_adam_step")
