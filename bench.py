@@ -1,0 +1,340 @@
+"""SUNet_B training throughput on synthetic 256x256 RGB patches (BASELINE.json configs[1]/[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo (CUDA, C ABI)
+    python bench.py --impl reference [--steps K] [--warmup W]           # the reference's CPU path
+
+One "step" = one full SUNet_B training step (forward, aux BCE + selective risk, backward, Adam,
+thresholded confusion-matrix update) over this rank's shard of the global batch of 128 patches.
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_PATCH_256 = 220.4e9          # fwd + dgrad + wgrad, no dgrad for layer 1
+GLOBAL_BATCH = 128
+PATCH = 256
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(bf16=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), hbm=d.get("hbm_gbs"), source="measured")
+    return dict(bf16=1590.0, hbm=6650.0, source="fallback")       # B200_PROFILING.md fallback
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step_rate(steps: int, warmup: int, batch: int = 4):
+    """The reference's CPU path (PyTorch fp32 on the host cores), restated by oracle/sunet_oracle.py:
+    SUNet_B forward + aux/selective losses + backward + Adam on a `batch`-patch sample of the workload."""
+    import torch
+    from oracle import sunet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.init_state_dict(0, "RGB", True)
+    names = [k for k in sd if "running" not in k and "num_batches" not in k]
+    params = [sd[n].requires_grad_(True) for n in names]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    x, label = O.synthetic_batch(batch, PATCH, seed=0)
+    ev = O.Evaluator(2, True)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, aux = O.train_losses(sd, x, label, s_lamb=2, selective=True)
+        loss.backward()
+        opt.step()
+        pred, sel = O.postprocess(aux["output"].detach().numpy(), aux["selection"].detach().numpy(), path="train")
+        ev.add_batch(label.numpy().astype("uint8"), pred, selection=sel)
+        float(loss)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    pps, sec, cores = cpu_reference_step_rate(steps, warmup, batch=4)
+    line = {
+        "impl": "reference", "metric": "SUNet_B train patches/sec (256^2)", "value": pps, "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SUNet_B (UNet_B --selective 1 --s_lamb 2, BCElogit) train step, 256x256 RGB patches",
+                   "global_batch": GLOBAL_BATCH, "timing": "host perf_counter"},
+        "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of a 4-patch shard of the 128-patch batch (oracle = the reference's "
+                                   f"PyTorch CPU ops, fp32, {cores} threads)"},
+        "e2e": {"value": pps, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from selectivenet_for_semantic_segmentation_binary_b200 import _lib
+    from selectivenet_for_semantic_segmentation_binary_b200 import kernels as K
+    from selectivenet_for_semantic_segmentation_binary_b200.model import UNet_B
+    from selectivenet_for_semantic_segmentation_binary_b200.trainer import SUNetTrainer, chunk_bounds
+    from selectivenet_for_semantic_segmentation_binary_b200.utils.compute_metric import Evaluator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    lib = _lib.load()
+
+    gb = args.batch
+    lo, hi = chunk_bounds(gb, world, rank)
+    b = hi - lo
+    torch.manual_seed(0)
+    net = UNet_B("RGB", selective=True).to(dev)
+    net.train()
+    ev = Evaluator(2, True, device=dev)
+    tr = SUNetTrainer(net, lr=1e-3, s_lamb=2, process_group=group, world_size=world, evaluator=ev,
+                      use_cuda_graph=not args.no_graph)
+    g = torch.Generator().manual_seed(1234)
+    x_all = torch.rand(gb, 3, args.size, args.size, generator=g) * 2 - 1
+    l_all = (torch.rand(gb, args.size, args.size, generator=g) < 0.4).float()
+    x_host = x_all[lo:hi].contiguous().pin_memory()
+    l_host = l_all[lo:hi].contiguous().pin_memory()
+    del x_all, l_all
+    x_dev, l_dev = x_host.to(dev), l_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # warm-up (also: eager steps that precede CUDA-graph capture)
+    n0 = lib.sunet_launch_count()
+    tr_eager_launches = None
+    for i in range(max(args.warmup, 3)):
+        before = lib.sunet_launch_count()
+        tr.step(x_dev, l_dev)
+        after = lib.sunet_launch_count()
+        if tr_eager_launches is None:
+            tr_eager_launches = after - before       # launches of one eager step == launches per graph replay
+    barrier()
+
+    # ---- value: inputs resident in HBM, device-timed, max over ranks
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        tr.step(x_dev, l_dev)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = gb * args.steps / (ms / 1e3)
+
+    # ---- e2e: pinned host inputs, H2D + step + D2H of the step's losses, every step
+    barrier()
+    e0.record()
+    res_host = None
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        ld = l_host.to(dev, non_blocking=True)
+        res = tr.step(xd, ld)
+        res_host = res.cpu()                      # loss / coverage read back (the reference's .item() calls)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = gb * args.steps / (ms_e2e / 1e3)
+    h2d = x_host.numel() * 4 + l_host.numel() * 4
+    d2h = 4 * 4
+
+    # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), timed live with CUDA events
+    roof = None
+    if rank == 0:
+        roof = tensor_core_roofline(tr, x_dev, l_dev, K, torch, min(args.steps, 3))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pps, sec, cores = cpu_reference_step_rate(3, 1, batch=4)
+        cpu = {"value": pps, "unit": "patches/s", "cores": cores, "kind": "port",
+               "sample": f"3 steps of a 4-patch shard of the same SUNet_B train step ({sec:.2f} s/step, fp32, "
+                         f"{cores} torch threads)"}
+
+    if rank == 0:
+        pk = peaks()
+        line = {
+            "metric": "SUNet_B train patches/sec (256^2, bf16)", "value": value, "unit": "patches/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "SUNet_B (UNet_B --selective 1 --s_lamb 2, BCElogit) train step: fwd + aux BCE + "
+                                   "selective risk + bwd + Adam + confusion matrix, 256x256 RGB patches, random init",
+                       "global_batch": gb, "per_gpu_batch": b, "patch": args.size, "parallelism": f"dp{world}",
+                       "l2": "inputs_exceed_l2 (activations ~120 MB/patch >> 126 MB L2)",
+                       "cuda_graph": bool(tr.use_graph)},
+            "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(tr_eager_launches) * args.steps,
+            "clocks": clocks,
+            "step_tflops": value * FLOP_PER_PATCH_256 * (args.size / 256) ** 2 / 1e12 / world,
+            "step_frac_of_bf16_peak": value * FLOP_PER_PATCH_256 * (args.size / 256) ** 2 / 1e12 / world / pk["bf16"],
+            "last_losses": [float(v) for v in res_host.tolist()] if res_host is not None else None,
+        }
+        if roof is not None:
+            roof["peak"] = pk["bf16"]
+            roof["frac"] = roof["achieved"] / pk["bf16"]
+            roof["peak_source"] = pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)"
+            line["roofline"] = roof
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def tensor_core_roofline(tr, x, label, K, torch, steps):
+    """Time every tensor-core launch (G1 conv_gemm + G2 wgrad_gemm) of `steps` eager training steps with
+    CUDA events on the launching stream and relate it to their ALGORITHMIC flops (2*M*N*K per launch,
+    real channels only).  Dominant kernel = conv_gemm_kernel (G1)."""
+    recs = {"conv_gemm": [0.0, 0.0, 0], "wgrad_gemm": [0.0, 0.0, 0]}
+    pending = []
+    orig_conv, orig_wgrad = K.conv_gemm, K.wgrad_gemm
+
+    def timed(name, flops, fn, *a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **kw)
+        e1.record()
+        pending.append((name, flops, e0, e1))
+        return r
+
+    def conv_gemm(a_mode, grid, src0, weights, dst, **kw):
+        m = grid[0] * grid[1] * grid[2]
+        n, k = weights.shape
+        if a_mode == K.A_PLAIN and k == 64 and src0 is tr.net._plans[next(iter(tr.net._plans))].col:
+            k = 27                                   # first layer: 9*3 real taps*channels, rest is zero padding
+        return timed("conv_gemm", 2.0 * m * n * k, orig_conv, a_mode, grid, src0, weights, dst, **kw)
+
+    def wgrad_gemm(grid, a, b_mode, b0, partials, b1=None):
+        m = grid[0] * grid[1] * grid[2]
+        taps = {K.A_CONV3X3: 9, K.A_PLAIN: 1, K.A_GATHER2X2: 4}[b_mode]
+        nb = b0.shape[3] + (b1.shape[3] if b1 is not None else 0)
+        if b_mode == K.A_PLAIN:
+            nb = 27
+        return timed("wgrad_gemm", 2.0 * m * taps * a.shape[3] * nb, orig_wgrad, grid, a, b_mode, b0, partials, b1)
+
+    use_graph = tr.use_graph
+    tr.use_graph = False
+    K.conv_gemm, K.wgrad_gemm = conv_gemm, wgrad_gemm
+    try:
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            tr.step(x, label)
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        K.conv_gemm, K.wgrad_gemm = orig_conv, orig_wgrad
+        tr.use_graph = use_graph
+    for name, flops, e0, e1 in pending:
+        recs[name][0] += flops
+        recs[name][1] += e0.elapsed_time(e1) * 1e-3
+        recs[name][2] += 1
+    total_s = t0.elapsed_time(t1) * 1e-3
+    g1f, g1t, g1n = recs["conv_gemm"]
+    g2f, g2t, g2n = recs["wgrad_gemm"]
+    return {
+        "bound": "tensor", "kernel": "conv_gemm_kernel (G1: conv3x3 fwd+dgrad, convT fwd+dgrad)",
+        "achieved": g1f / g1t / 1e12, "unit": "TFLOP/s", "traffic": None,
+        "launches": g1n, "avg_launch_ms": g1t / g1n * 1e3, "share_of_step": g1t / total_s,
+        "wgrad_gemm": {"achieved": g2f / g2t / 1e12, "launches": g2n, "avg_launch_ms": g2t / g2n * 1e3,
+                       "share_of_step": g2t / total_s},
+        "other_share_of_step": 1.0 - (g1t + g2t) / total_s,
+        "note": "algorithmic flops = 2*M*N*K per launch (real channels); durations = CUDA events around each launch "
+                "in an un-graphed instrumented pass after the timed region",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch (BASELINE: 128)")
+    ap.add_argument("--size", type=int, default=PATCH)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,8 @@ typedef struct CUstream_st* sunet_stream_t;
 
 int sunet_abi_version(void);
 const char* sunet_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long sunet_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * G1: tensor-core implicit GEMM  D[pixel, n] = sum_{tap,c} A_tap[pixel, c] * W[n, tap*C + c] (+bias)
@@ -197,9 +199,11 @@ typedef struct sunet_adam_tensor {
   float* exp_avg_sq;
   long long numel;
 } sunet_adam_tensor;
-/* table: DEVICE array of n_tensors entries */
+/* table: DEVICE array of n_tensors entries.  step is 1-based.  lr_dev / step_dev (device scalars,
+ * may be NULL) override lr / step so a CUDA graph of the whole step can be replayed unchanged. */
 int sunet_adam_step(const sunet_adam_tensor* table, int n_tensors, long long max_numel, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, int step, sunet_stream_t stream);
+                    float beta2, float eps, float weight_decay, int step, const float* lr_dev, const int* step_dev,
+                    sunet_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -139,8 +139,7 @@ def g1_convT(K):
         dx = torch.full((B, h, w_, Cin), float("nan"), dtype=torch.bfloat16, device=dev)
         K.conv_gemm(K.A_GATHER2X2, (B, h, w_), dbuf[..., :Cout], wd, dx)
         torch.cuda.synchronize()
-        ref_dx = F.conv2d(dbuf[..., :Cout].float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float().transpose(0, 1),
-                          stride=2)
+        ref_dx = F.conv2d(dbuf[..., :Cout].float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), stride=2)
         ok &= report("   convT dgrad", nchw(dx), ref_dx)
     return ok
 

@@ -58,7 +58,8 @@ _vp, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 SIGNATURES = {
     "sunet_abi_version": [],
     "sunet_last_error": [],
-    "sunet_conv_gemm": [C.POINTER(ConvGemmArgs), _vp],
+    "sunet_launch_count": [],
+    "sunet_conv_gemm":[C.POINTER(ConvGemmArgs), _vp],
     "sunet_conv_gemm_stat_rows": [_i, _i, _i, _i],
     "sunet_wgrad_gemm": [C.POINTER(WgradGemmArgs), _vp],
     "sunet_wgrad_gemm_splits": [C.POINTER(WgradGemmArgs)],
@@ -79,9 +80,9 @@ SIGNATURES = {
     "sunet_loss_finalize": [_vp, _ll, _f, _f, _vp, _vp],
     "sunet_loss_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _ll, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "sunet_metric_hist": [_vp, _vp, _vp, _i, _ll, _f, _f, _i, _vp, _vp],
-    "sunet_adam_step": [_vp, _i, _ll, _f, _f, _f, _f, _f, _i, _vp],
+    "sunet_adam_step": [_vp, _i, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp],
 }
-_RESTYPES = {"sunet_last_error": C.c_char_p}
+_RESTYPES = {"sunet_last_error": C.c_char_p, "sunet_launch_count": C.c_longlong}
 
 _lib = None
 

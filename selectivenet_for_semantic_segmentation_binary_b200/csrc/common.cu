@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace sunet {
@@ -23,7 +24,12 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return SUNET_OK;
   return set_error(SUNET_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
-int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
+static std::atomic<long long> g_launches{0};
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), what);
+}
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

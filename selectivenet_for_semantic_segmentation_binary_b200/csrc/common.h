@@ -19,7 +19,8 @@ enum {
 int set_error(int code, const char* fmt, ...);
 const char* last_error();
 int check_cuda(cudaError_t e, const char* what);
-int check_launch(const char* what);
+int check_launch(const char* what);   // also counts the launch (see sunet_launch_count)
+long long launch_count();
 
 // Rank-5 bf16 tensor map with 128-byte swizzle.  dims/strides are in elements /
 // bytes, innermost first; strides[0] is implied (2 bytes).  box[0] must be 64

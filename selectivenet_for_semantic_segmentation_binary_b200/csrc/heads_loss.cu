@@ -293,8 +293,14 @@ metric_hist_kernel(const float* __restrict__ out, const float* __restrict__ sel,
 // ------------------------------------------------------------------ Adam
 __global__ void __launch_bounds__(256)
 adam_kernel(const sunet_adam_tensor* __restrict__ table, float lr, float b1, float b2, float eps, float wd,
-            float bc1, float bc2_sqrt) {
+            int step, const float* __restrict__ lr_dev, const int* __restrict__ step_dev) {
   const sunet_adam_tensor t = table[blockIdx.y];
+  // hyper-parameters that change per step may live on the device so that a captured CUDA graph
+  // of the whole training step stays valid across replays
+  if (lr_dev) lr = *lr_dev;
+  if (step_dev) step = *step_dev;
+  const float bc1 = 1.f - powf(b1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
   const float step_size = lr / bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.numel;
        i += (long long)gridDim.x * blockDim.x) {
@@ -412,19 +418,18 @@ extern "C" int sunet_metric_hist(const float* out, const float* sel, const void*
 }
 
 extern "C" int sunet_adam_step(const sunet_adam_tensor* table, int n_tensors, long long max_numel, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int step,
-                               sunet_stream_t stream_) {
-  if (!table || n_tensors <= 0 || max_numel <= 0 || step <= 0)
+                               float beta1, float beta2, float eps, float weight_decay, int step, const float* lr_dev,
+                               const int* step_dev, sunet_stream_t stream_) {
+  if (!table || n_tensors <= 0 || max_numel <= 0 || (step <= 0 && !step_dev))
     return set_error(SUNET_ERR_INVALID, "adam_step: bad arguments");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
   long long bx = (max_numel + 256 * 8 - 1) / (256 * 8);
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)n_tensors);
-  adam_kernel<<<grid, 256, 0, STREAM>>>(table, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  adam_kernel<<<grid, 256, 0, STREAM>>>(table, lr, beta1, beta2, eps, weight_decay, step, lr_dev, step_dev);
   return check_launch("adam_step");
 }
 
 extern "C" int sunet_abi_version(void) { return SUNET_ABI_VERSION; }
+extern "C" long long sunet_launch_count(void) { return sunet::launch_count(); }
 extern "C" const char* sunet_last_error(void) { return sunet::last_error(); }

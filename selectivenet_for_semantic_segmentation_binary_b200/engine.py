@@ -1,0 +1,370 @@
+"""Execution plan of one UNet_B forward/backward on one GPU.
+
+A ``SUNetPlan`` is built for a fixed (batch, height, width, input channels, selective) and owns
+every device buffer the step needs — NHWC bf16 activations, packed bf16 weights, BatchNorm
+statistics, gradient scratch and one flat fp32 gradient buffer laid out in parameter order — so
+a steady-state step performs no allocation and is CUDA-graph capturable.  It drives the
+C-ABI kernels (``kernels.py``); it does no arithmetic of its own.
+
+Layer graph: /root/reference/model.py:68-103.  HBM layout (per level L = 1..4, resolution
+H/2^(L-1), channels 64*2^(L-1)):
+    y[layer]   raw conv output (bias-free), bf16 NHWC      kept for BN/ReLU backward
+    a[layer]   relu(bn(y)), bf16 NHWC                      the next conv's TMA source
+    pool[L]    2x2 max of the encoder output of level L    (L = 1..3)
+    up[L]      ConvTranspose output feeding level L        (L = 1..3); the decoder conv reads
+               (up[L], skip a[enc_L_2]) through two tensor maps — the concat is never built
+    dcat[L]    gradient w.r.t. that virtual concat, [.., 2C]: first C -> ConvT backward,
+               last C -> encoder skip
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from . import kernels as K
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+# (block name, level, cin from previous act, cout, kind)
+#   kind: 'first' (im2col'ed input), 'conv' (single source), 'cat' (up + skip), plus pool flag
+_ENC = [("encoder_layer_1_1", 1, "first"), ("encoder_layer_1_2", 1, "conv"),
+        ("encoder_layer_2_1", 2, "conv"), ("encoder_layer_2_2", 2, "conv"),
+        ("encoder_layer_3_1", 3, "conv"), ("encoder_layer_3_2", 3, "conv"),
+        ("decoder_layer_4_2", 4, "conv"), ("decoder_layer_4_1", 4, "conv")]
+_CH = {1: 64, 2: 128, 3: 256, 4: 512}
+
+
+class _Layer:
+    """One CBR block: buffers + parameter handles."""
+
+    def __init__(self, name: str, level: int, kind: str, cin: int, cout: int):
+        self.name, self.level, self.kind, self.cin, self.cout = name, level, kind, cin, cout
+        self.pool = False          # followed by MaxPool2d(2)
+        # filled by the plan
+        self.y = self.a = None
+        self.wf = self.wd = None
+        self.stats = None
+        self.stat_rows = 0
+        self.scale = self.shift = self.mean = self.invstd = None
+
+
+class SUNetPlan:
+    def __init__(self, batch: int, height: int, width: int, in_ch: int, selective: bool, device):
+        if height % 8 or width % 8:
+            raise ValueError("UNet_B needs H and W divisible by 8 (three 2x2 pools)")
+        self.B, self.H, self.W, self.in_ch, self.selective = batch, height, width, in_ch, selective
+        self.device = torch.device(device)
+        self.nheads = 3 if selective else 1
+        dev = self.device
+        bf = torch.bfloat16
+        B = batch
+        self.hw = {L: (height >> (L - 1), width >> (L - 1)) for L in (1, 2, 3, 4)}
+
+        def act(L, ch):
+            h, w = self.hw[L]
+            return torch.empty(B, h, w, ch, dtype=bf, device=dev)
+
+        # ---- layers in forward order
+        self.layers: Dict[str, _Layer] = {}
+        order: List[_Layer] = []
+
+        def add(name, L, kind, cin, cout):
+            ly = _Layer(name, L, kind, cin, cout)
+            self.layers[name] = ly
+            order.append(ly)
+            return ly
+
+        add("encoder_layer_1_1", 1, "first", in_ch, 64)
+        add("encoder_layer_1_2", 1, "conv", 64, 64).pool = True
+        add("encoder_layer_2_1", 2, "conv", 64, 128)
+        add("encoder_layer_2_2", 2, "conv", 128, 128).pool = True
+        add("encoder_layer_3_1", 3, "conv", 128, 256)
+        add("encoder_layer_3_2", 3, "conv", 256, 256).pool = True
+        add("decoder_layer_4_2", 4, "conv", 256, 512)
+        add("decoder_layer_4_1", 4, "conv", 512, 512)
+        add("decoder_layer_3_2", 3, "cat", 512, 256)
+        add("decoder_layer_3_1", 3, "conv", 256, 256)
+        add("decoder_layer_2_2", 2, "cat", 256, 128)
+        add("decoder_layer_2_1", 2, "conv", 128, 128)
+        add("decoder_layer_1_2", 1, "cat", 128, 64)
+        add("decoder_layer_1_1", 1, "conv", 64, 64)
+        self.order = order
+
+        self.col = act(1, 64)                                   # im2col'ed input (9*in_ch real channels)
+        for ly in order:
+            h, w = self.hw[ly.level]
+            ly.y = act(ly.level, ly.cout)
+            ly.a = act(ly.level, ly.cout)
+            kdim = 64 if ly.kind == "first" else 9 * ly.cin
+            ly.wf = torch.empty(ly.cout, kdim, dtype=bf, device=dev)
+            ly.wd = None if ly.kind == "first" else torch.empty(ly.cin, 9 * ly.cout, dtype=bf, device=dev)
+            ly.stat_rows = K.conv_gemm_stat_rows(B, h, w, ly.cout)
+            ly.stats = torch.zeros(ly.stat_rows, ly.cout, 2, device=dev)
+            ly.scale, ly.shift, ly.mean, ly.invstd = (torch.empty(ly.cout, device=dev) for _ in range(4))
+        self.pool = {L: act(L + 1, _CH[L]) for L in (1, 2, 3)}   # pooled encoder output of level L
+        self.up = {L: act(L, _CH[L]) for L in (1, 2, 3)}         # ConvT output feeding level L
+        # ConvT packs: unpool{L}: C_{L+1} -> C_L
+        self.upw = {}
+        for L in (1, 2, 3):
+            ci, co = _CH[L + 1], _CH[L]
+            self.upw[L] = dict(wf=torch.empty(4 * co, ci, dtype=bf, device=dev),
+                               wd=torch.empty(ci, 4 * co, dtype=bf, device=dev),
+                               b4=torch.empty(4 * co, device=dev))
+        P = B * height * width
+        self.P = P
+        self.logits = torch.empty(self.nheads, P, device=dev)
+
+        # ---- backward scratch
+        self.gA = {L: act(L, _CH[L]) for L in (1, 2, 3, 4)}
+        self.gB = {L: act(L, _CH[L]) for L in (1, 2, 3, 4)}
+        self.dcat = {L: act(L, 2 * _CH[L]) for L in (1, 2, 3)}
+        self.dpool = {L: act(L + 1, _CH[L]) for L in (1, 2, 3)}
+        self.dcat_stats = {}
+        for L in (1, 2, 3):
+            h, w = self.hw[L]
+            rows = K.conv_gemm_stat_rows(B, h, w, 2 * _CH[L])
+            self.dcat_stats[L] = (torch.zeros(rows, 2 * _CH[L], 2, device=dev), rows)
+        self.ws = K.new_workspace(dev)
+        self.partials = None      # sized lazily from the wgrad split plan
+        self._partials_bytes = 0
+        self._size_partials()
+        self.generation = 0       # bumped by every training forward; backward checks it
+
+    # ------------------------------------------------------------------ helpers
+    def _size_partials(self):
+        need = 0
+        B = self.B
+        for ly in self.order:
+            h, w = self.hw[ly.level]
+            dy = self.gB[ly.level]
+            if ly.kind == "first":
+                s = K.wgrad_splits((B, h, w), dy, K.A_PLAIN, self.col)
+                need = max(need, s * 1 * ly.cout * 64)
+            elif ly.kind == "cat":
+                s = K.wgrad_splits((B, h, w), dy, K.A_CONV3X3, self.up[ly.level], self._skip(ly.level))
+                need = max(need, s * 9 * ly.cout * ly.cin)
+            else:
+                src = self._conv_src(ly)
+                s = K.wgrad_splits((B, h, w), dy, K.A_CONV3X3, src)
+                need = max(need, s * 9 * ly.cout * ly.cin)
+        for L in (1, 2, 3):
+            h, w = self.hw[L + 1]
+            xin = self.layers[self._convT_input(L)].a
+            s = K.wgrad_splits((B, h, w), xin, K.A_GATHER2X2, self.dcat[L][..., :_CH[L]])
+            need = max(need, s * 4 * _CH[L + 1] * _CH[L])
+        self.partials = torch.empty(need, device=self.device)
+
+    def _skip(self, L) -> torch.Tensor:
+        return self.layers[f"encoder_layer_{L}_2"].a
+
+    @staticmethod
+    def _convT_input(L) -> str:
+        return {3: "decoder_layer_4_1", 2: "decoder_layer_3_1", 1: "decoder_layer_2_1"}[L]
+
+    def _conv_src(self, ly: _Layer) -> torch.Tensor:
+        """Activation tensor a single-source conv layer reads."""
+        n = ly.name
+        prev = {
+            "encoder_layer_1_2": self.layers["encoder_layer_1_1"].a,
+            "encoder_layer_2_1": self.pool[1], "encoder_layer_2_2": self.layers["encoder_layer_2_1"].a,
+            "encoder_layer_3_1": self.pool[2], "encoder_layer_3_2": self.layers["encoder_layer_3_1"].a,
+            "decoder_layer_4_2": self.pool[3], "decoder_layer_4_1": self.layers["decoder_layer_4_2"].a,
+            "decoder_layer_3_1": self.layers["decoder_layer_3_2"].a,
+            "decoder_layer_2_1": self.layers["decoder_layer_2_2"].a,
+            "decoder_layer_1_1": self.layers["decoder_layer_1_2"].a,
+        }
+        return prev[n]
+
+    # ------------------------------------------------------------------ weights
+    def pack_weights(self, params: Dict[str, torch.Tensor]) -> None:
+        """fp32 reference-layout parameters -> bf16 kernel operands (every forward; 7.7 M values)."""
+        for ly in self.order:
+            w = params[f"{ly.name}.0.weight"]
+            if ly.kind == "first":
+                K.pack_conv1_weights(w, ly.wf)
+            else:
+                K.pack_conv3x3_weights(w, ly.wf, ly.wd)
+        for L in (1, 2, 3):
+            u = self.upw[L]
+            K.pack_convT_weights(params[f"unpool{L}.weight"], params[f"unpool{L}.bias"], u["wf"], u["wd"], u["b4"])
+
+    # ------------------------------------------------------------------ forward
+    def _cbr_fwd(self, ly: _Layer, params, buffers, training: bool):
+        B = self.B
+        h, w = self.hw[ly.level]
+        grid = (B, h, w)
+        stats = ly.stats if training else None
+        if ly.kind == "first":
+            K.conv_gemm(K.A_PLAIN, grid, self.col, ly.wf, ly.y, stats=stats)
+        elif ly.kind == "cat":
+            K.conv_gemm(K.A_CONV3X3, grid, self.up[ly.level], ly.wf, ly.y, src1=self._skip(ly.level), stats=stats)
+        else:
+            K.conv_gemm(K.A_CONV3X3, grid, self._conv_src(ly), ly.wf, ly.y, stats=stats)
+        n = ly.name
+        if training:
+            K.bn_finalize(ly.stats, ly.stat_rows, ly.cout, B * h * w, params[f"{n}.1.weight"], params[f"{n}.1.bias"],
+                          params[f"{n}.0.bias"], buffers[f"{n}.1.running_mean"], buffers[f"{n}.1.running_var"],
+                          buffers[f"{n}.1.num_batches_tracked"], BN_MOMENTUM, BN_EPS, ly.scale, ly.shift, ly.mean,
+                          ly.invstd)
+        else:
+            K.bn_eval_affine(params[f"{n}.1.weight"], params[f"{n}.1.bias"], params[f"{n}.0.bias"],
+                             buffers[f"{n}.1.running_mean"], buffers[f"{n}.1.running_var"], BN_EPS, ly.scale,
+                             ly.shift)
+        K.bn_relu_pool(ly.y, ly.scale, ly.shift, ly.a, self.pool[ly.level] if ly.pool else None)
+
+    def forward(self, x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor],
+                training: bool) -> torch.Tensor:
+        """x: fp32 NCHW on this plan's device.  Returns the plan-owned logits buffer [nheads, P]."""
+        assert x.shape == (self.B, self.in_ch, self.H, self.W), (x.shape, (self.B, self.in_ch, self.H, self.W))
+        self.pack_weights(params)
+        K.pack_input_im2col(x, self.col)
+        L = self.layers
+        for name in ("encoder_layer_1_1", "encoder_layer_1_2", "encoder_layer_2_1", "encoder_layer_2_2",
+                     "encoder_layer_3_1", "encoder_layer_3_2", "decoder_layer_4_2", "decoder_layer_4_1"):
+            self._cbr_fwd(L[name], params, buffers, training)
+        for lvl, (n2, n1) in ((3, ("decoder_layer_3_2", "decoder_layer_3_1")),
+                              (2, ("decoder_layer_2_2", "decoder_layer_2_1")),
+                              (1, ("decoder_layer_1_2", "decoder_layer_1_1"))):
+            u = self.upw[lvl]
+            hh, ww = self.hw[lvl + 1]
+            K.conv_gemm(K.A_PLAIN, (self.B, hh, ww), L[self._convT_input(lvl)].a, u["wf"], self.up[lvl], bias=u["b4"],
+                        d_mode=K.D_SCATTER2X2)
+            self._cbr_fwd(L[n2], params, buffers, training)
+            self._cbr_fwd(L[n1], params, buffers, training)
+        heads = ["conv1x1"] + (["conv_select", "conv_aux"] if self.selective else [])
+        K.heads_fwd(L["decoder_layer_1_1"].a, [params[f"{h}.weight"] for h in heads],
+                    [params[f"{h}.bias"] for h in heads], self.logits)
+        if training:
+            self.generation += 1
+        return self.logits
+
+    # ------------------------------------------------------------------ backward
+    def _cbr_bwd(self, ly: _Layer, dA: Optional[torch.Tensor], dPool: Optional[torch.Tensor], params, grads,
+                 dgrad_out: Optional[torch.Tensor], dgrad_stats: Optional[torch.Tensor] = None):
+        """dA/dPool -> (dgamma, dbeta, dy) -> weight grad, and the input gradient into dgrad_out."""
+        B = self.B
+        h, w = self.hw[ly.level]
+        grid = (B, h, w)
+        n = ly.name
+        dy = self.gB[ly.level][..., :ly.cout] if ly.cout != self.gB[ly.level].shape[3] else self.gB[ly.level]
+        K.bn_relu_pool_bwd(dA, dPool, ly.y, ly.scale, ly.shift, ly.mean, ly.invstd, params[f"{n}.1.weight"],
+                           grads[f"{n}.1.weight"], grads[f"{n}.1.bias"], dy, self.ws)
+        gw = grads[f"{n}.0.weight"]
+        if ly.kind == "first":
+            s = K.wgrad_gemm(grid, dy, K.A_PLAIN, self.col, self.partials)
+            K.wgrad_reduce(self.partials, s, 1, ly.cout, 64, 2, gw, real_cin=ly.cin)
+        elif ly.kind == "cat":
+            s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self.up[ly.level], self.partials, self._skip(ly.level))
+            K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
+        else:
+            s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self._conv_src(ly), self.partials)
+            K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
+        if dgrad_out is not None:
+            K.conv_gemm(K.A_CONV3X3, grid, dy, ly.wd, dgrad_out, stats=dgrad_stats)
+
+    def backward(self, dlogits: torch.Tensor, params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor],
+                 on_group_done=None) -> None:
+        """dlogits: fp32 [nheads, P].  Fills every tensor of `grads` (reference layouts, fp32);
+        pre-BN conv bias gradients are identically zero and are left untouched (kept zero).
+
+        on_group_done(tag) is called (host side, after the launches are enqueued) each time a group of
+        parameters has all its gradients enqueued — 'dec1', 'dec2', 'dec3', 'dec4', 'enc3', 'enc2',
+        'enc1' in that order; each group is a contiguous suffix slice of the flat gradient buffer,
+        which is what the data-parallel trainer all-reduces while the rest of backward runs."""
+        done = on_group_done if on_group_done is not None else (lambda tag: None)
+        L = self.layers
+        B = self.B
+        heads = ["conv1x1"] + (["conv_select", "conv_aux"] if self.selective else [])
+        K.heads_bwd(dlogits, L["decoder_layer_1_1"].a, [params[f"{h}.weight"] for h in heads], self.gA[1],
+                    [grads[f"{h}.weight"] for h in heads], [grads[f"{h}.bias"] for h in heads], self.ws)
+        dA = self.gA[1]
+        for lvl, (n2, n1) in ((1, ("decoder_layer_1_2", "decoder_layer_1_1")),
+                              (2, ("decoder_layer_2_2", "decoder_layer_2_1")),
+                              (3, ("decoder_layer_3_2", "decoder_layer_3_1"))):
+            c = _CH[lvl]
+            self._cbr_bwd(L[n1], dA, None, params, grads, self.gA[lvl])
+            st, rows = self.dcat_stats[lvl]
+            self._cbr_bwd(L[n2], self.gA[lvl], None, params, grads, self.dcat[lvl], st)
+            # ConvTranspose backward: bias (column sums of d_up), weight, input
+            dup = self.dcat[lvl][..., :c]
+            K.colsum_finalize(st, rows, 2 * c, 0, c, grads[f"unpool{lvl}.bias"])
+            hh, ww = self.hw[lvl + 1]
+            xin = L[self._convT_input(lvl)].a
+            s = K.wgrad_gemm((B, hh, ww), xin, K.A_GATHER2X2, dup, self.partials)
+            K.wgrad_reduce(self.partials, s, 4, _CH[lvl + 1], c, 1, grads[f"unpool{lvl}.weight"])
+            K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1])
+            dA = self.gA[lvl + 1]
+            done(f"dec{lvl}")
+        # bottleneck
+        self._cbr_bwd(L["decoder_layer_4_1"], self.gA[4], None, params, grads, self.gA[4])
+        self._cbr_bwd(L["decoder_layer_4_2"], self.gA[4], None, params, grads, self.dpool[3])
+        done("dec4")
+        # encoder, deepest first; skip gradient = second half of dcat, pooled gradient = dpool
+        for lvl in (3, 2, 1):
+            c = _CH[lvl]
+            n2, n1 = f"encoder_layer_{lvl}_2", f"encoder_layer_{lvl}_1"
+            self._cbr_bwd(L[n2], self.dcat[lvl][..., c:], self.dpool[lvl], params, grads, self.gA[lvl])
+            self._cbr_bwd(L[n1], self.gA[lvl], None, params, grads, self.dpool[lvl - 1] if lvl > 1 else None)
+            done(f"enc{lvl}")
+
+
+def param_order(selective: bool) -> List[str]:
+    """Trainable tensors in nn.Module registration order (model.py:29-66): 68 (or 64) names."""
+    names = []
+    seq = ["encoder_layer_1_1", "encoder_layer_1_2", "encoder_layer_2_1", "encoder_layer_2_2", "encoder_layer_3_1",
+           "encoder_layer_3_2", "decoder_layer_4_2", "decoder_layer_4_1", "unpool3", "decoder_layer_3_2",
+           "decoder_layer_3_1", "unpool2", "decoder_layer_2_2", "decoder_layer_2_1", "unpool1", "decoder_layer_1_2",
+           "decoder_layer_1_1"]
+    for n in seq:
+        if n.startswith("unpool"):
+            names += [f"{n}.weight", f"{n}.bias"]
+        else:
+            names += [f"{n}.0.weight", f"{n}.0.bias", f"{n}.1.weight", f"{n}.1.bias"]
+    for h in ["conv1x1"] + (["conv_select", "conv_aux"] if selective else []):
+        names += [f"{h}.weight", f"{h}.bias"]
+    return names
+
+
+class FlatGrads:
+    """One flat fp32 buffer holding every parameter gradient, with per-parameter views."""
+
+    def __init__(self, shapes: Dict[str, Sequence[int]], order: List[str], device):
+        total = 0
+        self.offsets = {}
+        for n in order:
+            numel = 1
+            for s in shapes[n]:
+                numel *= s
+            self.offsets[n] = (total, numel)
+            total += (numel + 3) // 4 * 4      # keep every view 16-byte aligned
+        self.flat = torch.zeros(total, device=device)
+        self.views = {n: self.flat[o:o + k].view(*shapes[n]) for n, (o, k) in self.offsets.items()}
+        self.order = order
+        self.total = total
+
+    def group_ranges(self):
+        """Flat [lo, hi) ranges of the gradient groups, keyed by the tags SUNetPlan.backward reports."""
+        def off(name):
+            return self.offsets[name][0]
+        cuts = [("enc1", 0), ("enc2", off("encoder_layer_2_1.0.weight")), ("enc3", off("encoder_layer_3_1.0.weight")),
+                ("dec4", off("decoder_layer_4_2.0.weight")), ("dec3", off("unpool3.weight")),
+                ("dec2", off("unpool2.weight")), ("dec1", off("unpool1.weight"))]
+        out = {}
+        for i, (tag, lo) in enumerate(cuts):
+            hi = cuts[i + 1][1] if i + 1 < len(cuts) else self.total
+            out[tag] = (lo, hi)
+        return out
+
+
+def build_adam_table(params: List[torch.Tensor], grads: List[torch.Tensor], m: List[torch.Tensor],
+                     v: List[torch.Tensor], device) -> torch.Tensor:
+    tab = (_lib.AdamTensor * len(params))()
+    for i, p in enumerate(params):
+        tab[i].param, tab[i].grad = p.data_ptr(), grads[i].data_ptr()
+        tab[i].exp_avg, tab[i].exp_avg_sq = m[i].data_ptr(), v[i].data_ptr()
+        tab[i].numel = p.numel()
+    return torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(device)

@@ -245,6 +245,8 @@ def metric_hist(out, sel, label, thr_out, thr_sel, masked, counts) -> None:
                                              _stream()), "sunet_metric_hist")
 
 
-def adam_step(table_dev, n_tensors, max_numel, lr, beta1, beta2, eps, weight_decay, step) -> None:
+def adam_step(table_dev, n_tensors, max_numel, lr, beta1, beta2, eps, weight_decay, step, lr_dev=None,
+              step_dev=None) -> None:
     _lib.check(_lib.load().sunet_adam_step(table_dev.data_ptr(), n_tensors, max_numel, lr, beta1, beta2, eps,
-                                           weight_decay, step, _stream()), "sunet_adam_step")
+                                           weight_decay, step, _ptr(lr_dev), _ptr(step_dev), _stream()),
+               "sunet_adam_step")

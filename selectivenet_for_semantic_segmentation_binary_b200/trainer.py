@@ -1,0 +1,160 @@
+"""Fused SUNet_B training step and batch-sharded data parallelism.
+
+``SUNetTrainer.step(x, label)`` is the body of the reference's hot loop
+(/root/reference/train.py:183-241) — forward, aux BCE + selective risk, backward, Adam, and the
+thresholded confusion-matrix update — as one sequence of kernel launches with **no host
+synchronisation**: loss values stay on the device (the reference's four ``.item()`` calls per step
+become one optional read at logging time), the optimizer is one multi-tensor kernel, and on a
+single GPU the whole sequence is captured once into a CUDA graph and replayed.
+
+Data parallel (replaces ``torch.nn.DataParallel``, train.py:132-134): one process per GPU, weights
+resident on every rank, the batch sharded on dim 0.  Two exchanges per step over NCCL/NVLink:
+  1. all-reduce(sum) of the three loss sums between the loss phases, so coverage, risk and the
+     per-pixel gradients are *global-batch* quantities (the reference computes the loss on the
+     gathered batch; averaging per-shard losses is a different function);
+  2. all-reduce(sum) of the flat gradient buffer in seven groups, each launched on a side stream
+     as soon as backward has produced that group, overlapping the rest of backward.
+BatchNorm statistics stay per-shard, exactly like DataParallel's replicas.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import kernels as K
+from .engine import build_adam_table, param_order
+from .model import UNet_B
+
+
+class SUNetTrainer:
+    def __init__(self, net: UNet_B, lr: float = 1e-3, s_lamb: float = 2, target_coverage: float = 0.8,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, process_group=None,
+                 world_size: int = 1, evaluator=None, use_cuda_graph: bool = True):
+        self.net = net
+        self.selective = bool(net.selective)
+        self.lamb, self.tc = float(s_lamb), float(target_coverage)
+        self.betas, self.eps, self.wd = betas, eps, weight_decay
+        self.group, self.world = process_group, int(world_size)
+        self.evaluator = evaluator
+        p0 = next(net.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("SUNetTrainer needs the model on a CUDA device (no CPU path)")
+        self.device = p0.device
+        self.order = param_order(self.selective)
+        self.params = dict(net.named_parameters())
+        self.buffers = dict(net.named_buffers())
+        self.fg = net._flat_grads()
+        plist = [self.params[n] for n in self.order]
+        self.exp_avg = [torch.zeros_like(p) for p in plist]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in plist]
+        self.table = build_adam_table(plist, [self.fg.views[n] for n in self.order], self.exp_avg, self.exp_avg_sq,
+                                      self.device)
+        self.max_numel = max(p.numel() for p in plist)
+        self.lr_dev = torch.tensor([lr], dtype=torch.float32, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.sums = torch.zeros(3, dtype=torch.float64, device=self.device)
+        self.results = torch.zeros(4, device=self.device)
+        self.ws = K.new_workspace(self.device)
+        self.use_graph = bool(use_cuda_graph) and self.world == 1
+        self._graph = None
+        self._static = None           # (x, label, dlogits) static buffers of the captured shape
+        self._warm = 0
+        self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self._ranges = self.fg.group_ranges()
+        self.launches_per_step = 0
+
+    def set_lr(self, lr: float) -> None:
+        self.lr_dev.fill_(lr)
+
+    # ------------------------------------------------------------------ one step, eager
+    def _step_impl(self, x: torch.Tensor, label: torch.Tensor, dl: torch.Tensor) -> None:
+        net = self.net
+        plan = net._plan_for(x)
+        logits = plan.forward(x, self.params, self.buffers, True)
+        lab = label.reshape(-1)
+        P = plan.P
+        if self.selective:
+            K.loss_sums(logits[0], logits[1], logits[2], lab, self.sums, self.ws)
+        else:
+            K.loss_sums(None, None, logits[0], lab, self.sums, self.ws)
+        Pg = P * self.world
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
+        K.loss_finalize(self.sums, Pg, self.lamb, self.tc, self.results)
+        if self.selective:
+            K.loss_bwd(logits[0], logits[1], logits[2], lab, self.sums, Pg, self.lamb, self.tc, None, None, dl[0],
+                       dl[1], dl[2])
+        else:
+            K.loss_bwd(None, None, logits[0], lab, self.sums, Pg, 0.0, 0.0, None, None, None, None, dl[0])
+        if self.world > 1:
+            import torch.distributed as dist
+            comm, cur = self._comm, torch.cuda.current_stream()
+
+            def reduce_group(tag):
+                lo, hi = self._ranges[tag]
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(self.fg.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+            plan.backward(dl, self.params, self.fg.views, on_group_done=reduce_group)
+            cur.wait_stream(comm)
+        else:
+            plan.backward(dl, self.params, self.fg.views)
+        self.step_dev += 1
+        K.adam_step(self.table, len(self.order), self.max_numel, 0.0, self.betas[0], self.betas[1], self.eps, self.wd,
+                    1, lr_dev=self.lr_dev, step_dev=self.step_dev)
+        if self.evaluator is not None:
+            B, H, W = plan.B, plan.H, plan.W
+            self.evaluator.add_batch_from_logits(label.reshape(B, H, W), logits[0].view(B, H, W),
+                                                 logits[1].view(B, H, W) if self.selective else None, path='train')
+
+    # ------------------------------------------------------------------ public
+    def step(self, x: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+        """x: fp32 [N,C,H,W], label: fp32 {0,1} [N,H,W], both on this trainer's device.
+        Returns a device tensor [select_loss, coverage, aux_loss, total_loss] (no sync)."""
+        if not x.is_cuda or not label.is_cuda:
+            raise RuntimeError("SUNetTrainer.step: inputs must be CUDA tensors")
+        if label.dtype != torch.float32:
+            label = label.to(torch.float32)
+        plan = self.net._plan_for(x)
+        if not self.use_graph:
+            if self._static is None or self._static[2].shape != (plan.nheads, plan.P):
+                self._static = (None, None, torch.empty(plan.nheads, plan.P, device=self.device))
+            self._step_impl(x.contiguous(), label.contiguous(), self._static[2])
+            return self.results
+        key = tuple(x.shape)
+        if self._static is None or tuple(self._static[0].shape) != key:
+            self._static = (torch.empty_like(x), torch.empty_like(label),
+                            torch.empty(plan.nheads, plan.P, device=self.device))
+            self._graph, self._warm = None, 0
+        sx, sl, dl = self._static
+        sx.copy_(x, non_blocking=True)
+        sl.copy_(label, non_blocking=True)
+        if self._graph is None:
+            if self._warm < 2:
+                # two eager steps first: lazy one-time work (function attributes, plan buffers) must not
+                # happen inside capture
+                self._step_impl(sx, sl, dl)
+                self._warm += 1
+                return self.results
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g):
+                self._step_impl(sx, sl, dl)
+            self._graph = g
+            # capture does not execute: replay once so this call is a real step
+        self._graph.replay()
+        return self.results
+
+
+def chunk_bounds(total: int, world: int, rank: int):
+    """[lo, hi) of this rank's shard, with torch.chunk's sizes (DataParallel's scatter,
+    torch/nn/parallel/scatter_gather.py): ceil(total/world) per rank, remainder on the last."""
+    size = -(-total // world)
+    lo = min(total, rank * size)
+    hi = min(total, lo + size)
+    return lo, hi
