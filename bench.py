@@ -20,6 +20,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+LAUNCH_TABLE = [None]
 FLOP_PER_PATCH_256 = 220.4e9          # fwd + dgrad + wgrad, no dgrad for layer 1
 GLOBAL_BATCH = 128
 PATCH = 256
@@ -260,6 +261,7 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
     real channels only).  Dominant kernel = conv_gemm_kernel (G1)."""
     recs = {"conv_gemm": [0.0, 0.0, 0], "wgrad_gemm": [0.0, 0.0, 0]}
     pending = []
+    DESC = [""]
     orig_conv, orig_wgrad = K.conv_gemm, K.wgrad_gemm
 
     def timed(name, flops, fn, *a, **kw):
@@ -267,7 +269,7 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
         e0.record()
         r = fn(*a, **kw)
         e1.record()
-        pending.append((name, flops, e0, e1))
+        pending.append((name, flops, e0, e1, kw.pop("_desc", "") if False else DESC[0]))
         return r
 
     def conv_gemm(a_mode, grid, src0, weights, dst, **kw):
@@ -275,6 +277,7 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
         n, k = weights.shape
         if a_mode == K.A_PLAIN and k == 64 and src0 is tr.net._plans[next(iter(tr.net._plans))].col:
             k = 27                                   # first layer: 9*3 real taps*channels, rest is zero padding
+        DESC[0] = f"mode{a_mode} grid{tuple(grid)} C{src0.shape[3]}{'+' + str(kw['src1'].shape[3]) if kw.get('src1') is not None else ''} N{n} K{k}"
         return timed("conv_gemm", 2.0 * m * n * k, orig_conv, a_mode, grid, src0, weights, dst, **kw)
 
     def wgrad_gemm(grid, a, b_mode, b0, partials, b1=None):
@@ -283,6 +286,7 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
         nb = b0.shape[3] + (b1.shape[3] if b1 is not None else 0)
         if b_mode == K.A_PLAIN:
             nb = 27
+        DESC[0] = f"mode{b_mode} grid{tuple(grid)} A{a.shape[3]} B{nb} taps{taps}"
         return timed("wgrad_gemm", 2.0 * m * taps * a.shape[3] * nb, orig_wgrad, grid, a, b_mode, b0, partials, b1)
 
     use_graph = tr.use_graph
@@ -300,10 +304,16 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
     finally:
         K.conv_gemm, K.wgrad_gemm = orig_conv, orig_wgrad
         tr.use_graph = use_graph
-    for name, flops, e0, e1 in pending:
+    table = []
+    for name, flops, e0, e1, desc in pending:
+        dt = e0.elapsed_time(e1) * 1e-3
         recs[name][0] += flops
-        recs[name][1] += e0.elapsed_time(e1) * 1e-3
+        recs[name][1] += dt
         recs[name][2] += 1
+        table.append({"kernel": name, "shape": desc, "ms": dt * 1e3, "tflops": flops / dt / 1e12})
+    if LAUNCH_TABLE[0]:
+        with open(LAUNCH_TABLE[0], "w") as f:
+            json.dump(table[:len(table) // max(steps, 1)], f, indent=1)
     total_s = t0.elapsed_time(t1) * 1e-3
     g1f, g1t, g1n = recs["conv_gemm"]
     g2f, g2t, g2n = recs["wgrad_gemm"]
@@ -329,7 +339,9 @@ def main():
     ap.add_argument("--size", type=int, default=PATCH)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--launch-table", default=None, help="write per-launch tensor-core timings of one step here")
     args = ap.parse_args()
+    LAUNCH_TABLE[0] = args.launch_table
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -365,7 +365,49 @@ def ew_heads_loss(K):
     return ok
 
 
-GROUPS = {"g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g2_wgrad": g2_wgrad,
+def swizzle_exp(K):
+    """How does tcgen05.mma derive the 128B-swizzle phase of an operand whose descriptor start address is
+    NOT 1024-byte aligned (start shifted by whole 128-byte rows)?  From absolute smem address bits, or
+    relative to the start (+ base_offset field)?  Decides whether 3x3 taps can be shifted windows of one
+    halo tile in shared memory.  Prints errors for every (shift, base_offset) pair; no pass/fail."""
+    dev = "cuda"
+    B, H, W, Cin, N = 1, 8, 16, 64, 64          # exactly one 128-row tile, one K step
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(N, Cin, generator=g) / 8).to(dev).to(torch.bfloat16)
+    full = x.float().reshape(-1, Cin) @ w.float().t()
+    print("  G1 (K-major A operand): out[m] should equal A[m+shift] . W")
+    for shift in (1, 2, 3, 8, 9):
+        for boff in sorted({0, shift & 7}):
+            os.environ["SUNET_DBG_SHIFT"], os.environ["SUNET_DBG_BOFF"] = str(shift), str(boff)
+            y = torch.zeros(B, H, W, N, dtype=torch.bfloat16, device=dev)
+            K.conv_gemm(K.A_PLAIN, (B, H, W), x, w, y)
+            torch.cuda.synchronize()
+            got = y.float().reshape(-1, N)[:128 - shift]
+            e = rel_err(got, full[shift:])
+            print(f"    shift {shift} base_offset {boff}: max-rel-err {e:.3e} {'<== MATCH' if e < 2e-2 else ''}", flush=True)
+    # G2: MN-major B operand, shift along K (pixels).  dy is zero where the shifted window runs off the box.
+    B, H, W, Ca, Cb = 2, 4, 32, 64, 64
+    dy = torch.randn(B, H, W, Ca, generator=g).to(dev).to(torch.bfloat16)
+    xin = torch.randn(B, H, W, Cb, generator=g).to(dev).to(torch.bfloat16)
+    print("  G2 (MN-major B operand): D[m][n] should equal sum_p dy[p][m] * x[p+shift][n]")
+    for shift in (1, 2, 3, 8, 9):
+        dyz = dy.clone()
+        dyz[:, :, W - shift:, :] = 0
+        ref = torch.einsum("bhwm,bhwn->mn", dyz[:, :, :W - shift].float(), xin[:, :, shift:].float())
+        for boff in sorted({0, shift & 7}):
+            os.environ["SUNET_DBG_SHIFT"], os.environ["SUNET_DBG_BOFF"] = str(shift), str(boff)
+            splits = K.wgrad_splits((B, H, W), dyz, K.A_PLAIN, xin)
+            part = torch.zeros(splits, 1, Ca, Cb, device=dev)
+            K.wgrad_gemm((B, H, W), dyz, K.A_PLAIN, xin, part)
+            torch.cuda.synchronize()
+            e = rel_err(part.sum(0)[0], ref)
+            print(f"    shift {shift} base_offset {boff}: max-rel-err {e:.3e} {'<== MATCH' if e < 1e-2 else ''}", flush=True)
+    os.environ["SUNET_DBG_SHIFT"], os.environ["SUNET_DBG_BOFF"] = "0", "0"
+    return True
+
+
+GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g2_wgrad": g2_wgrad,
           "ew_bn": ew_bn, "ew_heads_loss": ew_heads_loss}
 
 

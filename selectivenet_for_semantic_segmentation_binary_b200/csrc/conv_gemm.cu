@@ -17,6 +17,8 @@
 //
 // Replaces: nn.Conv2d / nn.ConvTranspose2d forward+backward-data as dispatched by
 // /root/reference/model.py:11,44-45,51-52,57-58 (cuDNN in the reference).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 #include "../../include/sunet_b200.h"
@@ -36,6 +38,7 @@ struct ConvGemmParams {
   const float* bias;
   float* stats;     // [gridDim.x / n_tiles][n_total][2] or nullptr
   int n_total;
+  int dbg_shift, dbg_boff;  // SUNET_DBG_SHIFT / SUNET_DBG_BOFF: descriptor-swizzle experiment (scripts/gpu_probe.py)
 };
 
 template <int BN>
@@ -155,7 +158,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * C::A_BYTES), 16, 1024);
+          uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * C::A_BYTES) + p.dbg_shift * 128, 16, 1024);
+          adesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * C::B_BYTES), 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -447,6 +451,12 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
   p.bias = a->bias;
   p.stats = a->stats;
   p.n_total = a->n_total;
+  {
+    const char* s = getenv("SUNET_DBG_SHIFT");
+    const char* b = getenv("SUNET_DBG_BOFF");
+    p.dbg_shift = s ? atoi(s) : 0;
+    p.dbg_boff = b ? atoi(b) : 0;
+  }
   const int grid = conv_gemm_grid(g.m_tiles, n_tiles);
   switch (bn) {
     case 256: return launch<256>(mA0, mA1, mB, mD, p, grid, stream);

@@ -14,6 +14,8 @@
 //
 // Replaces: the weight-gradient half of conv2d / conv_transpose2d backward as dispatched by
 // loss.backward() in /root/reference/train.py:208 (cuDNN wgrad in the reference).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 #include "../../include/sunet_b200.h"
@@ -37,6 +39,7 @@ struct WgradParams {
   int Ca, Nb;      // real A channels (rows written), total B channels
   int taps_total;
   int tmem_cols;   // power of two >= T * BNW
+  int dbg_shift, dbg_boff;  // SUNET_DBG_SHIFT / SUNET_DBG_BOFF: descriptor-swizzle experiment
   float* out;      // [splits][taps_total][Ca][Nb]
 };
 
@@ -132,7 +135,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int kk = 0; kk < KP / 16; ++kk) {
           const uint64_t adesc = make_smem_desc_sw128(sa + kk * 2048, BOX_BYTES, 1024);
           for (int t = 0; t < p.T; ++t) {
-            const uint64_t bdesc = make_smem_desc_sw128(sb + t * p.nb64 * BOX_BYTES + kk * 2048, BOX_BYTES, 1024);
+            uint64_t bdesc = make_smem_desc_sw128(sb + t * p.nb64 * BOX_BYTES + kk * 2048 + p.dbg_shift * 128,
+                                                  BOX_BYTES, 1024);
+            bdesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
             umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
         }
@@ -285,6 +290,12 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
   p.Ca = a->a_channels; p.Nb = w.Nb;
   p.taps_total = w.taps_total;
   p.out = a->partials;
+  {
+    const char* s = getenv("SUNET_DBG_SHIFT");
+    const char* b = getenv("SUNET_DBG_BOFF");
+    p.dbg_shift = s ? atoi(s) : 0;
+    p.dbg_boff = b ? atoi(b) : 0;
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < w.T * w.BNW) p.tmem_cols *= 2;
   const int stage_bytes = BOX_BYTES * (2 + w.T * p.nb64);

@@ -1,0 +1,19 @@
+"""Tight per-kernel parity: every C-ABI entry point against plain PyTorch fp32 on the SAME bf16-rounded
+inputs (so only accumulation order / output rounding differ).  Reuses the bring-up probe's checks."""
+import importlib.util
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("gpu_probe", os.path.join(ROOT, "scripts", "gpu_probe.py"))
+probe = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(probe)
+
+
+@pytest.mark.parametrize("group", ["g1_plain", "g1_conv", "g1_convT", "g1_big", "g2_wgrad", "ew_bn", "ew_heads_loss"])
+def test_kernel_group(group):
+    from selectivenet_for_semantic_segmentation_binary_b200 import kernels as K
+    assert probe.GROUPS[group](K), f"kernel group {group} failed parity (see captured output)"
