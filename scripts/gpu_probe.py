@@ -148,7 +148,8 @@ def g2_wgrad(K):
     dev = "cuda"
     ok = True
     cases = [(2, 16, 16, 64, 64, False), (1, 32, 32, 128, 128, False), (2, 8, 8, 256, 128, False),
-             (2, 16, 16, 128, 64, True), (4, 64, 64, 64, 64, False), (2, 4, 4, 512, 256, False)]
+             (2, 16, 16, 128, 64, True), (4, 64, 64, 64, 64, False), (2, 4, 4, 512, 256, False),
+             (2, 8, 64, 128, 64, True), (1, 4, 256, 64, 64, False), (3, 32, 32, 256, 512, False)]
     for (B, H, W, Cin, Cout, dual) in cases:
         g = torch.Generator().manual_seed(3)
         x = torch.randn(B, Cin, H, W, generator=g).to(dev)

@@ -40,20 +40,27 @@ struct WgradParams {
   int taps_total;
   int tmem_cols;   // power of two >= T * BNW
   int dbg_shift, dbg_boff;  // SUNET_DBG_SHIFT / SUNET_DBG_BOFF: descriptor-swizzle experiment
+  int shifted;     // conv3x3 with W % 32 == 0: ONE (KP+2)-pixel B box per 64 channels serves the 3 column taps
+                   // as shifted descriptor windows (tcgen05 swizzles on absolute smem address bits)
+  int bslot;       // bytes reserved per B box in a stage (1024-aligned)
+  int b_tx;        // bytes one B box delivers
+  int bboxes;      // B boxes per stage
+  int stages;
   float* out;      // [splits][taps_total][Ca][Nb]
 };
+constexpr int MAX_STAGES = 12;
 
-template <int STAGES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
                   const __grid_constant__ CUtensorMap mapB1, const WgradParams p, const int stage_bytes) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* done_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* done_bar = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,11 +104,16 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int x0 = xt * p.tw, y0 = yt * p.th, n0 = nt * p.nb;
         uint8_t* st = smem + stage * stage_bytes;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        mbar_arrive_expect_tx(&full_bar[stage], 2 * BOX_BYTES + p.bboxes * p.b_tx);
         // A: two 64-channel boxes (the second may be fully out of range -> zeros)
         tma_load_5d(st, &mapA, &full_bar[stage], m_tile * 128, x0, y0, n0, 0);
         tma_load_5d(st + BOX_BYTES, &mapA, &full_bar[stage], m_tile * 128 + 64, x0, y0, n0, 0);
         uint8_t* sb = st + 2 * BOX_BYTES;
+        if (p.shifted) {
+          // one box of KP+2 pixels starting one pixel to the left, on input row y + (filter row - 1)
+          for (int j = 0; j < p.nb64; ++j)
+            tma_load_5d(sb + j * p.bslot, mapB, &full_bar[stage], cB + j * 64, x0 - 1, y0 + tg - 1, n0, 0);
+        } else
         for (int t = 0; t < p.T; ++t) {
           for (int j = 0; j < p.nb64; ++j) {
             uint8_t* dst = sb + (t * p.nb64 + j) * BOX_BYTES;
@@ -135,8 +147,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int kk = 0; kk < KP / 16; ++kk) {
           const uint64_t adesc = make_smem_desc_sw128(sa + kk * 2048, BOX_BYTES, 1024);
           for (int t = 0; t < p.T; ++t) {
-            uint64_t bdesc = make_smem_desc_sw128(sb + t * p.nb64 * BOX_BYTES + kk * 2048 + p.dbg_shift * 128,
-                                                  BOX_BYTES, 1024);
+            // shifted: tap t = window starting t pixels (rows of 128 B) into the halo box
+            const uint32_t boff = p.shifted ? (uint32_t)(t * 128) : (uint32_t)(t * p.nb64 * BOX_BYTES);
+            uint64_t bdesc = make_smem_desc_sw128(sb + boff + kk * 2048 + p.dbg_shift * 128, p.bslot, 1024);
             bdesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
             umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
@@ -189,6 +202,7 @@ struct WgPlan {
   int T, tap_groups, taps_total, BNW, m_tiles, n_tiles, splits, kb_total, kb_per_split;
   int tw, th, nb, tiles_x, tiles_y, tiles_n;
   int Nb;
+  int shifted;
 };
 
 static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
@@ -216,6 +230,7 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   w->tiles_y = H / w->th;
   w->tiles_n = (B + w->nb - 1) / w->nb;
   w->kb_total = w->tiles_x * w->tiles_y * w->tiles_n;
+  w->shifted = (a->b_mode == SUNET_A_CONV3X3 && w->tw == KP && getenv("SUNET_WGRAD_NO_SHIFT") == nullptr) ? 1 : 0;
   const int base_items = w->m_tiles * w->n_tiles * w->tap_groups;
   int want = (2 * num_sms() + base_items - 1) / base_items;  // ~2 CTAs per SM worth of items
   if (want < 1) want = 1;
@@ -227,7 +242,8 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   return SUNET_OK;
 }
 
-static int make_map(CUtensorMap* m, const void* base, int gs, int C, int S, int B, int H, int W, const WgPlan& w) {
+static int make_map(CUtensorMap* m, const void* base, int gs, int C, int S, int B, int H, int W, const WgPlan& w,
+                    int halo = 0) {
   uint64_t dims[5], str[4];
   uint32_t box[5];
   const uint64_t e = 2;
@@ -235,7 +251,7 @@ static int make_map(CUtensorMap* m, const void* base, int gs, int C, int S, int 
     dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = B; dims[4] = 1;
     str[0] = (uint64_t)S * e; str[1] = (uint64_t)W * S * e; str[2] = (uint64_t)H * W * S * e;
     str[3] = (uint64_t)B * H * W * S * e;
-    box[0] = 64; box[1] = w.tw; box[2] = w.th; box[3] = w.nb; box[4] = 1;
+    box[0] = 64; box[1] = w.tw + halo; box[2] = w.th; box[3] = w.nb; box[4] = 1;
   } else {
     dims[0] = C; dims[1] = 2; dims[2] = W; dims[3] = 2; dims[4] = (uint64_t)B * H;
     str[0] = (uint64_t)S * e; str[1] = (uint64_t)2 * S * e; str[2] = (uint64_t)2 * W * S * e;
@@ -250,7 +266,7 @@ static int make_map(CUtensorMap* m, const void* base, int gs, int C, int S, int 
 using namespace sunet;
 
 extern "C" int sunet_wgrad_gemm_splits(const sunet_wgrad_gemm_args* a) {
-  WgPlan w;
+  WgPlan w{};
   if (!a || plan_wgrad(a, &w)) return -1;
   return w.splits;
 }
@@ -261,7 +277,7 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
   if (!a->a || !a->b0 || !a->partials) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: null tensor");
   if (a->batch <= 0 || a->height <= 0 || a->width <= 0) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: bad grid");
   if (a->b_mode == SUNET_A_GATHER2X2 && a->b1) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: gather takes one B");
-  WgPlan w;
+  WgPlan w{};
   int e = plan_wgrad(a, &w);
   if (e) return e;
   const size_t need = (size_t)w.splits * w.taps_total * a->a_channels * w.Nb * sizeof(float);
@@ -272,10 +288,11 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
   CUtensorMap mA, mB0, mB1;
   const int B = a->batch, H = a->height, W = a->width;
   if ((e = make_map(&mA, a->a, 0, a->a_channels, a->a_pix_stride, B, H, W, w))) return e;
-  if ((e = make_map(&mB0, a->b0, a->b_mode == SUNET_A_GATHER2X2, a->b0_channels, a->b0_pix_stride, B, H, W, w)))
+  const int halo = w.shifted ? 2 : 0;
+  if ((e = make_map(&mB0, a->b0, a->b_mode == SUNET_A_GATHER2X2, a->b0_channels, a->b0_pix_stride, B, H, W, w, halo)))
     return e;
   if (a->b1) {
-    if ((e = make_map(&mB1, a->b1, 0, a->b1_channels, a->b1_pix_stride, B, H, W, w))) return e;
+    if ((e = make_map(&mB1, a->b1, 0, a->b1_channels, a->b1_pix_stride, B, H, W, w, halo))) return e;
   } else {
     mB1 = mB0;
   }
@@ -298,20 +315,33 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
   }
   p.tmem_cols = 32;
   while (p.tmem_cols < w.T * w.BNW) p.tmem_cols *= 2;
-  const int stage_bytes = BOX_BYTES * (2 + w.T * p.nb64);
-  constexpr int STAGES = 5;
-  const int smem = STAGES * stage_bytes + 1024 + 256;
-  if (smem > 227 * 1024) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: smem %d too large", smem);
-  static int max_set = 0;
-  if (smem > max_set) {
-    if ((e = check_cuda(cudaFuncSetAttribute(wgrad_gemm_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  p.shifted = w.shifted;
+  if (w.shifted) {
+    p.bslot = 5 * 1024;              // (KP + 2) * 128 = 4352 bytes, padded to the 1024-byte swizzle atom
+    p.b_tx = (KP + 2) * 128;
+    p.bboxes = p.nb64;
+  } else {
+    p.bslot = BOX_BYTES;
+    p.b_tx = BOX_BYTES;
+    p.bboxes = w.T * p.nb64;
+  }
+  const int stage_bytes = 2 * BOX_BYTES + p.bboxes * p.bslot;
+  const int bar_bytes = (2 * MAX_STAGES + 2) * 8;
+  int stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: stage of %d bytes does not fit", stage_bytes);
+  p.stages = stages;
+  const int smem = stages * stage_bytes + 1024 + bar_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if ((e = check_cuda(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024),
                         "cudaFuncSetAttribute(wgrad_gemm)")))
       return e;
-    max_set = 227 * 1024;
+    attr_set = true;
   }
   const int grid = w.m_tiles * w.n_tiles * w.tap_groups * w.splits;
-  wgrad_gemm_kernel<STAGES><<<grid, WG_THREADS, smem, stream>>>(mA, mB0, mB1, p, stage_bytes);
+  wgrad_gemm_kernel<<<grid, WG_THREADS, smem, stream>>>(mA, mB0, mB1, p, stage_bytes);
   return check_launch("wgrad_gemm_kernel");
 }
 
