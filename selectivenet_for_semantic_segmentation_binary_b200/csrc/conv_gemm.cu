@@ -43,11 +43,15 @@ struct ConvGemmParams {
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  // KSP = 64-wide K steps per pipeline stage.  The narrow tiles finish a K step in 128 (BN=64) or 256
+  // (BN=128) tensor-core cycles, which is less than one mbarrier round trip of the single issuing thread;
+  // two K steps per stage halve the number of round trips.
+  static constexpr int KSP = (BN == 256) ? 1 : 2;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 bf16
   static constexpr int B_BYTES = BN * 128;       // BN rows x 64 bf16
   static constexpr int STG_BYTES = 128 * 128;    // one 64-column output chunk
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 2 * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * KSP * (A_BYTES + B_BYTES) + 2 * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -62,8 +66,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = sA + C::STAGES * C::A_BYTES;
-  uint8_t* sStg = sB + C::STAGES * C::B_BYTES;
+  uint8_t* sB = sA + C::STAGES * C::KSP * C::A_BYTES;
+  uint8_t* sStg = sB + C::STAGES * C::KSP * C::B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * C::STG_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]
@@ -113,28 +117,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const int yt = (mt / p.tiles_x) % p.tiles_y;
         const int nt = mt / (p.tiles_x * p.tiles_y);
         const int x0 = xt * p.tw, y0 = yt * p.th, n0 = nt * p.nb;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int tap = ks / cpt;
-          int cc = ks - tap * cpt;
-          const CUtensorMap* mapA = &mapA0;
-          if (cc >= p.cpt0) {
-            cc -= p.cpt0;
-            mapA = &mapA1;
-          }
+        for (int ks0 = 0; ks0 < ksteps; ks0 += C::KSP) {
+          const int nks = min(C::KSP, ksteps - ks0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
-          if (p.gs_load) {
-            tma_load_5d(sA + stage * C::A_BYTES, mapA, &full_bar[stage], cc * 64, tap & 1, x0, tap >> 1,
-                        n0 * p.H + y0);
-          } else {
-            int dx = 0, dy = 0;
-            if (p.taps == 9) {
-              dy = tap / 3 - 1;
-              dx = tap - (tap / 3) * 3 - 1;
+          mbar_arrive_expect_tx(&full_bar[stage], nks * (C::A_BYTES + C::B_BYTES));
+          for (int j = 0; j < nks; ++j) {
+            const int ks = ks0 + j;
+            const int tap = ks / cpt;
+            int cc = ks - tap * cpt;
+            const CUtensorMap* mapA = &mapA0;
+            if (cc >= p.cpt0) {
+              cc -= p.cpt0;
+              mapA = &mapA1;
             }
-            tma_load_5d(sA + stage * C::A_BYTES, mapA, &full_bar[stage], cc * 64, x0 + dx, y0 + dy, n0, 0);
+            uint8_t* dA = sA + (stage * C::KSP + j) * C::A_BYTES;
+            if (p.gs_load) {
+              tma_load_5d(dA, mapA, &full_bar[stage], cc * 64, tap & 1, x0, tap >> 1, n0 * p.H + y0);
+            } else {
+              int dx = 0, dy = 0;
+              if (p.taps == 9) {
+                dy = tap / 3 - 1;
+                dx = tap - (tap / 3) * 3 - 1;
+              }
+              tma_load_5d(dA, mapA, &full_bar[stage], cc * 64, x0 + dx, y0 + dy, n0, 0);
+            }
+            tma_load_2d(sB + (stage * C::KSP + j) * C::B_BYTES, &mapB, &full_bar[stage], ks * 64, n_tile * BN);
           }
-          tma_load_2d(sB + stage * C::B_BYTES, &mapB, &full_bar[stage], ks * 64, n_tile * BN);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -155,16 +163,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int ks0 = 0; ks0 < ksteps; ks0 += C::KSP) {
+          const int nks = min(C::KSP, ksteps - ks0);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * C::A_BYTES) + p.dbg_shift * 128, 16, 1024);
-          adesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * C::B_BYTES), 16, 1024);
+          for (int j = 0; j < nks; ++j) {
+            uint64_t adesc =
+                make_smem_desc_sw128(smem_u32(sA + (stage * C::KSP + j) * C::A_BYTES) + p.dbg_shift * 128, 16, 1024);
+            adesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
+            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + (stage * C::KSP + j) * C::B_BYTES), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // +32 bytes along K inside the 128B swizzle span = +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // +32 bytes along K inside the 128B swizzle span = +2 in the (addr >> 4) field
+              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks0 | j | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) {

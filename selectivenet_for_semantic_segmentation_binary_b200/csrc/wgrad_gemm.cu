@@ -22,8 +22,9 @@
 
 namespace sunet {
 
-constexpr int KP = 32;                 // pixels per pipeline stage (two K=16 MMA steps)
-constexpr int BOX_BYTES = KP * 128;    // one TMA box: KP pixels x 64 channels
+// Pixels per pipeline stage (kp) is chosen per launch (32, 64 or 128) so that one stage carries
+// several hundred tensor-core cycles of work: a stage hand-off costs the single issuing thread an
+// mbarrier round trip, which a 32-pixel stage of a 64-channel layer (192 cycles of MMA) cannot hide.
 constexpr int WG_THREADS = 192;
 
 struct WgradParams {
@@ -46,6 +47,8 @@ struct WgradParams {
   int b_tx;        // bytes one B box delivers
   int bboxes;      // B boxes per stage
   int stages;
+  int kp;          // pixels per stage
+  int abox;        // bytes of one A box = kp * 128
   float* out;      // [splits][taps_total][Ca][Nb]
 };
 constexpr int MAX_STAGES = 12;
@@ -104,11 +107,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int x0 = xt * p.tw, y0 = yt * p.th, n0 = nt * p.nb;
         uint8_t* st = smem + stage * stage_bytes;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], 2 * BOX_BYTES + p.bboxes * p.b_tx);
+        mbar_arrive_expect_tx(&full_bar[stage], 2 * p.abox + p.bboxes * p.b_tx);
         // A: two 64-channel boxes (the second may be fully out of range -> zeros)
         tma_load_5d(st, &mapA, &full_bar[stage], m_tile * 128, x0, y0, n0, 0);
-        tma_load_5d(st + BOX_BYTES, &mapA, &full_bar[stage], m_tile * 128 + 64, x0, y0, n0, 0);
-        uint8_t* sb = st + 2 * BOX_BYTES;
+        tma_load_5d(st + p.abox, &mapA, &full_bar[stage], m_tile * 128 + 64, x0, y0, n0, 0);
+        uint8_t* sb = st + 2 * p.abox;
         if (p.shifted) {
           // one box of KP+2 pixels starting one pixel to the left, on input row y + (filter row - 1)
           for (int j = 0; j < p.nb64; ++j)
@@ -116,7 +119,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         } else
         for (int t = 0; t < p.T; ++t) {
           for (int j = 0; j < p.nb64; ++j) {
-            uint8_t* dst = sb + (t * p.nb64 + j) * BOX_BYTES;
+            uint8_t* dst = sb + (t * p.nb64 + j) * p.bslot;
             const int c = cB + j * 64;
             if (p.mode == SUNET_A_GATHER2X2) {
               tma_load_5d(dst, mapB, &full_bar[stage], c, t & 1, x0, t >> 1, n0 * p.H + y0);
@@ -142,13 +145,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-        const uint32_t sb = sa + 2 * BOX_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < KP / 16; ++kk) {
-          const uint64_t adesc = make_smem_desc_sw128(sa + kk * 2048, BOX_BYTES, 1024);
+        const uint32_t sb = sa + 2 * p.abox;
+        for (int kk = 0; kk < p.kp / 16; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(sa + kk * 2048, p.abox, 1024);
           for (int t = 0; t < p.T; ++t) {
             // shifted: tap t = window starting t pixels (rows of 128 B) into the halo box
-            const uint32_t boff = p.shifted ? (uint32_t)(t * 128) : (uint32_t)(t * p.nb64 * BOX_BYTES);
+            const uint32_t boff = p.shifted ? (uint32_t)(t * 128) : (uint32_t)(t * p.nb64 * p.bslot);
             uint64_t bdesc = make_smem_desc_sw128(sb + boff + kk * 2048 + p.dbg_shift * 128, p.bslot, 1024);
             bdesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
             umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
@@ -203,6 +205,7 @@ struct WgPlan {
   int tw, th, nb, tiles_x, tiles_y, tiles_n;
   int Nb;
   int shifted;
+  int kp;
 };
 
 static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
@@ -221,18 +224,34 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   w->m_tiles = (a->a_channels + 127) / 128;
   w->n_tiles = w->Nb / w->BNW;
   const int B = a->batch, H = a->height, W = a->width;
-  w->tw = pow2_div(W, KP);
-  w->th = pow2_div(H, KP / w->tw);
-  w->nb = KP / (w->tw * w->th);
-  if (w->nb > 1 && w->th != H)
-    return set_error(SUNET_ERR_INVALID, "wgrad_gemm: cannot tile %d x %d x %d into %d-pixel blocks", B, H, W, KP);
+  // stage size: aim at >= ~768 MMA cycles per stage = (kp/16) * T * BNW/2
+  int kp = (w->BNW == 128) ? 64 : 128;
+  if (w->T == 1) kp = 128;
+  {
+    const char* e = getenv("SUNET_WGRAD_KP");
+    if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) kp = atoi(e);
+  }
+  // never make a stage larger than the whole problem (tiny test shapes)
+  while (kp > 32 && (long long)B * H * W < 2LL * kp) kp /= 2;
+  // a stage must be whole image rows (or a power-of-two piece of one): shrink until it tiles
+  for (;;) {
+    w->tw = pow2_div(W, kp);
+    w->th = pow2_div(H, kp / w->tw);
+    w->nb = kp / (w->tw * w->th);
+    if (!(w->nb > 1 && w->th != H)) break;
+    if (kp == 32)
+      return set_error(SUNET_ERR_INVALID, "wgrad_gemm: cannot tile %d x %d x %d into pixel blocks", B, H, W);
+    kp /= 2;
+  }
+  w->kp = kp;
   w->tiles_x = W / w->tw;
   w->tiles_y = H / w->th;
   w->tiles_n = (B + w->nb - 1) / w->nb;
   w->kb_total = w->tiles_x * w->tiles_y * w->tiles_n;
-  w->shifted = (a->b_mode == SUNET_A_CONV3X3 && w->tw == KP && getenv("SUNET_WGRAD_NO_SHIFT") == nullptr) ? 1 : 0;
+  w->shifted = (a->b_mode == SUNET_A_CONV3X3 && w->tw == kp && getenv("SUNET_WGRAD_NO_SHIFT") == nullptr) ? 1 : 0;
   const int base_items = w->m_tiles * w->n_tiles * w->tap_groups;
-  int want = (2 * num_sms() + base_items - 1) / base_items;  // ~2 CTAs per SM worth of items
+  // two full waves of CTAs (one CTA per SM at a time): round DOWN so no third, nearly empty wave appears
+  int want = (2 * num_sms()) / base_items;
   if (want < 1) want = 1;
   int max_splits = (w->kb_total + 7) / 8;  // at least 8 k-blocks per CTA when possible
   if (max_splits < 1) max_splits = 1;
@@ -316,16 +335,18 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
   p.tmem_cols = 32;
   while (p.tmem_cols < w.T * w.BNW) p.tmem_cols *= 2;
   p.shifted = w.shifted;
+  p.kp = w.kp;
+  p.abox = w.kp * 128;
   if (w.shifted) {
-    p.bslot = 5 * 1024;              // (KP + 2) * 128 = 4352 bytes, padded to the 1024-byte swizzle atom
-    p.b_tx = (KP + 2) * 128;
+    p.b_tx = (w.kp + 2) * 128;                       // kp + 2 halo pixels
+    p.bslot = (p.b_tx + 1023) / 1024 * 1024;         // padded to the 1024-byte swizzle atom
     p.bboxes = p.nb64;
   } else {
-    p.bslot = BOX_BYTES;
-    p.b_tx = BOX_BYTES;
+    p.bslot = p.abox;
+    p.b_tx = p.abox;
     p.bboxes = w.T * p.nb64;
   }
-  const int stage_bytes = 2 * BOX_BYTES + p.bboxes * p.bslot;
+  const int stage_bytes = 2 * p.abox + p.bboxes * p.bslot;
   const int bar_bytes = (2 * MAX_STAGES + 2) * 8;
   int stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
