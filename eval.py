@@ -1,0 +1,141 @@
+"""eval.py with the reference's command line (/root/reference/eval.py:16-57), B200-native underneath.
+
+    python3 eval.py --model_dir ./model --selective 1 --select_eval 1 --local_rank 0 1 2 3 4 5 6 7 --synthetic 10000
+
+Forward in eval mode (BatchNorm folded from running statistics), thresholding with the float32 numpy
+semantics of eval.py:175-179 (`--cut_off`, `--s_cut_off`, `--single_scale`) and the coverage-masked
+confusion matrix, all on the GPU; patches are sharded across the ids of ``--local_rank`` (one process per
+GPU) and the six integer counters are all-reduced once at the end.  Single checkpoint only (the
+reference's ensemble branch does not support selection and is out of scope).
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_arguments(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--data_dir', type=str, default='./data')
+    parser.add_argument('--test_fold', type=int, default=1, help='which fold in 5-fold cv')
+    parser.add_argument('--input_type', type=str, default='RGB')
+    parser.add_argument('--patch_mag', type=int, default=200)
+    parser.add_argument('--patch_size', type=int, default=256)
+    parser.add_argument('--n_cls', type=int, default=2)
+    parser.add_argument('--batch_size', type=int, default=16)
+    parser.add_argument('--num_workers', type=int, default=16, help='Dataloader num_workers')
+    parser.add_argument('--model_dir', type=str, default='*/model', help='network ckpt (.pth) directory')
+    parser.add_argument('--model_arch', type=str, nargs='+', default=['UNet_B'], choices=['UNet_B'])
+    parser.add_argument('--selective', type=bool, default=False, help='Is the network based on SelectiveNet?')
+    parser.add_argument('--select_eval', type=bool, default=False, help='calculate metrics with/without selection')
+    parser.add_argument('--output_dim', type=str, default='NHW', choices=['NCHW', 'NHW'])
+    parser.add_argument('--single_scale', type=str, default='sigmoid', choices=['None', 'clip', 'sigmoid', 'minmax'])
+    parser.add_argument('--ens_scale', type=str, default='None', choices=['None', 'clip', 'sigmoid', 'minmax'])
+    parser.add_argument('--cut_off', type=float, default=0.5, help='prob > cut_off -> pred: 1')
+    parser.add_argument('--s_cut_off', type=float, default=0.5, help='selection > cut_off -> select: 1')
+    parser.add_argument('--local_rank', type=int, nargs='+', default=[0], help='local gpu ids')
+    parser.add_argument('--info_print', type=bool, default=False)
+    parser.add_argument('--save_dir', type=str, default='./output', help='saving results')
+    # additions
+    parser.add_argument('--synthetic', type=int, default=0, help='evaluate this many synthetic patches')
+    parser.add_argument('--random_init', type=bool, default=False, help='no checkpoint: seeded random weights')
+    parser.add_argument('--master_port', type=int, default=29534)
+    args = parser.parse_args(argv)
+    print('')
+    print('args={}\n'.format(args))
+    return args
+
+
+def eval_worker(rank, world, args, ret=None):
+    import torch.distributed as dist
+    from selectivenet_for_semantic_segmentation_binary_b200.model import UNet_B
+    from selectivenet_for_semantic_segmentation_binary_b200.trainer import chunk_bounds
+    from selectivenet_for_semantic_segmentation_binary_b200.utils.compute_metric import Evaluator
+    from selectivenet_for_semantic_segmentation_binary_b200.utils.net_utils import net_test_load
+
+    gpu = args.local_rank[rank]
+    torch.cuda.set_device(gpu)
+    dev = torch.device('cuda', gpu)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', str(args.master_port))
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    torch.manual_seed(0)
+    net = UNet_B(args.input_type, selective=args.selective)
+    if not args.random_init:
+        model_list = sorted([c for c in os.listdir(args.model_dir) if 'pth' in c])
+        if len(model_list) != 1:
+            raise SystemExit(f'expected exactly one checkpoint in {args.model_dir} (ensembles are out of scope)')
+        net = net_test_load(os.path.join(args.model_dir, model_list[0]), net, device='cpu')
+    net = net.to(dev)
+    net.train(False)
+    if args.select_eval and not args.selective:
+        raise SystemExit('--select_eval needs --selective')
+    evaluator = Evaluator(num_class=args.n_cls, selective=args.select_eval, device=dev)
+    if args.single_scale not in ('sigmoid', 'None'):
+        raise SystemExit("--single_scale clip/minmax are not built (DESIGN.md §6)")
+
+    n_total = args.synthetic
+    if n_total <= 0:
+        raise SystemExit('no dataset ships with the reference: pass --synthetic N (DESIGN.md §6)')
+    lo, hi = chunk_bounds(n_total, world, rank)
+    in_ch, size, bs = net.input_ch, args.patch_size, args.batch_size
+    print("Model Prediction...") if rank == 0 else None
+    with torch.no_grad():
+        for start in range(lo, hi, bs):
+            n = min(bs, hi - start)
+            g = torch.Generator(device=dev).manual_seed(1000 + start)       # batch content depends only on its position
+            x = torch.rand(n, in_ch, size, size, generator=g, device=dev) * 2 - 1
+            label = (torch.rand(n, size, size, generator=g, device=dev) < 0.4).to(torch.uint8)
+            if args.selective:
+                output, selection, _ = net(x)
+            else:
+                output, selection = net(x), None
+            evaluator.add_batch_from_logits(label, output, selection if args.select_eval else None,
+                                            cut_off=args.cut_off, s_cut_off=args.s_cut_off, path='eval',
+                                            scale=args.single_scale)
+    counts = evaluator.counts_tensor().clone()
+    if world > 1:
+        dist.all_reduce(counts)
+        dist.destroy_process_group()
+    if rank == 0:
+        c = counts.cpu().numpy()
+        final = Evaluator(num_class=args.n_cls, selective=args.select_eval)
+        final.confusion_matrix = c[:4].reshape(2, 2).astype(np.float64)
+        CM = final.Confusion_Matrix()
+        Acc = final.get_Pixel_Accuracy()
+        Acc_class = final.get_Pixel_Accuracy_Class()
+        Prec = final.get_Precision()
+        Recall = final.get_Recall()
+        F1_Score = final.get_F1_Score(Prec, Recall)
+        mIoU = final.get_mIoU()
+        IoU_class = final.get_IoU_Class()
+        if args.select_eval:
+            print(f'    rejection ratio: {round(float(c[5] - c[4]) / float(c[5]), 3)}')
+        print(f'    Acc:{Acc}')
+        print(f'    Acc_class:{Acc_class}')
+        print(f'    Prec:{Prec}, Recall:{Recall}, F1_Score:{F1_Score}')
+        print(f'    mIoU:{mIoU}')
+        print(f'    IoU_class:{IoU_class}')
+        if ret is not None:
+            ret['counts'] = c.tolist()
+        return CM
+
+
+def main(argv=None):
+    args = parse_arguments(argv)
+    world = len(args.local_rank)
+    if world == 1:
+        return eval_worker(0, 1, args)
+    import torch.multiprocessing as mp
+    mp.spawn(eval_worker, args=(world, args), nprocs=world, join=True)
+
+
+if __name__ == '__main__':
+    main()

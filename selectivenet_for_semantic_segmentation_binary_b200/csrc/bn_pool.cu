@@ -65,6 +65,36 @@ __global__ void pack_input_im2col_kernel(const float* __restrict__ x, bf16x8* __
   }
 }
 
+// one thread = one pixel: 9*CIN coalesced fp32 loads (lanes = consecutive x), eight 16-byte stores
+template <int CIN>
+__global__ void __launch_bounds__(256)
+pack_input_im2col_t_kernel(const float* __restrict__ x, bf16x8* __restrict__ out, int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float f[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) f[k] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      const bool in = sy >= 0 && sy < H && sx >= 0 && sx < W;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+        if (in) f[tap * CIN + ci] = __ldg(x + (((long long)n * CIN + ci) * H + sy) * W + sx);
+    }
+    bf16x8* o = out + pix * 8;
+    bf16x8 z = {{0u, 0u, 0u, 0u}};
+#pragma unroll
+    for (int g = 0; g < 4; ++g) o[g] = pack8(f + g * 8);
+#pragma unroll
+    for (int g = 4; g < 8; ++g) o[g] = z;
+  }
+}
+
 __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                     __nv_bfloat16* __restrict__ wd, int co_n, int ci_n) {
   const long long total = (long long)co_n * ci_n * 9;
@@ -385,6 +415,150 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bf
   }
 }
 
+
+// ------------------------------------------------------------------ non-pooled fast paths
+// Same math as the templates above for the layers that are not followed by a max-pool (11 of 14), with
+// the per-channel vectors hoisted out of the loop and FOUR independent 16-byte loads per operand in
+// flight per thread: these kernels are pure HBM streams and latency, not arithmetic, limits them.
+constexpr int EW_U = 4;
+
+struct ChanVec {
+  float v[8];
+};
+__device__ __forceinline__ ChanVec load_chan(const float* __restrict__ p, int g) {
+  ChanVec c;
+  *reinterpret_cast<float4*>(c.v) = __ldg(reinterpret_cast<const float4*>(p + g * 8));
+  *reinterpret_cast<float4*>(c.v + 4) = __ldg(reinterpret_cast<const float4*>(p + g * 8 + 4));
+  return c;
+}
+
+__global__ void __launch_bounds__(256)
+bn_relu_flat_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
+                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int as, long long total, int G) {
+  const int g = threadIdx.x % G;                 // 256 % G == 0 and every stride below is a multiple of 256
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
+  for (long long i0 = blockIdx.x * (long long)(256 * EW_U) + threadIdx.x; i0 < total;
+       i0 += (long long)gridDim.x * 256 * EW_U) {
+    bf16x8 v[EW_U];
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const long long i = i0 + u * 256;
+      if (i < total) v[u] = *reinterpret_cast<const bf16x8*>(y + (i / G) * ys + g * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const long long i = i0 + u * 256;
+      if (i < total) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc.v[j], sh.v[j]), 0.f);
+        *reinterpret_cast<bf16x8*>(a + (i / G) * as + g * 8) = pack8(f);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ y, int ys,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          float* __restrict__ partials, long long total, int C) {
+  __shared__ float red[256][17];
+  const int G = C >> 3;
+  const int g = threadIdx.x % G;
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g), mu = load_chan(mean, g), is = load_chan(invstd, g);
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (long long i0 = blockIdx.x * (long long)(256 * EW_U) + threadIdx.x; i0 < total;
+       i0 += (long long)gridDim.x * 256 * EW_U) {
+    bf16x8 vy[EW_U], vg[EW_U];
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const long long i = i0 + u * 256;
+      if (i < total) {
+        vy[u] = *reinterpret_cast<const bf16x8*>(y + (i / G) * ys + g * 8);
+        vg[u] = *reinterpret_cast<const bf16x8*>(dA + (i / G) * das + g * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const long long i = i0 + u * 256;
+      if (i < total) {
+        float fy[8], fg[8];
+        unpack8(vy[u], fy);
+        unpack8(vg[u], fg);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float act = round_bf16(fmaxf(fmaf(fy[j], sc.v[j], sh.v[j]), 0.f));
+          const float gg = act > 0.f ? fg[j] : 0.f;
+          acc[j] += gg;
+          acc[8 + j] = fmaf(gg, (fy[j] - mu.v[j]) * is.v[j], acc[8 + j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  const int reps = 256 / G;
+  for (int o = threadIdx.x; o < G * 16; o += 256) {
+    const int og = o >> 4, oj = o & 15;
+    float s = 0.f;
+    for (int r = 0; r < reps; ++r) s += red[r * G + og][oj];
+    const int c = og * 8 + (oj & 7);
+    partials[((size_t)blockIdx.x * C + c) * 2 + (oj >> 3)] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ y, int ys,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy, int dys, long long total,
+                         int C) {
+  const int G = C >> 3;
+  const int g = threadIdx.x % G;
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
+  const ChanVec kg = load_chan(coef, g), k1 = load_chan(coef + C, g), k0 = load_chan(coef + 2 * C, g);
+  for (long long i0 = blockIdx.x * (long long)(256 * EW_U) + threadIdx.x; i0 < total;
+       i0 += (long long)gridDim.x * 256 * EW_U) {
+    bf16x8 vy[EW_U], vg[EW_U];
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const long long i = i0 + u * 256;
+      if (i < total) {
+        vy[u] = *reinterpret_cast<const bf16x8*>(y + (i / G) * ys + g * 8);
+        vg[u] = *reinterpret_cast<const bf16x8*>(dA + (i / G) * das + g * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_U; ++u) {
+      const long long i = i0 + u * 256;
+      if (i < total) {
+        float fy[8], fg[8], o[8];
+        unpack8(vy[u], fy);
+        unpack8(vg[u], fg);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float act = round_bf16(fmaxf(fmaf(fy[j], sc.v[j], sh.v[j]), 0.f));
+          const float gg = act > 0.f ? fg[j] : 0.f;
+          o[j] = fmaf(kg.v[j], gg, fmaf(k1.v[j], fy[j], k0.v[j]));
+        }
+        *reinterpret_cast<bf16x8*>(dy + (i / G) * dys + g * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+static inline int flat_grid(long long total) {
+  long long b = (total + 256 * EW_U - 1) / (256 * EW_U);
+  const long long cap = (long long)num_sms() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
 }  // namespace sunet
 
 using namespace sunet;
@@ -396,8 +570,15 @@ extern "C" int sunet_pack_input_im2col(const float* x, void* out, int batch, int
   if (!x || !out || batch <= 0 || cin <= 0 || cin * 9 > 64 || height <= 0 || width <= 0)
     return set_error(SUNET_ERR_INVALID, "pack_input_im2col: bad arguments (cin=%d)", cin);
   const long long total = (long long)batch * height * width * 8;
-  pack_input_im2col_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(x, reinterpret_cast<bf16x8*>(out), batch, cin,
-                                                                     height, width);
+  if (cin == 3)
+    pack_input_im2col_t_kernel<3><<<ew_grid(total / 8, 256), 256, 0, STREAM>>>(x, reinterpret_cast<bf16x8*>(out), batch,
+                                                                               height, width);
+  else if (cin == 2)
+    pack_input_im2col_t_kernel<2><<<ew_grid(total / 8, 256), 256, 0, STREAM>>>(x, reinterpret_cast<bf16x8*>(out), batch,
+                                                                               height, width);
+  else
+    pack_input_im2col_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(x, reinterpret_cast<bf16x8*>(out), batch, cin,
+                                                                       height, width);
   return check_launch("pack_input_im2col");
 }
 
@@ -485,9 +666,13 @@ extern "C" int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* 
         batch, height, width, channels);
   } else {
     const long long total = (long long)batch * height * width * (channels / 8);
-    bn_relu_pool_kernel<false><<<ew_grid(total, 256), 256, 0, STREAM>>>(yp, y_pix_stride, scale, shift, ap,
-                                                                         a_pix_stride, nullptr, 0, batch, height,
-                                                                         width, channels);
+    if (256 % (channels / 8) == 0)
+      bn_relu_flat_kernel<<<flat_grid(total), 256, 0, STREAM>>>(yp, y_pix_stride, scale, shift, ap, a_pix_stride, total,
+                                                                channels / 8);
+    else
+      bn_relu_pool_kernel<false><<<ew_grid(total, 256), 256, 0, STREAM>>>(yp, y_pix_stride, scale, shift, ap,
+                                                                           a_pix_stride, nullptr, 0, batch, height,
+                                                                           width, channels);
   }
   return check_launch("bn_relu_pool");
 }
@@ -528,9 +713,8 @@ extern "C" int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const v
                                                             y_pix_stride, scale, shift, mean, invstd, partials, batch,
                                                             height, width, channels);
   else
-    bn_bwd_reduce_kernel<false><<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, nullptr, 0, yp, y_pix_stride, scale,
-                                                             shift, mean, invstd, partials, batch, height, width,
-                                                             channels);
+    bn_bwd_reduce_flat_kernel<<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, yp, y_pix_stride, scale, shift, mean,
+                                                           invstd, partials, total, channels);
   if ((e = check_launch("bn_bwd_reduce"))) return e;
   bn_bwd_finalize_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(partials, blocks, channels, count, scale, mean,
                                                                       invstd, dgamma, dbeta, coef);
@@ -541,8 +725,7 @@ extern "C" int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const v
                                                             scale, shift, coef, dyp, dy_pix_stride, batch, height,
                                                             width, channels);
   else
-    bn_bwd_apply_kernel<false><<<ablocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, nullptr, 0, yp, y_pix_stride, scale,
-                                                             shift, coef, dyp, dy_pix_stride, batch, height, width,
-                                                             channels);
+    bn_bwd_apply_flat_kernel<<<flat_grid(total), 256, 0, STREAM>>>(dAp, dA_pix_stride, yp, y_pix_stride, scale, shift,
+                                                                    coef, dyp, dy_pix_stride, total, channels);
   return check_launch("bn_bwd_apply");
 }

@@ -100,32 +100,47 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
   for (int h = 0; h < 3; ++h)
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw[h][j] = 0.f;
-  const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
-  for (long long p = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3); p < P; p += stride) {
-    float g[3];
+  // four pixels per thread per trip: all loads are issued before any is consumed
+  constexpr int U = 4;
+  const long long ppb = (long long)(blockDim.x >> 3);                 // pixels per block per sub-trip
+  for (long long p0 = blockIdx.x * ppb * U + (threadIdx.x >> 3); p0 < P; p0 += (long long)gridDim.x * ppb * U) {
+    float g[U][3];
+    bf16x8 v[U];
 #pragma unroll
-    for (int h = 0; h < 3; ++h) g[h] = (h < nheads) ? __ldg(dl + (long long)h * P + p) : 0.f;
-    const bf16x8 v = *reinterpret_cast<const bf16x8*>(a + p * as + sub * 8);
-    float av[8];
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * ppb;
+      if (p < P) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      av[2 * i] = bf16lo(v.w[i]);
-      av[2 * i + 1] = bf16hi(v.w[i]);
+        for (int h = 0; h < 3; ++h) g[u][h] = (h < nheads) ? __ldg(dl + (long long)h * P + p) : 0.f;
+        v[u] = *reinterpret_cast<const bf16x8*>(a + p * as + sub * 8);
+      }
     }
-    float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o[j] = g[0] * w[0][j] + g[1] * w[1][j] + g[2] * w[2][j];
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * ppb;
+      if (p < P) {
+        float av[8];
 #pragma unroll
-      for (int h = 0; h < 3; ++h) dw[h][j] = fmaf(g[h], av[j], dw[h][j]);
-    }
-    bf16x8 ov;
+        for (int i = 0; i < 4; ++i) {
+          av[2 * i] = bf16lo(v[u].w[i]);
+          av[2 * i + 1] = bf16hi(v[u].w[i]);
+        }
+        float o[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ov.w[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
-    *reinterpret_cast<bf16x8*>(dA + p * das + sub * 8) = ov;
-    if (sub == 0) {
+        for (int j = 0; j < 8; ++j) {
+          o[j] = g[u][0] * w[0][j] + g[u][1] * w[1][j] + g[u][2] * w[2][j];
 #pragma unroll
-      for (int h = 0; h < 3; ++h) db[h] += g[h];
+          for (int h = 0; h < 3; ++h) dw[h][j] = fmaf(g[u][h], av[j], dw[h][j]);
+        }
+        bf16x8 ov;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ov.w[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<bf16x8*>(dA + p * das + sub * 8) = ov;
+        if (sub == 0) {
+#pragma unroll
+          for (int h = 0; h < 3; ++h) db[h] += g[u][h];
+        }
+      }
     }
   }
 #pragma unroll

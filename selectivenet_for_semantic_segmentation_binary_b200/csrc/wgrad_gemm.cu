@@ -194,6 +194,129 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------ 64-output-channel variant
+// conv3x3 layers with Cout = 64 (the three full-resolution layers = the largest pixel counts) would
+// waste half of an M=128 tile on dY.  Here the roles are swapped: N = the 64 dY channels, and M = 128 =
+// TWO filter taps x 64 input channels, stacked through the descriptor's leading-dimension stride: the
+// second 64-row block of the A operand is simply the same halo tile shifted by (tap_b - tap_a) pixels.
+// All nine taps (five tap pairs, 5 x 64 TMEM columns) and all three halo rows live in one CTA, so each
+// dY pixel block is read once for the whole 3x3 filter.
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX0,
+               const __grid_constant__ CUtensorMap mapX1, const WgradParams p, const int stage_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* done_bar = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapDy);
+    tma_prefetch_desc(&mapX0);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tile = blockIdx.x % p.n_tiles;       // which 64-channel block of the (concatenated) input
+  const int split = blockIdx.x / p.n_tiles;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mapX = (n_tile < p.c0_blocks) ? &mapX0 : &mapX1;
+      const int cX = ((n_tile < p.c0_blocks) ? n_tile : (n_tile - p.c0_blocks)) * 64;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int xt = kb % p.tiles_x;
+        const int y = (kb / p.tiles_x) % p.tiles_y;
+        const int n = kb / (p.tiles_x * p.tiles_y);
+        const int x0 = xt * p.kp;
+        uint8_t* st = smem + stage * stage_bytes;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], p.abox + 3 * p.b_tx);
+        tma_load_5d(st, &mapDy, &full_bar[stage], 0, x0, y, n, 0);
+        for (int r = 0; r < 3; ++r)
+          tma_load_5d(st + p.abox + r * p.bslot, mapX, &full_bar[stage], cX, x0 - 1, y + r - 1, n, 0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t sdy = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sx = sdy + p.abox;
+        for (int kk = 0; kk < p.kp / 16; ++kk) {
+          const uint64_t bdesc = make_smem_desc_sw128(sdy + kk * 2048, 1024, 1024);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int ta = 2 * j, tb = 2 * j + 1;
+            const uint32_t offa = (ta / 3) * p.bslot + (ta % 3) * 128;
+            const uint32_t offb = (j < 4) ? (uint32_t)((tb / 3) * p.bslot + (tb % 3) * 128) : offa + 128;
+            const uint64_t adesc = make_smem_desc_sw128(sx + offa + kk * 2048, offb - offa, 1024);
+            umma_bf16(tmem_base + j * 64, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int half = row >> 6, ci = row & 63;
+    mbar_wait(done_bar, 0);
+    tc_fence_after_sync();
+    for (int j = 0; j < 5; ++j) {
+      const int tap = 2 * j + half;
+      uint32_t v[64];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + j * 64;
+      tmem_ld_32x32b_x32(taddr, v);
+      tmem_ld_32x32b_x32(taddr + 32, v + 32);
+      tmem_ld_wait();
+      if (tap < 9) {
+        // out[split][tap][co][ci]: for a fixed co the 32 lanes write 32 consecutive floats
+        float* o = p.out + ((static_cast<size_t>(split) * 9 + tap) * 64) * p.Nb + n_tile * 64 + ci;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) o[static_cast<size_t>(c) * p.Nb] = __uint_as_float(v[c]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int pow2_div(int v, int cap) {
   int t = 1;
   while (t < cap && (v % (t * 2)) == 0) t *= 2;
@@ -206,6 +329,7 @@ struct WgPlan {
   int Nb;
   int shifted;
   int kp;
+  int stacked;     // wgrad64_kernel
 };
 
 static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
@@ -224,6 +348,24 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   w->m_tiles = (a->a_channels + 127) / 128;
   w->n_tiles = w->Nb / w->BNW;
   const int B = a->batch, H = a->height, W = a->width;
+  w->stacked = (a->b_mode == SUNET_A_CONV3X3 && a->a_channels == 64 && W % 64 == 0 &&
+                getenv("SUNET_WGRAD_NO_STACK") == nullptr) ? 1 : 0;
+  if (w->stacked) {
+    w->kp = 64;
+    w->tw = 64; w->th = 1; w->nb = 1;
+    w->tiles_x = W / 64; w->tiles_y = H; w->tiles_n = B;
+    w->kb_total = w->tiles_x * H * B;
+    w->n_tiles = w->Nb / 64;
+    w->m_tiles = 1;
+    w->shifted = 1;
+    int want = (2 * num_sms()) / w->n_tiles;
+    if (want < 1) want = 1;
+    int max_splits = (w->kb_total + 7) / 8;
+    if (want > max_splits) want = max_splits;
+    w->kb_per_split = (w->kb_total + want - 1) / want;
+    w->splits = (w->kb_total + w->kb_per_split - 1) / w->kb_per_split;
+    return SUNET_OK;
+  }
   // stage size: aim at >= ~768 MMA cycles per stage = (kp/16) * T * BNW/2
   int kp = (w->BNW == 128) ? 64 : 128;
   if (w->T == 1) kp = 128;
@@ -314,6 +456,33 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     if ((e = make_map(&mB1, a->b1, 0, a->b1_channels, a->b1_pix_stride, B, H, W, w, halo))) return e;
   } else {
     mB1 = mB0;
+  }
+  if (w.stacked) {
+    if (a->b1 && (a->b0_channels % 64)) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: b0 channels vs tile");
+    WgradParams q{};
+    q.mode = a->b_mode;
+    q.n_tiles = w.n_tiles; q.splits = w.splits; q.kb_total = w.kb_total; q.kb_per_split = w.kb_per_split;
+    q.tiles_x = w.tiles_x; q.tiles_y = w.tiles_y;
+    q.c0_blocks = a->b0_channels / 64;
+    q.Ca = 64; q.Nb = w.Nb; q.taps_total = 9;
+    q.out = a->partials;
+    q.kp = w.kp; q.abox = w.kp * 128;
+    q.b_tx = (w.kp + 2) * 128;
+    q.bslot = (q.b_tx + 1023) / 1024 * 1024;
+    const int sbytes = q.abox + 3 * q.bslot;
+    const int bbytes = (2 * MAX_STAGES + 2) * 8;
+    int st = (227 * 1024 - 1024 - bbytes) / sbytes;
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    q.stages = st;
+    static bool attr64 = false;
+    if (!attr64) {
+      if ((e = check_cuda(cudaFuncSetAttribute(wgrad64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               227 * 1024), "cudaFuncSetAttribute(wgrad64)")))
+        return e;
+      attr64 = true;
+    }
+    wgrad64_kernel<<<w.n_tiles * w.splits, WG_THREADS, st * sbytes + 1024 + bbytes, stream>>>(mA, mB0, mB1, q, sbytes);
+    return check_launch("wgrad64_kernel");
   }
   WgradParams p;
   p.mode = a->b_mode;
