@@ -62,12 +62,13 @@ typedef struct sunet_conv_gemm_args {
   void* dst;                   /* NHWC bf16; SCATTER2X2: [batch][2*height][2*width][n_total/4],   */
   int dst_pix_stride;          /*   column n = (a*2+b)*C' + co goes to pixel (2y+a, 2x+b), chan co */
   int d_mode;
-  float* stats;                /* optional fp32 [sunet_conv_gemm_stat_rows()][n_total][2]:        */
+  float* stats;                /* optional fp32 [sunet_conv_gemm_stat_rows(args)][n_total][2]:    */
                                /*   per-CTA partial (sum, sum of squares) of the bf16 outputs     */
 } sunet_conv_gemm_args;
 
 int sunet_conv_gemm(const sunet_conv_gemm_args* args, sunet_stream_t stream);
-int sunet_conv_gemm_stat_rows(int batch, int height, int width, int n_total);
+/* rows of `stats` the call described by args will write (args->stats itself is ignored) */
+int sunet_conv_gemm_stat_rows(const sunet_conv_gemm_args* args);
 
 /* ------------------------------------------------------------------------------------------
  * G2: weight-gradient GEMM over pixels, split-K with fp32 partials.

@@ -50,7 +50,7 @@ def conv3x3_case(K, B, H, W, Cin, Cout, dual=False, stats=True):
     wd = torch.empty(Cin, 9 * Cout, dtype=torch.bfloat16, device=dev)
     K.pack_conv3x3_weights(w, wf, wd)
     y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
-    rows = K.conv_gemm_stat_rows(B, H, W, Cout)
+    rows = K.conv_gemm_stat_rows(B, H, W, Cout, K.A_CONV3X3)
     st = torch.zeros(rows, Cout, 2, device=dev)
     if dual:
         c0 = Cin // 2

@@ -60,7 +60,7 @@ SIGNATURES = {
     "sunet_last_error": [],
     "sunet_launch_count": [],
     "sunet_conv_gemm":[C.POINTER(ConvGemmArgs), _vp],
-    "sunet_conv_gemm_stat_rows": [_i, _i, _i, _i],
+    "sunet_conv_gemm_stat_rows": [C.POINTER(ConvGemmArgs)],
     "sunet_wgrad_gemm": [C.POINTER(WgradGemmArgs), _vp],
     "sunet_wgrad_gemm_splits": [C.POINTER(WgradGemmArgs)],
     "sunet_wgrad_reduce": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],

@@ -38,6 +38,10 @@ _ENC = [("encoder_layer_1_1", 1, "first"), ("encoder_layer_1_2", 1, "conv"),
 _CH = {1: 64, 2: 128, 3: 256, 4: 512}
 
 
+def kind_first(ly) -> bool:
+    return ly.kind == "first"
+
+
 class _Layer:
     """One CBR block: buffers + parameter handles."""
 
@@ -102,7 +106,7 @@ class SUNetPlan:
             kdim = 64 if ly.kind == "first" else 9 * ly.cin
             ly.wf = torch.empty(ly.cout, kdim, dtype=bf, device=dev)
             ly.wd = None if ly.kind == "first" else torch.empty(ly.cin, 9 * ly.cout, dtype=bf, device=dev)
-            ly.stat_rows = K.conv_gemm_stat_rows(B, h, w, ly.cout)
+            ly.stat_rows = K.conv_gemm_stat_rows(B, h, w, ly.cout, K.A_PLAIN if kind_first(ly) else K.A_CONV3X3)
             ly.stats = torch.zeros(ly.stat_rows, ly.cout, 2, device=dev)
             ly.scale, ly.shift, ly.mean, ly.invstd = (torch.empty(ly.cout, device=dev) for _ in range(4))
         self.pool = {L: act(L + 1, _CH[L]) for L in (1, 2, 3)}   # pooled encoder output of level L

@@ -46,8 +46,13 @@ def new_workspace(device) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- G1
-def conv_gemm_stat_rows(batch: int, height: int, width: int, n_total: int) -> int:
-    r = _lib.load().sunet_conv_gemm_stat_rows(batch, height, width, n_total)
+def conv_gemm_stat_rows(batch: int, height: int, width: int, n_total: int, a_mode: int = A_CONV3X3,
+                        d_mode: int = D_NHWC, bias: bool = False) -> int:
+    """Partial-statistics rows a conv_gemm call of this shape writes (depends on the kernel variant chosen)."""
+    a = _lib.ConvGemmArgs()
+    a.batch, a.height, a.width, a.n_total, a.a_mode, a.d_mode = batch, height, width, n_total, a_mode, d_mode
+    a.bias = 1 if bias else None          # only null / non-null matters here
+    r = _lib.load().sunet_conv_gemm_stat_rows(C.byref(a))
     if r <= 0:
         raise _lib.SunetError("conv_gemm_stat_rows: bad shape")
     return r
@@ -71,7 +76,7 @@ def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst:
     a.dst, _, a.dst_pix_stride = _act(dst)
     a.d_mode = d_mode
     if stats is not None:
-        rows = conv_gemm_stat_rows(a.batch, a.height, a.width, a.n_total)
+        rows = _lib.load().sunet_conv_gemm_stat_rows(C.byref(a))
         assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= rows * a.n_total * 2
         a.stats = stats.data_ptr()
     _lib.check(lib.sunet_conv_gemm(C.byref(a), _stream()), "sunet_conv_gemm")

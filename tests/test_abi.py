@@ -34,7 +34,7 @@ def test_argument_validation_without_gpu(built_lib):
     a = _lib.ConvGemmArgs()
     assert built_lib.sunet_conv_gemm(ctypes.byref(a), None) != 0
     assert b"conv_gemm" in built_lib.sunet_last_error()
-    assert built_lib.sunet_conv_gemm_stat_rows(0, 8, 8, 64) == -1
+    assert built_lib.sunet_conv_gemm_stat_rows(ctypes.byref(a)) == -1
     assert built_lib.sunet_metric_hist(None, None, None, 0, 0, 0.0, 0.0, 0, None, None) != 0
     assert built_lib.sunet_adam_step(None, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None, None, None) != 0
 
