@@ -197,16 +197,39 @@ def run_ours(args):
     value = gb * args.steps / (ms / 1e3)
 
     # ---- e2e: pinned host inputs, H2D + step + D2H of the step's losses, every step
+    # Double-buffered like a pin_memory DataLoader: the copy of step i+1 is issued on a side stream right
+    # after step i is enqueued, so it overlaps step i's kernels; every step's copy and its D2H read of the
+    # losses are inside the timed region (the first copy is not overlapped with anything).
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(x_dev), torch.empty_like(l_dev)) for _ in range(2)]
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2][0].copy_(x_host, non_blocking=True)
+            bufs[i % 2][1].copy_(l_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
     barrier()
     e0.record()
     res_host = None
-    for _ in range(args.steps):
-        xd = x_host.to(dev, non_blocking=True)
-        ld = l_host.to(dev, non_blocking=True)
-        res = tr.step(xd, ld)
+    ev = issue_copy(0)
+    for i in range(args.steps):
+        torch.cuda.current_stream().wait_event(ev)
+        res = tr.step(*bufs[i % 2])
+        if i + 1 < args.steps:
+            ev = issue_copy(i + 1)
         res_host = res.cpu()                      # loss / coverage read back (the reference's .item() calls)
     e1.record()
     barrier()
+    # plain H2D bandwidth of this box, for context
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    bufs[0][0].copy_(x_host, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize(dev)
+    h2d_gbps = x_host.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e = gb * args.steps / (ms_e2e / 1e3)
     h2d = x_host.numel() * 4 + l_host.numel() * 4
@@ -236,7 +259,9 @@ def run_ours(args):
                        "l2": "inputs_exceed_l2 (activations ~120 MB/patch >> 126 MB L2)",
                        "cuda_graph": bool(tr.use_graph)},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "h2d_gbps_measured": h2d_gbps,
+                    "pipeline": "pinned host -> device copy of step i+1 overlaps step i; 4 loss scalars read back "
+                                "(sync) every step"},
             "gpu_launches": int(tr_eager_launches) * args.steps,
             "clocks": clocks,
             "step_tflops": value * FLOP_PER_PATCH_256 * (args.size / 256) ** 2 / 1e12 / world,

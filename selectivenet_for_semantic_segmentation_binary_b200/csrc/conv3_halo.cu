@@ -292,8 +292,11 @@ static int halo_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUt
 }
 
 bool conv3_halo_eligible(const sunet_conv_gemm_args* a) {
+  // N % 256 == 0 stays on conv_gemm_kernel<256>: its 128x256 tile already runs at the cuBLAS-measured peak
+  // (1450-1550 TFLOP/s, profiles/r01), while two 128-wide halo tiles measured 1280-1330.
+  const bool wide = (a->n_total % 256 == 0) && getenv("SUNET_HALO_ALL") == nullptr;
   return a->a_mode == SUNET_A_CONV3X3 && a->d_mode == SUNET_D_NHWC && a->bias == nullptr && a->height % 16 == 0 &&
-         a->width % 16 == 0 && getenv("SUNET_NO_HALO") == nullptr;
+         a->width % 16 == 0 && !wide && getenv("SUNET_NO_HALO") == nullptr;
 }
 
 int conv3_halo_stat_rows(int batch, int height, int width, int n_total) {
