@@ -63,6 +63,7 @@ class SUNetTrainer:
         self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self._ranges = self.fg.group_ranges()
         self.launches_per_step = 0
+        self.global_pixels_override = 0
 
     def set_lr(self, lr: float) -> None:
         self.lr_dev.fill_(lr)
@@ -78,7 +79,8 @@ class SUNetTrainer:
             K.loss_sums(logits[0], logits[1], logits[2], lab, self.sums, self.ws)
         else:
             K.loss_sums(None, None, logits[0], lab, self.sums, self.ws)
-        Pg = P * self.world
+        # global pixel count: equal shards unless the caller states the true global count (uneven tail shard)
+        Pg = self.global_pixels_override if self.global_pixels_override else P * self.world
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
