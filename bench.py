@@ -136,7 +136,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         group = dist.group.WORLD
     lib = _lib.load()
 
@@ -236,9 +237,10 @@ def run_ours(args):
     d2h = 4 * 4
 
     # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), timed live with CUDA events
-    roof = None
-    if rank == 0:
-        roof = tensor_core_roofline(tr, x_dev, l_dev, K, torch, min(args.steps, 3))
+    # (every rank runs it: the instrumented steps contain the same collectives as the timed ones)
+    roof = tensor_core_roofline(tr, x_dev, l_dev, K, torch, min(args.steps, 3))
+    if rank != 0:
+        roof = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -26,7 +26,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     total, size = 2 * world + 1, 64                      # uneven shards on purpose
     x, label = O.synthetic_batch(total, size, seed=11)
     torch.manual_seed(0)

@@ -1,0 +1,65 @@
+"""Small single-kernel workloads for `ncu --set full` (B200_PROFILING.md: keep the profiled command short).
+
+    python scripts/ncu_target.py conv64|conv128|conv256|wgrad128|wgrad256|wgrad64|bnbwd|bnfwd
+
+Shapes are the bench shapes (batch 128 of 256x256 patches) of the corresponding SUNet_B layer.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from selectivenet_for_semantic_segmentation_binary_b200 import kernels as K
+
+
+def bf(*shape):
+    return torch.randn(*shape, device="cuda").to(torch.bfloat16)
+
+
+def conv(B, H, W, Cin, Cout, iters=3):
+    x = bf(B, H, W, Cin)
+    w = (torch.randn(Cout, 9 * Cin, device="cuda") / (3 * Cin ** 0.5)).to(torch.bfloat16)
+    y = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+    rows = K.conv_gemm_stat_rows(B, H, W, Cout, K.A_CONV3X3)
+    st = torch.zeros(rows, Cout, 2, device="cuda")
+    for _ in range(iters):
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), x, w, y, stats=st)
+
+
+def wgrad(B, H, W, Ca, Cb, iters=3):
+    dy, x = bf(B, H, W, Ca), bf(B, H, W, Cb)
+    splits = K.wgrad_splits((B, H, W), dy, K.A_CONV3X3, x)
+    part = torch.empty(splits, 9, Ca, Cb, device="cuda")
+    for _ in range(iters):
+        K.wgrad_gemm((B, H, W), dy, K.A_CONV3X3, x, part)
+
+
+def bn(B, H, W, C, bwd, iters=3):
+    y, dA = bf(B, H, W, C), bf(B, H, W, C)
+    sc, sh, mu, istd = (torch.rand(C, device="cuda") + 0.5 for _ in range(4))
+    out = torch.empty_like(y)
+    ws = K.new_workspace("cuda")
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    for _ in range(iters):
+        if bwd:
+            K.bn_relu_pool_bwd(dA, None, y, sc, sh, mu, istd, sc, dg, db, out, ws)
+        else:
+            K.bn_relu_pool(y, sc, sh, out, None)
+
+
+MODES = {
+    "conv64": lambda: conv(128, 256, 256, 64, 64),
+    "conv128": lambda: conv(128, 128, 128, 128, 128),
+    "conv256": lambda: conv(128, 64, 64, 256, 256),
+    "wgrad128": lambda: wgrad(128, 128, 128, 128, 128),
+    "wgrad256": lambda: wgrad(128, 64, 64, 256, 256),
+    "wgrad64": lambda: wgrad(128, 256, 256, 64, 64),
+    "bnbwd": lambda: bn(128, 256, 256, 64, True),
+    "bnfwd": lambda: bn(128, 256, 256, 64, False),
+}
+
+if __name__ == "__main__":
+    MODES[sys.argv[1]]()
+    torch.cuda.synchronize()
+    print("done", sys.argv[1])

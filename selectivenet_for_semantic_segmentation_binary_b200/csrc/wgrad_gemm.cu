@@ -138,7 +138,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BNW, true, true);
+      // dbg_boff bit 3 (SUNET_DBG_BOFF=8): timing-only experiment, pretend the operands are K-major
+      const bool mn = !(p.dbg_boff & 8);
+      const uint32_t idesc = make_idesc_bf16(128, BNW, mn, mn);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -261,7 +263,8 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+      const bool mn = !(p.dbg_boff & 8);
+      const uint32_t idesc = make_idesc_bf16(128, 64, mn, mn);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -466,6 +469,10 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     q.c0_blocks = a->b0_channels / 64;
     q.Ca = 64; q.Nb = w.Nb; q.taps_total = 9;
     q.out = a->partials;
+    {
+      const char* b = getenv("SUNET_DBG_BOFF");
+      q.dbg_boff = b ? atoi(b) : 0;
+    }
     q.kp = w.kp; q.abox = w.kp * 128;
     q.b_tx = (w.kp + 2) * 128;
     q.bslot = (q.b_tx + 1023) / 1024 * 1024;

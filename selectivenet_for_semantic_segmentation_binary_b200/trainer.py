@@ -56,7 +56,9 @@ class SUNetTrainer:
         self.sums = torch.zeros(3, dtype=torch.float64, device=self.device)
         self.results = torch.zeros(4, device=self.device)
         self.ws = K.new_workspace(self.device)
-        self.use_graph = bool(use_cuda_graph) and self.world == 1
+        # multi-GPU too: NCCL all-reduces issued through torch.distributed are graph-capturable, and at 16
+        # patches per GPU the ~170 launches of a step would otherwise be host-bound
+        self.use_graph = bool(use_cuda_graph)
         self._graph = None
         self._static = None           # (x, label, dlogits) static buffers of the captured shape
         self._warm = 0
@@ -145,8 +147,16 @@ class SUNetTrainer:
                 return self.results
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.device)
-            with torch.cuda.graph(g):
+            try:
+                with torch.cuda.graph(g):
+                    self._step_impl(sx, sl, dl)
+            except Exception as e:  # noqa: BLE001 - capture is an optimisation; eager is always valid
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({e!r}); running eagerly")
+                self.use_graph = False
+                torch.cuda.synchronize(self.device)
                 self._step_impl(sx, sl, dl)
+                return self.results
             self._graph = g
             # capture does not execute: replay once so this call is a real step
         self._graph.replay()
