@@ -12,7 +12,7 @@ def run(B, H, W, Ca, Cb, label):
     x = torch.randn(B, H, W, Cb, device=dev).to(torch.bfloat16)
     splits = K.wgrad_splits((B, H, W), dy, K.A_CONV3X3, x)
     part = torch.empty(splits, 9, Ca, Cb, device=dev)
-    for boff in ("0", "8"):
+    for boff in ("0", "16", "32"):
         os.environ["SUNET_DBG_BOFF"] = boff
         for _ in range(3):
             K.wgrad_gemm((B, H, W), dy, K.A_CONV3X3, x, part)
@@ -23,9 +23,13 @@ def run(B, H, W, Ca, Cb, label):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         fl = 2.0 * B * H * W * 9 * Ca * Cb
-        print(f"{label} {'MN-major (real)' if boff == '0' else 'K-major (timing only)'}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s splits={splits}", flush=True)
+        print(f"{label} { {'0': 'real', '16': 'no TMA loads after fill (MMA+smem only)', '32': 'no MMAs (TMA delivery only)'}[boff] }: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s splits={splits}", flush=True)
     os.environ["SUNET_DBG_BOFF"] = "0"
 
 run(128, 128, 128, 128, 128, "128->128 @128^2")
 run(128, 64, 64, 256, 256, "256->256 @64^2")
-run(128, 256, 256, 64, 64, "64->64 @256^2 (wgrad64)")
+os.environ["SUNET_WGRAD_NO_STACK"] = "1"
+run(128, 256, 256, 64, 64, "64->64 @256^2 (generic kernel, M half empty)")
+for kp in ("32", "128"):
+    os.environ["SUNET_WGRAD_KP"] = kp
+    run(128, 128, 128, 128, 128, f"128->128 @128^2 kp={kp}")

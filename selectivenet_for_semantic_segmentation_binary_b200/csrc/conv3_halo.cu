@@ -96,7 +96,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int mb = m_first; mb < p.m_blocks; mb += m_step) {
@@ -107,16 +107,22 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const CUtensorMap* mapA = (cc < p.cpt0) ? &mapA0 : &mapA1;
           const int c0 = ((cc < p.cpt0) ? cc : cc - p.cpt0) * 64;
           mbar_wait(&aempty[as], aph ^ 1);
-          mbar_arrive_expect_tx(&afull[as], C::A_TX);
-          tma_load_5d(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * 16 - 1, by * 16 - 1, n, 0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&afull[as], C::A_TX);
+            tma_load_5d(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * 16 - 1, by * 16 - 1, n, 0);
+          }
+          __syncwarp();
           if (++as == C::A_STAGES) {
             as = 0;
             aph ^= 1;
           }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&bempty[bs], bph ^ 1);
-            mbar_arrive_expect_tx(&bfull[bs], C::B_BYTES);
-            tma_load_2d(sB + bs * C::B_BYTES, &mapB, &bfull[bs], (tap * cpt + cc) * 64, n_tile * BN);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bfull[bs], C::B_BYTES);
+              tma_load_2d(sB + bs * C::B_BYTES, &mapB, &bfull[bs], (tap * cpt + cc) * 64, n_tile * BN);
+            }
+            __syncwarp();
             if (++bs == C::B_STAGES) {
               bs = 0;
               bph ^= 1;
@@ -127,7 +133,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -147,26 +153,31 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             tc_fence_after_sync();
             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + bs * C::B_BYTES), 16, 1024);
             const int r = tap / 3, s = tap - r * 3;
+            if (elect_one()) {
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const uint64_t adesc = make_smem_desc_sw128(a_base + (r * 18 + 8 * t + s) * 128, 16, 18 * 128);
+              for (int t = 0; t < 2; ++t) {
+                const uint64_t adesc = make_smem_desc_sw128(a_base + (r * 18 + 8 * t + s) * 128, 16, 18 * 128);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_d + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_d + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&bempty[bs]);
             }
-            umma_commit(&bempty[bs]);
+            __syncwarp();
             if (++bs == C::B_STAGES) {
               bs = 0;
               bph ^= 1;
             }
           }
-          umma_commit(&aempty[as]);
+          if (elect_one()) umma_commit(&aempty[as]);
+          __syncwarp();
           if (++as == C::A_STAGES) {
             as = 0;
             aph ^= 1;
           }
         }
-        umma_commit(&tfull[acs]);
+        if (elect_one()) umma_commit(&tfull[acs]);
+        __syncwarp();
       }
     }
   } else {

@@ -108,8 +108,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   const int ksteps = p.taps * cpt;
 
   if (warp == 0) {
-    // ------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------- TMA producer (warp-uniform, elected issue)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int mt = m_first; mt < p.m_tiles; mt += m_step) {
@@ -120,7 +120,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         for (int ks0 = 0; ks0 < ksteps; ks0 += C::KSP) {
           const int nks = min(C::KSP, ksteps - ks0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], nks * (C::A_BYTES + C::B_BYTES));
+          const bool leader = elect_one();
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], nks * (C::A_BYTES + C::B_BYTES));
           for (int j = 0; j < nks; ++j) {
             const int ks = ks0 + j;
             const int tap = ks / cpt;
@@ -131,18 +132,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               mapA = &mapA1;
             }
             uint8_t* dA = sA + (stage * C::KSP + j) * C::A_BYTES;
-            if (p.gs_load) {
-              tma_load_5d(dA, mapA, &full_bar[stage], cc * 64, tap & 1, x0, tap >> 1, n0 * p.H + y0);
-            } else {
-              int dx = 0, dy = 0;
-              if (p.taps == 9) {
-                dy = tap / 3 - 1;
-                dx = tap - (tap / 3) * 3 - 1;
-              }
-              tma_load_5d(dA, mapA, &full_bar[stage], cc * 64, x0 + dx, y0 + dy, n0, 0);
+            int dx = 0, dy = 0;
+            if (p.taps == 9) {
+              dy = tap / 3 - 1;
+              dx = tap - (tap / 3) * 3 - 1;
             }
-            tma_load_2d(sB + (stage * C::KSP + j) * C::B_BYTES, &mapB, &full_bar[stage], ks * 64, n_tile * BN);
+            if (leader) {
+              if (p.gs_load) {
+                tma_load_5d(dA, mapA, &full_bar[stage], cc * 64, tap & 1, x0, tap >> 1, n0 * p.H + y0);
+              } else {
+                tma_load_5d(dA, mapA, &full_bar[stage], cc * 64, x0 + dx, y0 + dy, n0, 0);
+              }
+              tma_load_2d(sB + (stage * C::KSP + j) * C::B_BYTES, &mapB, &full_bar[stage], ks * 64, n_tile * BN);
+            }
           }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -151,8 +155,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------- MMA issuer (warp-uniform, elected issue)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -167,24 +171,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           const int nks = min(C::KSP, ksteps - ks0);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          for (int j = 0; j < nks; ++j) {
-            uint64_t adesc =
-                make_smem_desc_sw128(smem_u32(sA + (stage * C::KSP + j) * C::A_BYTES) + p.dbg_shift * 128, 16, 1024);
-            adesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
-            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + (stage * C::KSP + j) * C::B_BYTES), 16, 1024);
+          if (elect_one()) {
+            for (int j = 0; j < nks; ++j) {
+              uint64_t adesc =
+                  make_smem_desc_sw128(smem_u32(sA + (stage * C::KSP + j) * C::A_BYTES) + p.dbg_shift * 128, 16, 1024);
+              adesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
+              const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + (stage * C::KSP + j) * C::B_BYTES), 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // +32 bytes along K inside the 128B swizzle span = +2 in the (addr >> 4) field
-              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks0 | j | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                // +32 bytes along K inside the 128B swizzle span = +2 in the (addr >> 4) field
+                umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks0 | j | k) != 0 ? 1u : 0u);
+              }
             }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);
+        if (elect_one()) umma_commit(&tfull_bar[as]);
+        __syncwarp();
       }
     }
   } else {

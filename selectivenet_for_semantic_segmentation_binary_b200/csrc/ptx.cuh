@@ -62,6 +62,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp.  The producer / MMA warps run their loops warp-uniformly and only
+// predicate the issuing instruction on this: descriptors and addresses then stay in uniform registers
+// (a `if (lane == 0)` body forces an R2UR.BROADCAST chain in front of every UTCHMMA / UTMALDG).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -95,7 +95,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int BNW = p.nb64 * 64;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       const CUtensorMap* mapB = (n_tile < p.c0_blocks) ? &mapB0 : &mapB1;
       const int cB = ((n_tile < p.c0_blocks) ? n_tile : (n_tile - p.c0_blocks)) * BNW;
       int stage = 0;
@@ -107,11 +107,21 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int x0 = xt * p.tw, y0 = yt * p.th, n0 = nt * p.nb;
         uint8_t* st = smem + stage * stage_bytes;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if ((p.dbg_boff & 16) && kb >= kb0 + STAGES) {   // timing experiment: no TMA traffic after the first fill
+          if (elect_one()) mbar_arrive(&full_bar[stage]);
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
+        uint8_t* sb = st + 2 * p.abox;
+        if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[stage], 2 * p.abox + p.bboxes * p.b_tx);
         // A: two 64-channel boxes (the second may be fully out of range -> zeros)
         tma_load_5d(st, &mapA, &full_bar[stage], m_tile * 128, x0, y0, n0, 0);
         tma_load_5d(st + p.abox, &mapA, &full_bar[stage], m_tile * 128 + 64, x0, y0, n0, 0);
-        uint8_t* sb = st + 2 * p.abox;
         if (p.shifted) {
           // one box of KP+2 pixels starting one pixel to the left, on input row y + (filter row - 1)
           for (int j = 0; j < p.nb64; ++j)
@@ -130,6 +140,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
           }
         }
+        }  // elect_one
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -137,7 +149,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // dbg_boff bit 3 (SUNET_DBG_BOFF=8): timing-only experiment, pretend the operands are K-major
       const bool mn = !(p.dbg_boff & 8);
       const uint32_t idesc = make_idesc_bf16(128, BNW, mn, mn);
@@ -148,23 +160,31 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + 2 * p.abox;
-        for (int kk = 0; kk < p.kp / 16; ++kk) {
-          const uint64_t adesc = make_smem_desc_sw128(sa + kk * 2048, p.abox, 1024);
-          for (int t = 0; t < p.T; ++t) {
-            // shifted: tap t = window starting t pixels (rows of 128 B) into the halo box
-            const uint32_t boff = p.shifted ? (uint32_t)(t * 128) : (uint32_t)(t * p.nb64 * p.bslot);
-            uint64_t bdesc = make_smem_desc_sw128(sb + boff + kk * 2048 + p.dbg_shift * 128, p.bslot, 1024);
-            bdesc |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;   // experiment hook, 0 in production
-            umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+        const uint32_t tstep = p.shifted ? 128u : (uint32_t)(p.nb64 * p.bslot);   // smem distance between taps
+        const int nkk = (p.dbg_boff & 32) ? 0 : p.kp / 16;                        // bit 5: timing experiment, no MMAs
+        if (elect_one()) {
+          uint64_t adesc = make_smem_desc_sw128(sa, p.abox, 1024);
+          uint64_t bdesc0 = make_smem_desc_sw128(sb + p.dbg_shift * 128, p.bslot, 1024);
+          bdesc0 |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;                  // experiment hook, 0 in production
+          for (int kk = 0; kk < nkk; ++kk) {
+            uint64_t bdesc = bdesc0;
+            for (int t = 0; t < p.T; ++t) {
+              umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              bdesc += tstep >> 4;            // next tap: shifted window (or next box group)
+            }
+            adesc += 2048 >> 4;               // next 16 pixels (16 rows of 128 B)
+            bdesc0 += 2048 >> 4;
           }
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(done_bar);
+      if (elect_one()) umma_commit(done_bar);
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
@@ -239,7 +259,7 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant_
   const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       const CUtensorMap* mapX = (n_tile < p.c0_blocks) ? &mapX0 : &mapX1;
       const int cX = ((n_tile < p.c0_blocks) ? n_tile : (n_tile - p.c0_blocks)) * 64;
       int stage = 0;
@@ -251,10 +271,13 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant_
         const int x0 = xt * p.kp;
         uint8_t* st = smem + stage * stage_bytes;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], p.abox + 3 * p.b_tx);
-        tma_load_5d(st, &mapDy, &full_bar[stage], 0, x0, y, n, 0);
-        for (int r = 0; r < 3; ++r)
-          tma_load_5d(st + p.abox + r * p.bslot, mapX, &full_bar[stage], cX, x0 - 1, y + r - 1, n, 0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], p.abox + 3 * p.b_tx);
+          tma_load_5d(st, &mapDy, &full_bar[stage], 0, x0, y, n, 0);
+          for (int r = 0; r < 3; ++r)
+            tma_load_5d(st + p.abox + r * p.bslot, mapX, &full_bar[stage], cX, x0 - 1, y + r - 1, n, 0);
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -262,7 +285,7 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const bool mn = !(p.dbg_boff & 8);
       const uint32_t idesc = make_idesc_bf16(128, 64, mn, mn);
       int stage = 0;
@@ -272,24 +295,35 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant_
         tc_fence_after_sync();
         const uint32_t sdy = smem_u32(smem + stage * stage_bytes);
         const uint32_t sx = sdy + p.abox;
-        for (int kk = 0; kk < p.kp / 16; ++kk) {
-          const uint64_t bdesc = make_smem_desc_sw128(sdy + kk * 2048, 1024, 1024);
+        if (elect_one()) {
+          // five tap-pair descriptors for this stage; every K step only advances them by 16 rows
+          uint64_t ad[5];
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
             const int ta = 2 * j, tb = 2 * j + 1;
             const uint32_t offa = (ta / 3) * p.bslot + (ta % 3) * 128;
             const uint32_t offb = (j < 4) ? (uint32_t)((tb / 3) * p.bslot + (tb % 3) * 128) : offa + 128;
-            const uint64_t adesc = make_smem_desc_sw128(sx + offa + kk * 2048, offb - offa, 1024);
-            umma_bf16(tmem_base + j * 64, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            ad[j] = make_smem_desc_sw128(sx + offa, offb - offa, 1024);
           }
+          uint64_t bdesc = make_smem_desc_sw128(sdy, 1024, 1024);
+          for (int kk = 0; kk < p.kp / 16; ++kk) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              umma_bf16(tmem_base + j * 64, ad[j], bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              ad[j] += 2048 >> 4;
+            }
+            bdesc += 2048 >> 4;
+          }
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(done_bar);
+      if (elect_one()) umma_commit(done_bar);
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
