@@ -142,19 +142,29 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __re
 }
 
 // ------------------------------------------------------------------ BN finalize
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ conv_bias, float* running_mean, float* running_var,
-                                   long long* nbt, float momentum, float eps, float* scale, float* shift, float* mean,
-                                   float* invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt) *nbt += 1;
+// one warp per channel: lanes stride over the per-CTA partial rows, fp64 tree reduction
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ conv_bias, float* running_mean, float* running_var,
+                   long long* nbt, float momentum, float eps, float* scale, float* shift, float* mean,
+                   float* invstd) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c == 0 && lane == 0 && nbt) *nbt += 1;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s += (double)stats[((size_t)r * C + c) * 2];
-    q += (double)stats[((size_t)r * C + c) * 2 + 1];
+  for (int r = lane; r < rows; r += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(stats + ((size_t)r * C + c) * 2);
+    s += (double)v.x;
+    q += (double)v.y;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane != 0) return;
   const double m = s / count;
   double var = q / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -551,6 +561,160 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
   }
 }
 
+// ------------------------------------------------------------------ pooled-layer backward, lean form
+// The three encoder outputs feed both a skip connection and a 2x2 max-pool.  One thread = one 2x2 window
+// x 8 channels; operands stay packed (bf16x8) and the per-channel decisions (ReLU mask, first-max winner)
+// are bit masks, so the kernel fits two 256-thread blocks per SM (the template version above needs 159
+// registers and ran at 1.4 TB/s).
+struct PoolWin {
+  bf16x8 vy[4], vg[4], vp;
+  long long pix[4];
+  uint32_t pos;     // bit (k*8 + j): activation of pixel k, channel j is > 0
+  uint32_t best;    // 2 bits per channel j: index of the first maximum of the window
+};
+__device__ __forceinline__ float bf16_elem(const bf16x8& v, int j) {
+  return (j & 1) ? bf16hi(v.w[j >> 1]) : bf16lo(v.w[j >> 1]);
+}
+__device__ __forceinline__ void pool_win_load(PoolWin& w, long long win, int g, const __nv_bfloat16* __restrict__ dA,
+                                              int das, const __nv_bfloat16* __restrict__ dP, int dps,
+                                              const __nv_bfloat16* __restrict__ y, int ys, int H, int W) {
+  const int HW = H >> 1, WW = W >> 1;
+  const int wx = (int)(win % WW);
+  const int wy = (int)((win / WW) % HW);
+  const int n = (int)(win / ((long long)WW * HW));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    w.pix[k] = ((long long)n * H + (wy * 2 + (k >> 1))) * W + (wx * 2 + (k & 1));
+    w.vy[k] = *reinterpret_cast<const bf16x8*>(y + w.pix[k] * ys + g * 8);
+    if (dA) w.vg[k] = *reinterpret_cast<const bf16x8*>(dA + w.pix[k] * das + g * 8);
+    else w.vg[k] = bf16x8{{0u, 0u, 0u, 0u}};
+  }
+  w.vp = *reinterpret_cast<const bf16x8*>(dP + win * dps + g * 8);
+}
+__device__ __forceinline__ void pool_win_decide(PoolWin& w, const ChanVec& sc, const ChanVec& sh) {
+  uint32_t pos = 0, best = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float bv = 0.f;
+    int bk = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float act = round_bf16(fmaxf(fmaf(bf16_elem(w.vy[k], j), sc.v[j], sh.v[j]), 0.f));
+      if (act > 0.f) pos |= 1u << (k * 8 + j);
+      if (k == 0 || act > bv) {
+        bv = act;
+        bk = k;
+      }
+    }
+    best |= (uint32_t)bk << (2 * j);
+  }
+  w.pos = pos;
+  w.best = best;
+}
+__device__ __forceinline__ float pool_win_grad(const PoolWin& w, int k, int j) {
+  if (!((w.pos >> (k * 8 + j)) & 1u)) return 0.f;
+  float g = bf16_elem(w.vg[k], j);
+  if (((w.best >> (2 * j)) & 3u) == (uint32_t)k) g += bf16_elem(w.vp, j);
+  return g;
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_pool_reduce_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ dP, int dps,
+                          const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, float* __restrict__ partials, int B, int H, int W, int C) {
+  __shared__ float red[256][17];
+  const int G = C >> 3;
+  const int g = threadIdx.x % G;
+  const long long total = (long long)B * (H >> 1) * (W >> 1) * G;
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g), mu = load_chan(mean, g), is = load_chan(invstd, g);
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    PoolWin w;
+    pool_win_load(w, i / G, g, dA, das, dP, dps, y, ys, H, W);
+    pool_win_decide(w, sc, sh);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = pool_win_grad(w, k, j);
+        acc[j] += gg;
+        acc[8 + j] = fmaf(gg, (bf16_elem(w.vy[k], j) - mu.v[j]) * is.v[j], acc[8 + j]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  const int reps = 256 / G;
+  for (int o = threadIdx.x; o < G * 16; o += 256) {
+    const int og = o >> 4, oj = o & 15;
+    float s = 0.f;
+    for (int r = 0; r < reps; ++r) s += red[r * G + og][oj];
+    const int c = og * 8 + (oj & 7);
+    partials[((size_t)blockIdx.x * C + c) * 2 + (oj >> 3)] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_pool_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ dP, int dps,
+                         const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ coef,
+                         __nv_bfloat16* __restrict__ dy, int dys, int B, int H, int W, int C) {
+  const int G = C >> 3;
+  const int g = threadIdx.x % G;
+  const long long total = (long long)B * (H >> 1) * (W >> 1) * G;
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
+  const ChanVec kg = load_chan(coef, g), k1 = load_chan(coef + C, g), k0 = load_chan(coef + 2 * C, g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    PoolWin w;
+    pool_win_load(w, i / G, g, dA, das, dP, dps, y, ys, H, W);
+    pool_win_decide(w, sc, sh);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = fmaf(kg.v[j], pool_win_grad(w, k, j), fmaf(k1.v[j], bf16_elem(w.vy[k], j), k0.v[j]));
+      *reinterpret_cast<bf16x8*>(dy + w.pix[k] * dys + g * 8) = pack8(o);
+    }
+  }
+}
+
+// parallel fold of the per-block partial rows: one warp per channel, lanes stride over the rows
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_par_kernel(const float* __restrict__ partials, int blocks, int C, double count,
+                           const float* __restrict__ scale, const float* __restrict__ mean,
+                           const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double sg = 0.0, sgx = 0.0;
+  for (int b = lane; b < blocks; b += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(partials + ((size_t)b * C + c) * 2);
+    sg += (double)v.x;
+    sgx += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+  }
+  if (lane == 0) {
+    if (dbeta) dbeta[c] = (float)sg;
+    if (dgamma) dgamma[c] = (float)sgx;
+    const double scv = scale[c];
+    const double k1 = -scv * (double)invstd[c] * sgx / count;
+    const double k0 = -scv * sg / count - k1 * (double)mean[c];
+    coef[c] = (float)scv;
+    coef[C + c] = (float)k1;
+    coef[2 * C + c] = (float)k0;
+  }
+}
+
 static inline int flat_grid(long long total) {
   long long b = (total + 256 * EW_U - 1) / (256 * EW_U);
   const long long cap = (long long)num_sms() * 8;
@@ -615,7 +779,7 @@ extern "C" int sunet_bn_finalize(const float* stats, int rows, int channels, lon
     return set_error(SUNET_ERR_INVALID, "bn_finalize: bad arguments");
   if ((running_mean == nullptr) != (running_var == nullptr))
     return set_error(SUNET_ERR_INVALID, "bn_finalize: running_mean/var must both be given or both NULL");
-  bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(stats, rows, channels, (double)count, gamma, beta,
+  bn_finalize_kernel<<<(channels + 7) / 8, 256, 0, STREAM>>>(stats, rows, channels, (double)count, gamma, beta,
                                                                   conv_bias, running_mean, running_var,
                                                                   num_batches_tracked, momentum, eps, scale, shift,
                                                                   mean, invstd);
@@ -709,19 +873,19 @@ extern "C" int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const v
   __nv_bfloat16* dyp = reinterpret_cast<__nv_bfloat16*>(dy);
   const double count = (double)batch * height * width;
   if (pool)
-    bn_bwd_reduce_kernel<true><<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, dPp, dPool_pix_stride, yp,
+    bn_bwd_pool_reduce_kernel<<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, dPp, dPool_pix_stride, yp,
                                                             y_pix_stride, scale, shift, mean, invstd, partials, batch,
                                                             height, width, channels);
   else
     bn_bwd_reduce_flat_kernel<<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, yp, y_pix_stride, scale, shift, mean,
                                                            invstd, partials, total, channels);
   if ((e = check_launch("bn_bwd_reduce"))) return e;
-  bn_bwd_finalize_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(partials, blocks, channels, count, scale, mean,
+  bn_bwd_finalize_par_kernel<<<(channels + 7) / 8, 256, 0, STREAM>>>(partials, blocks, channels, count, scale, mean,
                                                                       invstd, dgamma, dbeta, coef);
   if ((e = check_launch("bn_bwd_finalize"))) return e;
   const int ablocks = ew_grid(total, 256);
   if (pool)
-    bn_bwd_apply_kernel<true><<<ablocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, dPp, dPool_pix_stride, yp, y_pix_stride,
+    bn_bwd_pool_apply_kernel<<<ablocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, dPp, dPool_pix_stride, yp, y_pix_stride,
                                                             scale, shift, coef, dyp, dy_pix_stride, batch, height,
                                                             width, channels);
   else
