@@ -279,7 +279,13 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL collectives keep the communicator busy: destroy_process_group()
+        # was observed to hang after such a run.  Everything is flushed and synchronised, so leave directly.
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def tensor_core_roofline(tr, x, label, K, torch, steps):

@@ -114,6 +114,20 @@ int sunet_pack_conv1_weights(const float* w, void* wf, int cout, int cin, sunet_
 int sunet_pack_convT_weights(const float* w, const float* bias, void* wf, void* wd, float* bias4, int cin, int cout,
                              sunet_stream_t stream);
 
+/* every pack of one forward pass in ONE launch: a DEVICE table of jobs.
+ *   kind 0: conv3x3  (a = cout, b = cin; wf, wd as sunet_pack_conv3x3_weights)
+ *   kind 1: first conv (a = cout, b = cin; wf as sunet_pack_conv1_weights)
+ *   kind 2: ConvTranspose2d (a = cin, b = cout; wf, wd, bias, bias4 as sunet_pack_convT_weights) */
+typedef struct sunet_pack_job {
+  int kind, a, b, pad_;
+  const float* w;
+  const float* bias;
+  void* wf;
+  void* wd;
+  float* bias4;
+} sunet_pack_job;
+int sunet_pack_weights_table(const sunet_pack_job* jobs_dev, int n_jobs, sunet_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * BatchNorm2d + ReLU (+ MaxPool2d(2)), model.py:12-13,31,35,39
  * ---------------------------------------------------------------------------------------- */

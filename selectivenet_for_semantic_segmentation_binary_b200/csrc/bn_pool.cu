@@ -141,6 +141,56 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __re
   }
 }
 
+// ------------------------------------------------------------------ all weight packs in one launch
+// blockIdx.y = job (one per layer), blockIdx.x strides over that layer's elements.  Replaces 17 tiny
+// launches per forward pass: at 16 patches per GPU the step is launch-latency sensitive.
+__global__ void __launch_bounds__(256)
+pack_table_kernel(const sunet_pack_job* __restrict__ jobs) {
+  const sunet_pack_job j = jobs[blockIdx.y];
+  const long long start = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  if (j.kind == 0) {            // conv3x3: a = cout, b = cin
+    const int co_n = j.a, ci_n = j.b;
+    __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
+    __nv_bfloat16* wd = reinterpret_cast<__nv_bfloat16*>(j.wd);
+    const long long total = (long long)co_n * ci_n * 9;
+    for (long long i = start; i < total; i += step) {
+      const int ci = (int)(i % ci_n);
+      const int tap = (int)((i / ci_n) % 9);
+      const int co = (int)(i / ((long long)ci_n * 9));
+      const __nv_bfloat16 b = __float2bfloat16_rn(j.w[((long long)co * ci_n + ci) * 9 + tap]);
+      wf[i] = b;
+      if (wd) wd[((long long)ci * 9 + (8 - tap)) * co_n + co] = b;
+    }
+  } else if (j.kind == 1) {     // first conv: a = cout, b = cin, K padded to 64
+    const int co_n = j.a, cin = j.b;
+    __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
+    for (long long i = start; i < (long long)co_n * 64; i += step) {
+      const int k = (int)(i & 63), co = (int)(i >> 6);
+      float v = 0.f;
+      if (k < 9 * cin) {
+        const int tap = k / cin, ci = k - tap * cin;
+        v = j.w[((long long)co * cin + ci) * 9 + tap];
+      }
+      wf[i] = __float2bfloat16_rn(v);
+    }
+  } else {                      // ConvTranspose2d: a = cin, b = cout
+    const int ci_n = j.a, co_n = j.b;
+    __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
+    __nv_bfloat16* wd = reinterpret_cast<__nv_bfloat16*>(j.wd);
+    const long long total = (long long)ci_n * co_n * 4;
+    for (long long i = start; i < total; i += step) {
+      const int ci = (int)(i % ci_n);
+      const int row = (int)(i / ci_n);
+      const int co = row % co_n, tap = row / co_n;
+      const __nv_bfloat16 b = __float2bfloat16_rn(j.w[((long long)ci * co_n + co) * 4 + tap]);
+      wf[i] = b;
+      if (wd) wd[(long long)ci * (4 * co_n) + row] = b;
+      if (ci == 0 && j.bias4) j.bias4[row] = j.bias ? j.bias[co] : 0.f;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ BN finalize
 // one warp per channel: lanes stride over the per-CTA partial rows, fp64 tree reduction
 __global__ void __launch_bounds__(256)
@@ -769,6 +819,13 @@ extern "C" int sunet_pack_convT_weights(const float* w, const float* bias, void*
   pack_convT_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(wf),
                                                               reinterpret_cast<__nv_bfloat16*>(wd), bias4, cin, cout);
   return check_launch("pack_convT_weights");
+}
+
+extern "C" int sunet_pack_weights_table(const sunet_pack_job* jobs_dev, int n_jobs, sunet_stream_t stream_) {
+  if (!jobs_dev || n_jobs <= 0) return set_error(SUNET_ERR_INVALID, "pack_weights_table: bad arguments");
+  dim3 grid(96, (unsigned)n_jobs);
+  pack_table_kernel<<<grid, 256, 0, STREAM>>>(jobs_dev);
+  return check_launch("pack_weights_table");
 }
 
 extern "C" int sunet_bn_finalize(const float* stats, int rows, int channels, long long count, const float* gamma,

@@ -185,7 +185,30 @@ class SUNetPlan:
 
     # ------------------------------------------------------------------ weights
     def pack_weights(self, params: Dict[str, torch.Tensor]) -> None:
-        """fp32 reference-layout parameters -> bf16 kernel operands (every forward; 7.7 M values)."""
+        """fp32 reference-layout parameters -> bf16 kernel operands (every forward; 7.7 M values), one launch."""
+        key = tuple(params[f"{ly.name}.0.weight"].data_ptr() for ly in self.order) + tuple(
+            params[f"unpool{L}.weight"].data_ptr() for L in (1, 2, 3))
+        if getattr(self, "_pack_key", None) != key:
+            jobs = (_lib.PackJob * (len(self.order) + 3))()
+            for i, ly in enumerate(self.order):
+                w = params[f"{ly.name}.0.weight"]
+                assert w.dtype == torch.float32 and w.is_contiguous()
+                jobs[i].kind = 1 if ly.kind == "first" else 0
+                jobs[i].a, jobs[i].b = ly.cout, ly.cin
+                jobs[i].w, jobs[i].wf = w.data_ptr(), ly.wf.data_ptr()
+                jobs[i].wd = None if ly.wd is None else ly.wd.data_ptr()
+            for k, L in enumerate((1, 2, 3)):
+                j = jobs[len(self.order) + k]
+                u = self.upw[L]
+                w, b = params[f"unpool{L}.weight"], params[f"unpool{L}.bias"]
+                j.kind, j.a, j.b = 2, w.shape[0], w.shape[1]
+                j.w, j.bias, j.wf, j.wd, j.bias4 = (w.data_ptr(), b.data_ptr(), u["wf"].data_ptr(), u["wd"].data_ptr(),
+                                                   u["b4"].data_ptr())
+            self._pack_jobs = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device)
+            self._pack_n = len(self.order) + 3
+            self._pack_key = key
+        K.pack_weights_table(self._pack_jobs, self._pack_n)
+        return
         for ly in self.order:
             w = params[f"{ly.name}.0.weight"]
             if ly.kind == "first":

@@ -147,6 +147,11 @@ def pack_convT_weights(w, bias, wf, wd, bias4) -> None:
                                                     _stream()), "sunet_pack_convT_weights")
 
 
+def pack_weights_table(table_dev: torch.Tensor, n_jobs: int) -> None:
+    _lib.check(_lib.load().sunet_pack_weights_table(table_dev.data_ptr(), n_jobs, _stream()),
+               "sunet_pack_weights_table")
+
+
 # ----------------------------------------------------------------------------- BN / pool
 def bn_finalize(stats, rows, channels, count, gamma, beta, conv_bias, running_mean, running_var, nbt, momentum, eps,
                 scale, shift, mean, invstd) -> None:
