@@ -167,7 +167,11 @@ def train_worker(rank, world, args, ckpt_dir):
             net_save(ckpt_dir, net, _Opt(), epoch)
         evaluator.reset()
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that captured NCCL collectives make destroy_process_group() hang: synchronise and leave
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def train(args, ckpt_dir):
