@@ -102,11 +102,14 @@ def run_reference(args):
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
     pps, sec, cores = cpu_reference_step_rate(steps, warmup, batch=4)
     line = {
-        "impl": "reference", "metric": "SUNet_B train patches/sec (256^2)", "value": pps, "unit": "patches/s",
+        "impl": "reference", "metric": "SUNet_B train patches/sec (256^2, bf16)", "value": pps, "unit": "patches/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SUNet_B (UNet_B --selective 1 --s_lamb 2, BCElogit) train step, 256x256 RGB patches",
-                   "global_batch": GLOBAL_BATCH, "timing": "host perf_counter"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SUNet_B (UNet_B --selective 1 --s_lamb 2, BCElogit) train step: fwd + aux BCE + "
+                               "selective risk + bwd + Adam + confusion matrix, 256x256 RGB patches, random init",
+                   "global_batch": GLOBAL_BATCH, "patch": PATCH, "timing": "host perf_counter",
+                   "note": "the reference's own CPU path (PyTorch fp32 ops, all host cores) on a 4-patch sample of "
+                           "the batch per step; rank 0 only"},
         "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of a 4-patch shard of the 128-patch batch (oracle = the reference's "
                                    f"PyTorch CPU ops, fp32, {cores} threads)"},
