@@ -522,32 +522,15 @@ bn_relu_flat_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __
   }
 }
 
-// per-channel constants live in shared memory (broadcast reads) rather than 32-40 registers per thread, so
-// four 256-thread blocks fit per SM and twice as many 16-byte loads are in flight
-__device__ __forceinline__ void stage_chan(float* dst, const float* __restrict__ src, int C) {
-  for (int i = threadIdx.x; i < C; i += blockDim.x) dst[i] = __ldg(src + i);
-}
-__device__ __forceinline__ ChanVec lds_chan(const float* s, int g) {
-  ChanVec c;
-  *reinterpret_cast<float4*>(c.v) = *reinterpret_cast<const float4*>(s + g * 8);
-  *reinterpret_cast<float4*>(c.v + 4) = *reinterpret_cast<const float4*>(s + g * 8 + 4);
-  return c;
-}
-
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ y, int ys,
                           const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           float* __restrict__ partials, long long total, int C) {
   __shared__ float red[256][17];
-  __shared__ __align__(16) float s_c[4][512];
   const int G = C >> 3;
   const int g = threadIdx.x % G;
-  stage_chan(s_c[0], scale, C);
-  stage_chan(s_c[1], shift, C);
-  stage_chan(s_c[2], mean, C);
-  stage_chan(s_c[3], invstd, C);
-  __syncthreads();
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g), mu = load_chan(mean, g), is = load_chan(invstd, g);
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
@@ -566,14 +549,15 @@ bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
     for (int u = 0; u < EW_U; ++u) {
       const long long i = i0 + u * 256;
       if (i < total) {
+        float fy[8], fg[8];
+        unpack8(vy[u], fy);
+        unpack8(vg[u], fg);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int c = g * 8 + j;
-          const float fy = bf16_elem(vy[u], j);
-          const float act = round_bf16(fmaxf(fmaf(fy, s_c[0][c], s_c[1][c]), 0.f));
-          const float gg = act > 0.f ? bf16_elem(vg[u], j) : 0.f;
+          const float act = round_bf16(fmaxf(fmaf(fy[j], sc.v[j], sh.v[j]), 0.f));
+          const float gg = act > 0.f ? fg[j] : 0.f;
           acc[j] += gg;
-          acc[8 + j] = fmaf(gg, (fy - s_c[2][c]) * s_c[3][c], acc[8 + j]);
+          acc[8 + j] = fmaf(gg, (fy[j] - mu.v[j]) * is.v[j], acc[8 + j]);
         }
       }
     }
@@ -591,20 +575,15 @@ bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
   }
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ y, int ys,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy, int dys, long long total,
                          int C) {
-  __shared__ __align__(16) float s_c[5][512];
   const int G = C >> 3;
   const int g = threadIdx.x % G;
-  stage_chan(s_c[0], scale, C);
-  stage_chan(s_c[1], shift, C);
-  stage_chan(s_c[2], coef, C);
-  stage_chan(s_c[3], coef + C, C);
-  stage_chan(s_c[4], coef + 2 * C, C);
-  __syncthreads();
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
+  const ChanVec kg = load_chan(coef, g), k1 = load_chan(coef + C, g), k0 = load_chan(coef + 2 * C, g);
   for (long long i0 = blockIdx.x * (long long)(256 * EW_U) + threadIdx.x; i0 < total;
        i0 += (long long)gridDim.x * 256 * EW_U) {
     bf16x8 vy[EW_U], vg[EW_U];
@@ -620,14 +599,14 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
     for (int u = 0; u < EW_U; ++u) {
       const long long i = i0 + u * 256;
       if (i < total) {
-        float o[8];
+        float fy[8], fg[8], o[8];
+        unpack8(vy[u], fy);
+        unpack8(vg[u], fg);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int c = g * 8 + j;
-          const float fy = bf16_elem(vy[u], j);
-          const float act = round_bf16(fmaxf(fmaf(fy, s_c[0][c], s_c[1][c]), 0.f));
-          const float gg = act > 0.f ? bf16_elem(vg[u], j) : 0.f;
-          o[j] = fmaf(s_c[2][c], gg, fmaf(s_c[3][c], fy, s_c[4][c]));
+          const float act = round_bf16(fmaxf(fmaf(fy[j], sc.v[j], sh.v[j]), 0.f));
+          const float gg = act > 0.f ? fg[j] : 0.f;
+          o[j] = fmaf(kg.v[j], gg, fmaf(k1.v[j], fy[j], k0.v[j]));
         }
         *reinterpret_cast<bf16x8*>(dy + (i / G) * dys + g * 8) = pack8(o);
       }
