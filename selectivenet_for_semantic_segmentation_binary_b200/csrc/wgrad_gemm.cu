@@ -396,6 +396,8 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
     w->m_tiles = 1;
     w->shifted = 1;
     int want = (2 * num_sms()) / w->n_tiles;
+    // short problems: one wave of longer CTAs (prologue + partial-store epilogue cost ~10 us per CTA)
+    if (want > 1 && w->kb_total / want < 48) want = num_sms() / w->n_tiles;
     if (want < 1) want = 1;
     int max_splits = (w->kb_total + 7) / 8;
     if (want > max_splits) want = max_splits;
@@ -431,6 +433,8 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   const int base_items = w->m_tiles * w->n_tiles * w->tap_groups;
   // two full waves of CTAs (one CTA per SM at a time): round DOWN so no third, nearly empty wave appears
   int want = (2 * num_sms()) / base_items;
+  // short problems: one wave of longer CTAs (prologue + partial-store epilogue cost ~10 us per CTA)
+  if (want > 1 && w->kb_total / want < 48) want = num_sms() / base_items;
   if (want < 1) want = 1;
   int max_splits = (w->kb_total + 7) / 8;  // at least 8 k-blocks per CTA when possible
   if (max_splits < 1) max_splits = 1;
