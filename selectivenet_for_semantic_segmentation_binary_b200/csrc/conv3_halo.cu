@@ -28,16 +28,20 @@ struct HaloParams {
   int n_total;
 };
 
+// TILES = M=128 tiles per block: 2 (16x16 block, BN <= 128) or 1 (8 wide x 16 tall block, BN = 256 —
+// TMEM holds TILES x BN x 2 accumulator stages = 512 columns either way).
 template <int BN>
 struct HCfg {
-  static constexpr int A_SLOT = 41 * 1024;         // 18*18*128 = 41472 bytes, padded to 1024
-  static constexpr int A_TX = 18 * 18 * 128;
+  static constexpr int TILES = (BN == 256) ? 1 : 2;
+  static constexpr int PITCH = 8 * TILES + 2;                  // halo row pitch in pixels (18 or 10)
+  static constexpr int A_TX = 18 * PITCH * 128;                // 18 halo rows
+  static constexpr int A_SLOT = (A_TX + 1023) / 1024 * 1024;   // padded to the 1024-byte swizzle atom
   static constexpr int A_STAGES = 2;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int B_STAGES = (BN == 128) ? 5 : 8;
+  static constexpr int B_STAGES = (BN == 256) ? 4 : ((BN == 128) ? 5 : 8);
   static constexpr int STG_BYTES = 128 * 128;
   static constexpr int SMEM = A_STAGES * A_SLOT + B_STAGES * B_BYTES + 2 * STG_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 4 * BN;         // 2 tiles x 2 accumulator stages
+  static constexpr int TMEM_COLS = 2 * TILES * BN;
 };
 
 constexpr int kHThreads = 192;
@@ -109,7 +113,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           mbar_wait(&aempty[as], aph ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&afull[as], C::A_TX);
-            tma_load_5d(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * 16 - 1, by * 16 - 1, n, 0);
+            tma_load_5d(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * (8 * C::TILES) - 1, by * 16 - 1, n, 0);
           }
           __syncwarp();
           if (++as == C::A_STAGES) {
@@ -143,7 +147,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const uint32_t acph = (it >> 1) & 1;
         mbar_wait(&tempty[acs], acph ^ 1);
         tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + acs * (2 * BN);
+        const uint32_t tmem_d = tmem_base + acs * (C::TILES * BN);
         for (int cc = 0; cc < cpt; ++cc) {
           mbar_wait(&afull[as], aph);
           tc_fence_after_sync();
@@ -155,8 +159,9 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const int r = tap / 3, s = tap - r * 3;
             if (elect_one()) {
 #pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                const uint64_t adesc = make_smem_desc_sw128(a_base + (r * 18 + 8 * t + s) * 128, 16, 18 * 128);
+              for (int t = 0; t < C::TILES; ++t) {
+                const uint64_t adesc =
+                    make_smem_desc_sw128(a_base + (r * C::PITCH + 8 * t + s) * 128, 16, C::PITCH * 128);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_bf16(tmem_d + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
@@ -201,12 +206,12 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_wait(&tfull[acs], acph);
       tc_fence_after_sync();
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < C::TILES; ++t) {
 #pragma unroll
         for (int q = 0; q < NCHUNK; ++q, ++chunk_ctr) {
           uint32_t v[64];
           const uint32_t taddr =
-              tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * (2 * BN) + t * BN + q * 64;
+              tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * (C::TILES * BN) + t * BN + q * 64;
           tmem_ld_32x32b_x32(taddr, v);
           tmem_ld_32x32b_x32(taddr + 32, v + 32);
           tmem_ld_wait();
@@ -226,7 +231,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           if (issuer) tma_store_wait_read<0>();
           named_bar_sync(1, 128);
           if (issuer) {
-            tma_store_5d(&mapD, stg, ncol0, bx * 16 + 8 * t, by * 16, n, 0);
+            tma_store_5d(&mapD, stg, ncol0, bx * (8 * C::TILES) + 8 * t, by * 16, n, 0);
             tma_store_commit();
           }
           if (p.stats != nullptr) {
@@ -302,18 +307,23 @@ static int halo_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUt
   return check_launch("conv3_halo_kernel");
 }
 
+static int halo_bn(int n_total) {
+  // N % 256 == 0: one 128-pixel tile x 256 channels per block (two 128-wide tiles measured slower than
+  // the per-tap 128x256 kernel; the single-tile halo variant keeps the wide N and still loads A once)
+  if (n_total % 256 == 0 && getenv("SUNET_HALO_NO256") == nullptr) return 256;
+  return (n_total % 128 == 0) ? 128 : 64;
+}
+
 bool conv3_halo_eligible(const sunet_conv_gemm_args* a) {
-  // N % 256 == 0 stays on conv_gemm_kernel<256>: its 128x256 tile already runs at the cuBLAS-measured peak
-  // (1450-1550 TFLOP/s, profiles/r01), while two 128-wide halo tiles measured 1280-1330.
-  const bool wide = (a->n_total % 256 == 0) && getenv("SUNET_HALO_ALL") == nullptr;
+  if (a->n_total % 256 == 0 && getenv("SUNET_HALO_NO256") != nullptr) return false;   // fall back to conv_gemm<256>
   return a->a_mode == SUNET_A_CONV3X3 && a->d_mode == SUNET_D_NHWC && a->bias == nullptr && a->height % 16 == 0 &&
-         a->width % 16 == 0 && !wide && getenv("SUNET_NO_HALO") == nullptr;
+         a->width % 16 == 0 && getenv("SUNET_NO_HALO") == nullptr;
 }
 
 int conv3_halo_stat_rows(int batch, int height, int width, int n_total) {
-  const int bn = (n_total % 128 == 0) ? 128 : 64;
+  const int bn = halo_bn(n_total);
   const int n_tiles = n_total / bn;
-  const int m_blocks = batch * (height / 16) * (width / 16);
+  const int m_blocks = batch * (height / 16) * (width / (bn == 256 ? 8 : 16));
   int slots = num_sms() / n_tiles;
   if (slots < 1) slots = 1;
   if (slots > m_blocks) slots = m_blocks;
@@ -322,12 +332,13 @@ int conv3_halo_stat_rows(int batch, int height, int width, int n_total) {
 
 int conv3_halo_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   const int B = a->batch, H = a->height, W = a->width;
-  const int bn = (a->n_total % 128 == 0) ? 128 : 64;
+  const int bn = halo_bn(a->n_total);
+  const int bw = (bn == 256) ? 8 : 16;           // block width in pixels
   CUtensorMap mA0, mA1, mB, mD;
   int e;
-  if ((e = halo_map(&mA0, a->src0, a->src0_channels, a->src0_pix_stride, B, H, W, 18, 18))) return e;
+  if ((e = halo_map(&mA0, a->src0, a->src0_channels, a->src0_pix_stride, B, H, W, bw + 2, 18))) return e;
   if (a->src1) {
-    if ((e = halo_map(&mA1, a->src1, a->src1_channels, a->src1_pix_stride, B, H, W, 18, 18))) return e;
+    if ((e = halo_map(&mA1, a->src1, a->src1_channels, a->src1_pix_stride, B, H, W, bw + 2, 18))) return e;
   } else {
     mA1 = mA0;
   }
@@ -338,7 +349,7 @@ int conv3_halo_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   HaloParams p;
   p.cpt0 = a->src0_channels / 64;
   p.cpt1 = a->src1 ? a->src1_channels / 64 : 0;
-  p.blocks_x = W / 16;
+  p.blocks_x = W / bw;
   p.blocks_y = H / 16;
   p.m_blocks = B * p.blocks_x * p.blocks_y;
   p.n_tiles = a->n_total / bn;
@@ -346,6 +357,7 @@ int conv3_halo_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   p.n_total = a->n_total;
   const int slots = conv3_halo_stat_rows(B, H, W, a->n_total);
   const int grid = slots * p.n_tiles;
+  if (bn == 256) return halo_launch_t<256>(mA0, mA1, mB, mD, p, grid, stream);
   if (bn == 128) return halo_launch_t<128>(mA0, mA1, mB, mD, p, grid, stream);
   return halo_launch_t<64>(mA0, mA1, mB, mD, p, grid, stream);
 }
