@@ -166,6 +166,12 @@ int sunet_colsum_finalize(const float* stats, int rows, int n_total, int col_off
 int sunet_heads_fwd(const void* a, int a_pix_stride, const float* w0, const float* b0, const float* w1,
                     const float* b1, const float* w2, const float* b2, int nheads, float* logits, long long pixels,
                     sunet_stream_t stream);
+/* last block fused: a = relu(y*scale + shift) (64 channels, written for backward) and the heads' logits
+ * from the same registers (model.py:12-13 of decoder_layer_1_1 + :96-101) */
+int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
+                        int a_pix_stride, const float* w0, const float* b0, const float* w1, const float* b1,
+                        const float* w2, const float* b2, int nheads, float* logits, long long pixels,
+                        sunet_stream_t stream);
 /* dA[p][c] = sum_h dl[h][p]*w_h[c] (bf16);  dw_h[c] = sum_p dl[h][p]*a[p][c];  db_h = sum_p dl[h][p] */
 int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,
                     const float* w2, int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0, float* dw1,

@@ -297,6 +297,20 @@ def ew_heads_loss(K):
     af = a.float().reshape(P, 64)
     ref = torch.stack([af @ w.reshape(64) + b for w, b in zip(ws_, bs_)])
     ok &= report("heads fwd", logits, ref, 1e-5)
+    # fused BN+ReLU+heads must reproduce (bn_relu -> heads_fwd) exactly
+    yraw = torch.randn(B, H, W, 64, generator=g).to(dev).to(torch.bfloat16)
+    sc_ = (torch.rand(64, generator=g) + 0.5).to(dev)
+    sh_ = (torch.randn(64, generator=g) * 0.3).to(dev)
+    a1 = torch.empty_like(yraw)
+    a2 = torch.empty_like(yraw)
+    lg1, lg2 = torch.empty(3, P, device=dev), torch.empty(3, P, device=dev)
+    K.bn_relu_pool(yraw, sc_, sh_, a1, None)
+    K.heads_fwd(a1, ws_, bs_, lg1)
+    K.bn_relu_heads(yraw, sc_, sh_, a2, ws_, bs_, lg2)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(a1, a2)) and bool(torch.equal(lg1, lg2))
+    print(f"  [{'OK ' if same else 'BAD'}] fused bn_relu_heads == bn_relu + heads_fwd (bitwise)")
+    ok &= same
     # losses vs autograd of the reference formula (stable form)
     tgt = (torch.rand(P, generator=g) < 0.4).float().to(dev)
     lg = ref.clone().requires_grad_(True)

@@ -83,6 +83,7 @@ SIGNATURES = {
                                _vp, _sz, _vp],
     "sunet_colsum_finalize": [_vp, _i, _i, _i, _i, _vp, _vp],
     "sunet_heads_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp],
+    "sunet_bn_relu_heads": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp],
     "sunet_heads_bwd": [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _sz, _vp],
     "sunet_loss_sums": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _sz, _vp],
     "sunet_loss_finalize": [_vp, _ll, _f, _f, _vp, _vp],

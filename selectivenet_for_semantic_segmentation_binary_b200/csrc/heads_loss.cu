@@ -83,6 +83,72 @@ heads_fwd_kernel(const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nhea
   }
 }
 
+// ------------------------------------------------------------------ BN + ReLU of the last block fused with the heads
+// a = relu(y*scale + shift) is written once (backward needs it) and the three 64->1 dots are taken from
+// the registers that just produced it: saves re-reading the 8.4 MB/patch activation (heads_fwd_kernel).
+__global__ void __launch_bounds__(256)
+bn_relu_heads_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
+                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
+                     float* __restrict__ logits, long long P) {
+  const int sub = threadIdx.x & 7;
+  float w[3][8], bias[3], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + sub * 8 + j);
+    sh[j] = __ldg(shift + sub * 8 + j);
+  }
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    bias[h] = (h < nheads) ? __ldg(hw.b[h]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[h][j] = (h < nheads) ? __ldg(hw.w[h] + sub * 8 + j) : 0.f;
+  }
+  constexpr int U = 4;
+  const long long ppb = (long long)(blockDim.x >> 3);       // pixels per block per sub-trip (32)
+  // trip count is uniform across the block (bounds depend on blockIdx only), so full-mask shuffles are legal
+  for (long long base = blockIdx.x * ppb * U; base < P; base += (long long)gridDim.x * ppb * U) {
+    bf16x8 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = base + u * ppb + (threadIdx.x >> 3);
+      v[u] = bf16x8{{0u, 0u, 0u, 0u}};
+      if (p < P) v[u] = *reinterpret_cast<const bf16x8*>(y + p * ys + sub * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = base + u * ppb + (threadIdx.x >> 3);
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[2 * i] = fmaxf(fmaf(bf16lo(v[u].w[i]), sc[2 * i], sh[2 * i]), 0.f);
+        f[2 * i + 1] = fmaxf(fmaf(bf16hi(v[u].w[i]), sc[2 * i + 1], sh[2 * i + 1]), 0.f);
+      }
+      bf16x8 o;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o.w[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      if (p < P) *reinterpret_cast<bf16x8*>(a + p * as + sub * 8) = o;
+      float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // the heads read the bf16-rounded activation, exactly as the un-fused path does
+        const float lo = bf16lo(o.w[i]), hi = bf16hi(o.w[i]);
+#pragma unroll
+        for (int h = 0; h < 3; ++h) acc[h] = fmaf(lo, w[h][2 * i], fmaf(hi, w[h][2 * i + 1], acc[h]));
+      }
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+        acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 2);
+        acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 4);
+      }
+      if (p < P && sub < nheads) {
+        const float r = sub == 0 ? acc[0] + bias[0] : (sub == 1 ? acc[1] + bias[1] : acc[2] + bias[2]);
+        logits[(long long)sub * P + p] = r;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ heads backward
 __global__ void __launch_bounds__(256)
 heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
@@ -347,6 +413,22 @@ extern "C" int sunet_heads_fwd(const void* a, int a_pix_stride, const float* w0,
   heads_fwd_kernel<<<grid_for(pixels * 8, 256, 8), 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(a),
                                                                       a_pix_stride, hw, nheads, logits, pixels);
   return check_launch("heads_fwd");
+}
+
+extern "C" int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
+                                   int a_pix_stride, const float* w0, const float* b0, const float* w1,
+                                   const float* b1, const float* w2, const float* b2, int nheads, float* logits,
+                                   long long pixels, sunet_stream_t stream_) {
+  if (!y || !scale || !shift || !a || !logits || pixels <= 0 || (nheads != 1 && nheads != 3) || y_pix_stride < 64 ||
+      y_pix_stride % 8 || a_pix_stride < 64 || a_pix_stride % 8)
+    return set_error(SUNET_ERR_INVALID, "bn_relu_heads: bad arguments");
+  HeadW hw = {{w0, w1, w2}, {b0, b1, b2}};
+  for (int h = 0; h < nheads; ++h)
+    if (!hw.w[h] || !hw.b[h]) return set_error(SUNET_ERR_INVALID, "bn_relu_heads: missing head %d parameters", h);
+  bn_relu_heads_kernel<<<grid_for(pixels * 2, 256, 8), 256, 0, STREAM>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), y_pix_stride, scale, shift, reinterpret_cast<__nv_bfloat16*>(a),
+      a_pix_stride, hw, nheads, logits, pixels);
+  return check_launch("bn_relu_heads");
 }
 
 extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,

@@ -241,7 +241,13 @@ class SUNetPlan:
             K.bn_eval_affine(params[f"{n}.1.weight"], params[f"{n}.1.bias"], params[f"{n}.0.bias"],
                              buffers[f"{n}.1.running_mean"], buffers[f"{n}.1.running_var"], BN_EPS, ly.scale,
                              ly.shift)
-        K.bn_relu_pool(ly.y, ly.scale, ly.shift, ly.a, self.pool[ly.level] if ly.pool else None)
+        if n == "decoder_layer_1_1":
+            # last block: BN + ReLU fused with the three 1x1 heads
+            heads = ["conv1x1"] + (["conv_select", "conv_aux"] if self.selective else [])
+            K.bn_relu_heads(ly.y, ly.scale, ly.shift, ly.a, [params[f"{h}.weight"] for h in heads],
+                            [params[f"{h}.bias"] for h in heads], self.logits)
+        else:
+            K.bn_relu_pool(ly.y, ly.scale, ly.shift, ly.a, self.pool[ly.level] if ly.pool else None)
 
     def forward(self, x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor],
                 training: bool) -> torch.Tensor:
@@ -262,9 +268,6 @@ class SUNetPlan:
                         d_mode=K.D_SCATTER2X2)
             self._cbr_fwd(L[n2], params, buffers, training)
             self._cbr_fwd(L[n1], params, buffers, training)
-        heads = ["conv1x1"] + (["conv_select", "conv_aux"] if self.selective else [])
-        K.heads_fwd(L["decoder_layer_1_1"].a, [params[f"{h}.weight"] for h in heads],
-                    [params[f"{h}.bias"] for h in heads], self.logits)
         if training:
             self.generation += 1
         return self.logits

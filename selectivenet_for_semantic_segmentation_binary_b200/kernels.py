@@ -208,6 +208,18 @@ def heads_fwd(a, weights, biases, logits) -> None:
                                            _stream()), "sunet_heads_fwd")
 
 
+def bn_relu_heads(y, scale, shift, a, weights, biases, logits) -> None:
+    yp, _, ys = _act(y)
+    ap, _, as_ = _act(a)
+    n = len(weights)
+    w = [_f32(t.reshape(-1)) for t in weights] + [None] * (3 - n)
+    b = [_f32(t.reshape(-1)) for t in biases] + [None] * (3 - n)
+    P = y.shape[0] * y.shape[1] * y.shape[2]
+    assert y.shape[3] == 64 and logits.dtype == torch.float32 and logits.is_contiguous() and logits.numel() == n * P
+    _lib.check(_lib.load().sunet_bn_relu_heads(yp, ys, _f32(scale), _f32(shift), ap, as_, w[0], b[0], w[1], b[1],
+                                               w[2], b[2], n, logits.data_ptr(), P, _stream()), "sunet_bn_relu_heads")
+
+
 def heads_bwd(dlogits, a, weights, dA, dws, dbs, workspace) -> None:
     ap, _, as_ = _act(a)
     dp, _, ds = _act(dA)
