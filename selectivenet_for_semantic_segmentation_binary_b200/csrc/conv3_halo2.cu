@@ -1,0 +1,372 @@
+// G1h2 — the halo-tile conv3x3 kernel on CTA PAIRS (tcgen05 cta_group::2).
+//
+// conv3_halo_kernel<64/128> is bound by shared-memory bandwidth, not by the tensor pipe: an M=128,
+// N=128 MMA reads 8 KB of operands per 64 tensor cycles (128 B/clk, the whole SMEM port), N=64 needs
+// 192 B/clk, and TMA fills + epilogue staging compete for the same port (scripts/mma_rate.py: N=64 tops
+// out at 62 % of tensor peak even with nothing else touching SMEM).  With cta_group::2 the two CTAs of a
+// cluster issue ONE M=256 MMA: each supplies its own 128 pixel rows (its own halo tile) but only HALF
+// of the weight rows, so per-SM operand reads and weight TMA traffic drop by a quarter to a third.
+//
+// Differences from conv3_halo.cu: cluster of 2 CTAs; the pair works on blocks (2j, 2j+1); "full" barriers
+// live in the leader CTA and are signalled by both CTAs' TMA loads (peer-bit-masked barrier address) plus
+// one plain arrival per CTA; the leader alone issues tcgen05.mma.cta_group::2 and multicasts its commits
+// to both CTAs' "empty" / "tmem full" barriers; both epilogues release the accumulators to the leader.
+#include <stdlib.h>
+
+#include "common.h"
+#include "ptx.cuh"
+#include "../../include/sunet_b200.h"
+
+namespace sunet {
+
+struct Halo2Params {
+  int cpt0, cpt1;
+  int blocks_x, blocks_y;
+  int m_blocks, n_tiles;
+  float* stats;              // [gridDim.x / n_tiles][n_total][2] or nullptr (one row per CTA)
+  int n_total;
+};
+
+template <int BN>
+struct H2Cfg {
+  static constexpr int PITCH = 18;
+  static constexpr int A_TX = 18 * 18 * 128;
+  static constexpr int A_SLOT = 41 * 1024;
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_HALF = (BN / 2) * 128;      // this CTA's half of one weight tile
+  static constexpr int B_STAGES = 10;
+  static constexpr int STG_BYTES = 128 * 128;
+  static constexpr int SMEM = A_STAGES * A_SLOT + B_STAGES * B_HALF + 2 * STG_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = 4 * BN;           // 2 tiles x BN columns x 2 accumulator stages
+};
+
+constexpr int kH2Threads = 192;
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
+conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
+                   const Halo2Params p) {
+  using C = H2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + C::A_STAGES * C::A_SLOT;
+  uint8_t* sStg = sB + C::B_STAGES * C::B_HALF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * C::STG_BYTES);
+  uint64_t* afull = bars;
+  uint64_t* aempty = afull + C::A_STAGES;
+  uint64_t* bfull = aempty + C::A_STAGES;
+  uint64_t* bempty = bfull + C::B_STAGES;
+  uint64_t* tfull = bempty + C::B_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::A_STAGES; ++i) {
+      mbar_init(&afull[i], 2);      // one arrival per CTA of the pair (+ both CTAs' TMA bytes)
+      mbar_init(&aempty[i], 1);
+    }
+    for (int i = 0; i < C::B_STAGES; ++i) {
+      mbar_init(&bfull[i], 2);
+      mbar_init(&bempty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);     // 4 epilogue warps x 2 CTAs (only the leader's copy is waited on)
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapD);
+  }
+  __syncthreads();
+  cluster_sync_all();               // both CTAs' barriers exist before anything signals across the pair
+  if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int pair = blockIdx.x >> 1;
+  const int n_tile = pair % p.n_tiles;
+  const int m_first = pair / p.n_tiles;
+  const int m_step = (gridDim.x >> 1) / p.n_tiles;
+  const int m_pairs = (p.m_blocks + 1) >> 1;
+  const int cpt = p.cpt0 + p.cpt1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer (both CTAs)
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int mp = m_first; mp < m_pairs; mp += m_step) {
+      const int mb = 2 * mp + (int)rank;           // may be == m_blocks for the odd tail: n lands out of range -> zeros
+      const int bx = mb % p.blocks_x;
+      const int by = (mb / p.blocks_x) % p.blocks_y;
+      const int n = mb / (p.blocks_x * p.blocks_y);
+      for (int cc = 0; cc < cpt; ++cc) {
+        const CUtensorMap* mapA = (cc < p.cpt0) ? &mapA0 : &mapA1;
+        const int c0 = ((cc < p.cpt0) ? cc : cc - p.cpt0) * 64;
+        mbar_wait(&aempty[as], aph ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&afull[as], 2 * C::A_TX);
+          else mbar_arrive_remote(&afull[as], 0);
+          tma_load_5d_pair(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * 16 - 1, by * 16 - 1, n, 0);
+        }
+        __syncwarp();
+        if (++as == C::A_STAGES) {
+          as = 0;
+          aph ^= 1;
+        }
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&bempty[bs], bph ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&bfull[bs], 2 * C::B_HALF);
+            else mbar_arrive_remote(&bfull[bs], 0);
+            tma_load_2d_pair(sB + bs * C::B_HALF, &mapB, &bfull[bs], (tap * cpt + cc) * 64,
+                             n_tile * BN + (int)rank * (BN / 2));
+          }
+          __syncwarp();
+          if (++bs == C::B_STAGES) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer (leader CTA only)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, false, false);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int mp = m_first; mp < m_pairs; mp += m_step, ++it) {
+        const int acs = it & 1;
+        const uint32_t acph = (it >> 1) & 1;
+        mbar_wait(&tempty[acs], acph ^ 1);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acs * (2 * BN);
+        for (int cc = 0; cc < cpt; ++cc) {
+          mbar_wait(&afull[as], aph);
+          tc_fence_after_sync();
+          const uint32_t a_base = smem_u32(sA + as * C::A_SLOT);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bfull[bs], bph);
+            tc_fence_after_sync();
+            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + bs * C::B_HALF), 16, 1024);
+            const int r = tap / 3, s = tap - r * 3;
+            if (elect_one()) {
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const uint64_t adesc =
+                    make_smem_desc_sw128(a_base + (r * C::PITCH + 8 * t + s) * 128, 16, C::PITCH * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_pair(tmem_d + t * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+              }
+              umma_commit_pair(&bempty[bs]);
+            }
+            __syncwarp();
+            if (++bs == C::B_STAGES) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+          if (elect_one()) umma_commit_pair(&aempty[as]);
+          __syncwarp();
+          if (++as == C::A_STAGES) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit_pair(&tfull[acs]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue (both CTAs, 128 threads each)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const bool issuer = (threadIdx.x == 64);
+    constexpr int NCHUNK = BN / 64;
+    float ssum[NCHUNK][2], ssq[NCHUNK][2];
+#pragma unroll
+    for (int q = 0; q < NCHUNK; ++q) ssum[q][0] = ssum[q][1] = ssq[q][0] = ssq[q][1] = 0.f;
+
+    int it = 0;
+    uint32_t chunk_ctr = 0;
+    for (int mp = m_first; mp < m_pairs; mp += m_step, ++it) {
+      const int acs = it & 1;
+      const uint32_t acph = (it >> 1) & 1;
+      const int mb = 2 * mp + (int)rank;
+      const int bx = mb % p.blocks_x;
+      const int by = (mb / p.blocks_x) % p.blocks_y;
+      const int n = mb / (p.blocks_x * p.blocks_y);
+      mbar_wait(&tfull[acs], acph);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int q = 0; q < NCHUNK; ++q, ++chunk_ctr) {
+          uint32_t v[64];
+          const uint32_t taddr =
+              tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * (2 * BN) + t * BN + q * 64;
+          tmem_ld_32x32b_x32(taddr, v);
+          tmem_ld_32x32b_x32(taddr + 32, v + 32);
+          tmem_ld_wait();
+          const int ncol0 = n_tile * BN + q * 64;
+          uint8_t* stg = sStg + (chunk_ctr & 1) * C::STG_BYTES;
+          uint4* rowp = reinterpret_cast<uint4*>(stg + row * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+            w.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+            w.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+            w.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            rowp[j ^ (row & 7)] = w;
+          }
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_5d(&mapD, stg, ncol0, bx * 16 + 8 * t, by * 16, n, 0);   // out-of-range n: clipped
+            tma_store_commit();
+          }
+          if (p.stats != nullptr) {
+            const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int rr = quad * 32 + r;
+              const uint32_t w = words[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+              const float a = bf16lo(w), b = bf16hi(w);
+              s0 += a;
+              s1 += b;
+              q0 = fmaf(a, a, q0);
+              q1 = fmaf(b, b, q1);
+            }
+            ssum[q][0] += s0;
+            ssum[q][1] += s1;
+            ssq[q][0] += q0;
+            ssq[q][1] += q1;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty[acs]);
+        else mbar_arrive_remote(&tempty[acs], 0);
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+    if (p.stats != nullptr) {
+      named_bar_sync(1, 128);
+      float* red = reinterpret_cast<float*>(sStg);
+#pragma unroll
+      for (int q = 0; q < NCHUNK; ++q) {
+        const int c = q * 64 + lane * 2;
+        red[(quad * BN + c) * 2 + 0] = ssum[q][0];
+        red[(quad * BN + c) * 2 + 1] = ssq[q][0];
+        red[(quad * BN + c + 1) * 2 + 0] = ssum[q][1];
+        red[(quad * BN + c + 1) * 2 + 1] = ssq[q][1];
+      }
+      named_bar_sync(1, 128);
+      const int t = threadIdx.x - 64;
+      const int srow = m_first * 2 + (int)rank;      // one partial row per CTA
+      float* dst = p.stats + (static_cast<size_t>(srow) * p.n_total + n_tile * BN) * 2;
+      for (int i = t; i < BN * 2; i += 128) dst[i] = red[i] + red[BN * 2 + i] + red[2 * BN * 2 + i] + red[3 * BN * 2 + i];
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();               // nobody leaves (or frees TMEM) while the pair may still touch it
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+  }
+}
+
+static int halo2_map(CUtensorMap* m, const void* base, int C, int S, int B, int H, int W, int bw, int bh) {
+  uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B, 1};
+  uint64_t str[4] = {(uint64_t)S * 2, (uint64_t)W * S * 2, (uint64_t)H * W * S * 2, (uint64_t)B * H * W * S * 2};
+  uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, 1, 1};
+  return make_tmap_bf16_5d(m, base, dims, str, box);
+}
+
+template <int BN>
+static int halo2_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d,
+                          const Halo2Params& p, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int e = check_cuda(cudaFuncSetAttribute(conv3_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            H2Cfg<BN>::SMEM),
+                       "cudaFuncSetAttribute(conv3_halo2)");
+    if (e) return e;
+    attr_set = true;
+  }
+  conv3_halo2_kernel<BN><<<grid, kH2Threads, H2Cfg<BN>::SMEM, stream>>>(a0, a1, b, d, p);
+  return check_launch("conv3_halo2_kernel");
+}
+
+bool conv3_halo2_eligible(const sunet_conv_gemm_args* a) {
+  static const int mode = [] {
+    const char* e = getenv("SUNET_HALO_2CTA");
+    return e ? atoi(e) : 0;
+  }();
+  if (!mode) return false;
+  const bool narrow = (a->n_total % 256 != 0) && (a->n_total % 64 == 0);
+  return narrow && a->a_mode == SUNET_A_CONV3X3 && a->d_mode == SUNET_D_NHWC && a->bias == nullptr &&
+         a->height % 16 == 0 && a->width % 16 == 0;
+}
+
+static int halo2_slots(int batch, int height, int width, int n_tiles) {
+  const int m_pairs = (batch * (height / 16) * (width / 16) + 1) / 2;
+  int slots = (num_sms() / 2) / n_tiles;
+  if (slots < 1) slots = 1;
+  if (slots > m_pairs) slots = m_pairs;
+  return slots;
+}
+
+int conv3_halo2_stat_rows(int batch, int height, int width, int n_total) {
+  const int bn = (n_total % 128 == 0) ? 128 : 64;
+  return 2 * halo2_slots(batch, height, width, n_total / bn);
+}
+
+int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
+  const int B = a->batch, H = a->height, W = a->width;
+  const int bn = (a->n_total % 128 == 0) ? 128 : 64;
+  CUtensorMap mA0, mA1, mB, mD;
+  int e;
+  if ((e = halo2_map(&mA0, a->src0, a->src0_channels, a->src0_pix_stride, B, H, W, 18, 18))) return e;
+  if (a->src1) {
+    if ((e = halo2_map(&mA1, a->src1, a->src1_channels, a->src1_pix_stride, B, H, W, 18, 18))) return e;
+  } else {
+    mA1 = mA0;
+  }
+  if ((e = make_tmap_bf16_2d(&mB, a->weights, (uint64_t)a->k_total, (uint64_t)a->n_total, (uint64_t)a->k_total * 2,
+                             (uint32_t)(bn / 2))))
+    return e;
+  if ((e = halo2_map(&mD, a->dst, a->n_total, a->dst_pix_stride, B, H, W, 8, 16))) return e;
+  Halo2Params p;
+  p.cpt0 = a->src0_channels / 64;
+  p.cpt1 = a->src1 ? a->src1_channels / 64 : 0;
+  p.blocks_x = W / 16;
+  p.blocks_y = H / 16;
+  p.m_blocks = B * p.blocks_x * p.blocks_y;
+  p.n_tiles = a->n_total / bn;
+  p.stats = a->stats;
+  p.n_total = a->n_total;
+  const int grid = halo2_slots(B, H, W, p.n_tiles) * p.n_tiles * 2;
+  if (bn == 128) return halo2_launch_t<128>(mA0, mA1, mB, mD, p, grid, stream);
+  return halo2_launch_t<64>(mA0, mA1, mB, mD, p, grid, stream);
+}
+
+}  // namespace sunet

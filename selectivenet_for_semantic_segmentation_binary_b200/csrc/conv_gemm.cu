@@ -400,12 +400,16 @@ namespace sunet {
 bool conv3_halo_eligible(const sunet_conv_gemm_args* a);
 int conv3_halo_stat_rows(int batch, int height, int width, int n_total);
 int conv3_halo_launch(const sunet_conv_gemm_args* a, cudaStream_t stream);
+bool conv3_halo2_eligible(const sunet_conv_gemm_args* a);
+int conv3_halo2_stat_rows(int batch, int height, int width, int n_total);
+int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream);
 }  // namespace sunet
 
 extern "C" int sunet_conv_gemm_stat_rows(const sunet_conv_gemm_args* a) {
   if (!a) return -1;
   const int batch = a->batch, height = a->height, width = a->width, n_total = a->n_total;
   if (batch <= 0 || height <= 0 || width <= 0 || n_total <= 0 || n_total % 64) return -1;
+  if (conv3_halo2_eligible(a)) return conv3_halo2_stat_rows(batch, height, width, n_total);
   if (conv3_halo_eligible(a)) return conv3_halo_stat_rows(batch, height, width, n_total);
   TileGeom g = tile_geom(batch, height, width, 128);
   const int bn = pick_bn(n_total);
@@ -442,6 +446,7 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
   if (a->d_mode == SUNET_D_SCATTER2X2 && (a->n_total % 4 || (a->n_total / 4) % 64))
     return set_error(SUNET_ERR_INVALID, "conv_gemm: scatter store needs n_total = 4 x (multiple of 64)");
 
+  if (conv3_halo2_eligible(a)) return conv3_halo2_launch(a, stream);
   if (conv3_halo_eligible(a)) return conv3_halo_launch(a, stream);
 
   TileGeom g = tile_geom(B, H, W, 128);
