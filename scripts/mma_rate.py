@@ -20,3 +20,14 @@ for n in (64, 128, 192, 256):
         cyc = out.double().mean().item() / (4 * iters)
         print(f"N={n:3d} A={'MN' if a_mn else 'K '} B={'MN' if b_mn else 'K '}: {cyc:7.1f} cycles/MMA  (ideal {n / 2:5.1f}) -> "
               f"{100 * (n / 2) / cyc:5.1f}% of tensor peak", flush=True)
+
+raw.sunet_dbg_mma_probe_pair.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+pairs = grid // 2
+print("CTA pairs (cta_group::2, M=256): ideal = n/2 cycles per MMA if both SMs run at full rate")
+for n in (64, 128, 256):
+    for _ in range(2):
+        rc = raw.sunet_dbg_mma_probe_pair(n, iters, pairs, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.sunet_last_error()
+        torch.cuda.synchronize()
+    cyc = out[:pairs].double().mean().item() / (4 * iters)
+    print(f"N={n:3d} pair: {cyc:7.1f} cycles/MMA (256 x {n} x 16)  (ideal {n / 2:5.1f}) -> {100 * (n / 2) / cyc:5.1f}% of tensor peak", flush=True)

@@ -68,11 +68,11 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::A_STAGES; ++i) {
-      mbar_init(&afull[i], 2);      // one arrival per CTA of the pair (+ both CTAs' TMA bytes)
+      mbar_init(&afull[i], 1);      // the leader's arrive.expect_tx covers BOTH CTAs' TMA bytes
       mbar_init(&aempty[i], 1);
     }
     for (int i = 0; i < C::B_STAGES; ++i) {
-      mbar_init(&bfull[i], 2);
+      mbar_init(&bfull[i], 1);
       mbar_init(&bempty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -113,8 +113,9 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const int c0 = ((cc < p.cpt0) ? cc : cc - p.cpt0) * 64;
         mbar_wait(&aempty[as], aph ^ 1);
         if (elect_one()) {
+          // Only the leader arrives.  The peer cannot run a phase ahead: it refills slot s only after the
+          // leader's MMAs that consumed the previous contents have committed to its aempty[s].
           if (rank == 0) mbar_arrive_expect_tx(&afull[as], 2 * C::A_TX);
-          else mbar_arrive_remote(&afull[as], 0);
           tma_load_5d_pair(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * 16 - 1, by * 16 - 1, n, 0);
         }
         __syncwarp();
@@ -126,7 +127,6 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           mbar_wait(&bempty[bs], bph ^ 1);
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&bfull[bs], 2 * C::B_HALF);
-            else mbar_arrive_remote(&bfull[bs], 0);
             tma_load_2d_pair(sB + bs * C::B_HALF, &mapB, &bfull[bs], (tap * cpt + cc) * 64,
                              n_tile * BN + (int)rank * (BN / 2));
           }

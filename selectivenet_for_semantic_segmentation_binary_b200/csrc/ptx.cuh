@@ -222,7 +222,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
