@@ -27,17 +27,19 @@ struct Halo2Params {
   int n_total;
 };
 
+// TILES = M=128 tiles per CTA and block: 2 (16x16 block) for BN <= 128, 1 (8 wide x 16 tall) for BN = 256
 template <int BN>
 struct H2Cfg {
-  static constexpr int PITCH = 18;
-  static constexpr int A_TX = 18 * 18 * 128;
-  static constexpr int A_SLOT = 41 * 1024;
+  static constexpr int TILES = (BN == 256) ? 1 : 2;
+  static constexpr int PITCH = 8 * TILES + 2;
+  static constexpr int A_TX = 18 * PITCH * 128;
+  static constexpr int A_SLOT = (A_TX + 1023) / 1024 * 1024;
   static constexpr int A_STAGES = 2;
   static constexpr int B_HALF = (BN / 2) * 128;      // this CTA's half of one weight tile
-  static constexpr int B_STAGES = 10;
+  static constexpr int B_STAGES = (BN == 256) ? 8 : 10;
   static constexpr int STG_BYTES = 128 * 128;
   static constexpr int SMEM = A_STAGES * A_SLOT + B_STAGES * B_HALF + 2 * STG_BYTES + 1024 + 512;
-  static constexpr int TMEM_COLS = 4 * BN;           // 2 tiles x BN columns x 2 accumulator stages
+  static constexpr int TMEM_COLS = 2 * TILES * BN;   // TILES x BN columns x 2 accumulator stages
 };
 
 constexpr int kH2Threads = 192;
@@ -116,7 +118,7 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           // Only the leader arrives.  The peer cannot run a phase ahead: it refills slot s only after the
           // leader's MMAs that consumed the previous contents have committed to its aempty[s].
           if (rank == 0) mbar_arrive_expect_tx(&afull[as], 2 * C::A_TX);
-          tma_load_5d_pair(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * 16 - 1, by * 16 - 1, n, 0);
+          tma_load_5d_pair(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * (8 * C::TILES) - 1, by * 16 - 1, n, 0);
         }
         __syncwarp();
         if (++as == C::A_STAGES) {
@@ -150,7 +152,7 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const uint32_t acph = (it >> 1) & 1;
         mbar_wait(&tempty[acs], acph ^ 1);
         tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + acs * (2 * BN);
+        const uint32_t tmem_d = tmem_base + acs * (C::TILES * BN);
         for (int cc = 0; cc < cpt; ++cc) {
           mbar_wait(&afull[as], aph);
           tc_fence_after_sync();
@@ -162,7 +164,7 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
             const int r = tap / 3, s = tap - r * 3;
             if (elect_one()) {
 #pragma unroll
-              for (int t = 0; t < 2; ++t) {
+              for (int t = 0; t < C::TILES; ++t) {
                 const uint64_t adesc =
                     make_smem_desc_sw128(a_base + (r * C::PITCH + 8 * t + s) * 128, 16, C::PITCH * 128);
 #pragma unroll
@@ -210,12 +212,12 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       mbar_wait(&tfull[acs], acph);
       tc_fence_after_sync();
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < C::TILES; ++t) {
 #pragma unroll
         for (int q = 0; q < NCHUNK; ++q, ++chunk_ctr) {
           uint32_t v[64];
           const uint32_t taddr =
-              tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * (2 * BN) + t * BN + q * 64;
+              tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acs * (C::TILES * BN) + t * BN + q * 64;
           tmem_ld_32x32b_x32(taddr, v);
           tmem_ld_32x32b_x32(taddr + 32, v + 32);
           tmem_ld_wait();
@@ -235,7 +237,7 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           if (issuer) tma_store_wait_read<0>();
           named_bar_sync(1, 128);
           if (issuer) {
-            tma_store_5d(&mapD, stg, ncol0, bx * 16 + 8 * t, by * 16, n, 0);   // out-of-range n: clipped
+            tma_store_5d(&mapD, stg, ncol0, bx * (8 * C::TILES) + 8 * t, by * 16, n, 0);   // out-of-range n: clipped
             tma_store_commit();
           }
           if (p.stats != nullptr) {
@@ -318,17 +320,22 @@ static int halo2_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 
 bool conv3_halo2_eligible(const sunet_conv_gemm_args* a) {
   static const int mode = [] {
-    const char* e = getenv("SUNET_HALO_2CTA");
-    return e ? atoi(e) : 0;
+    const char* e = getenv("SUNET_HALO_2CTA");     // default on; SUNET_HALO_2CTA=0 falls back to conv3_halo_kernel
+    return e ? atoi(e) : 1;
   }();
   if (!mode) return false;
-  const bool narrow = (a->n_total % 256 != 0) && (a->n_total % 64 == 0);
-  return narrow && a->a_mode == SUNET_A_CONV3X3 && a->d_mode == SUNET_D_NHWC && a->bias == nullptr &&
+  const bool ok_n = (a->n_total % 64 == 0) && (a->n_total % 256 != 0 || getenv("SUNET_HALO2_NO256") == nullptr);
+  return ok_n && a->a_mode == SUNET_A_CONV3X3 && a->d_mode == SUNET_D_NHWC && a->bias == nullptr &&
          a->height % 16 == 0 && a->width % 16 == 0;
 }
 
-static int halo2_slots(int batch, int height, int width, int n_tiles) {
-  const int m_pairs = (batch * (height / 16) * (width / 16) + 1) / 2;
+static int halo2_bn(int n_total) {
+  if (n_total % 256 == 0) return 256;
+  return (n_total % 128 == 0) ? 128 : 64;
+}
+
+static int halo2_slots(int batch, int height, int width, int n_tiles, int bw) {
+  const int m_pairs = (batch * (height / 16) * (width / bw) + 1) / 2;
   int slots = (num_sms() / 2) / n_tiles;
   if (slots < 1) slots = 1;
   if (slots > m_pairs) slots = m_pairs;
@@ -336,18 +343,19 @@ static int halo2_slots(int batch, int height, int width, int n_tiles) {
 }
 
 int conv3_halo2_stat_rows(int batch, int height, int width, int n_total) {
-  const int bn = (n_total % 128 == 0) ? 128 : 64;
-  return 2 * halo2_slots(batch, height, width, n_total / bn);
+  const int bn = halo2_bn(n_total);
+  return 2 * halo2_slots(batch, height, width, n_total / bn, bn == 256 ? 8 : 16);
 }
 
 int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   const int B = a->batch, H = a->height, W = a->width;
-  const int bn = (a->n_total % 128 == 0) ? 128 : 64;
+  const int bn = halo2_bn(a->n_total);
+  const int bw = (bn == 256) ? 8 : 16;
   CUtensorMap mA0, mA1, mB, mD;
   int e;
-  if ((e = halo2_map(&mA0, a->src0, a->src0_channels, a->src0_pix_stride, B, H, W, 18, 18))) return e;
+  if ((e = halo2_map(&mA0, a->src0, a->src0_channels, a->src0_pix_stride, B, H, W, bw + 2, 18))) return e;
   if (a->src1) {
-    if ((e = halo2_map(&mA1, a->src1, a->src1_channels, a->src1_pix_stride, B, H, W, 18, 18))) return e;
+    if ((e = halo2_map(&mA1, a->src1, a->src1_channels, a->src1_pix_stride, B, H, W, bw + 2, 18))) return e;
   } else {
     mA1 = mA0;
   }
@@ -358,13 +366,14 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   Halo2Params p;
   p.cpt0 = a->src0_channels / 64;
   p.cpt1 = a->src1 ? a->src1_channels / 64 : 0;
-  p.blocks_x = W / 16;
+  p.blocks_x = W / bw;
   p.blocks_y = H / 16;
   p.m_blocks = B * p.blocks_x * p.blocks_y;
   p.n_tiles = a->n_total / bn;
   p.stats = a->stats;
   p.n_total = a->n_total;
-  const int grid = halo2_slots(B, H, W, p.n_tiles) * p.n_tiles * 2;
+  const int grid = halo2_slots(B, H, W, p.n_tiles, bw) * p.n_tiles * 2;
+  if (bn == 256) return halo2_launch_t<256>(mA0, mA1, mB, mD, p, grid, stream);
   if (bn == 128) return halo2_launch_t<128>(mA0, mA1, mB, mD, p, grid, stream);
   return halo2_launch_t<64>(mA0, mA1, mB, mD, p, grid, stream);
 }

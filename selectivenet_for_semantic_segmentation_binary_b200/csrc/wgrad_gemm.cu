@@ -217,6 +217,157 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 
+// ------------------------------------------------------------------ CTA-pair variant (A channels >= 256)
+// tcgen05 cta_group::2: one M=256 MMA spans two CTAs; each loads its own 128 dY channels but only HALF
+// of the B channels (64 of the 128-wide tile), so B TMA traffic and per-SM operand reads drop by a third.
+// Launched as a 2-CTA cluster; barriers the leader's MMA warp waits on live in the leader CTA.
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
+                       const __grid_constant__ CUtensorMap mapB1, const WgradParams p, const int stage_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* done_bar = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);      // leader's arrive.expect_tx covers both CTAs' bytes
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB0);
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_pair(tmem_slot, p.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int item = blockIdx.x >> 1;
+  const int n_tile = item % p.n_tiles; item /= p.n_tiles;
+  const int m_pair = item % p.m_tiles; item /= p.m_tiles;      // m_tiles counts 256-channel pairs here
+  const int tg = item % p.tap_groups;  item /= p.tap_groups;
+  const int split = item;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  const int BNW = p.nb64 * 64;                                   // 128: N of the pair MMA
+  const int a_base = m_pair * 256 + (int)rank * 128;
+
+  if (warp == 0) {
+    const CUtensorMap* mapB = (n_tile < p.c0_blocks) ? &mapB0 : &mapB1;
+    const int cB = ((n_tile < p.c0_blocks) ? n_tile : (n_tile - p.c0_blocks)) * BNW + (int)rank * 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int xt = kb % p.tiles_x;
+      const int yt = (kb / p.tiles_x) % p.tiles_y;
+      const int nt = kb / (p.tiles_x * p.tiles_y);
+      const int x0 = xt * p.tw, y0 = yt * p.th, n0 = nt * p.nb;
+      uint8_t* st = smem + stage * stage_bytes;
+      uint8_t* sb = st + 2 * p.abox;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (2 * p.abox + p.bboxes * p.b_tx));
+        tma_load_5d_pair(st, &mapA, &full_bar[stage], a_base, x0, y0, n0, 0);
+        tma_load_5d_pair(st + p.abox, &mapA, &full_bar[stage], a_base + 64, x0, y0, n0, 0);
+        if (p.shifted) {
+          tma_load_5d_pair(sb, mapB, &full_bar[stage], cB, x0 - 1, y0 + tg - 1, n0, 0);
+        } else {
+          for (int t = 0; t < p.T; ++t) {
+            uint8_t* dst = sb + t * p.bslot;
+            if (p.mode == SUNET_A_GATHER2X2) {
+              tma_load_5d_pair(dst, mapB, &full_bar[stage], cB, t & 1, x0, t >> 1, n0 * p.H + y0);
+            } else if (p.mode == SUNET_A_CONV3X3) {
+              tma_load_5d_pair(dst, mapB, &full_bar[stage], cB, x0 + t - 1, y0 + tg - 1, n0, 0);
+            } else {
+              tma_load_5d_pair(dst, mapB, &full_bar[stage], cB, x0, y0, n0, 0);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, BNW, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sb = sa + 2 * p.abox;
+        const uint32_t tstep = p.shifted ? 128u : (uint32_t)p.bslot;
+        const int nkk = p.kp / 16;
+        if (elect_one()) {
+          uint64_t adesc = make_smem_desc_sw128(sa, p.abox, 1024);
+          uint64_t bdesc0 = make_smem_desc_sw128(sb, p.bslot, 1024);
+          for (int kk = 0; kk < nkk; ++kk) {
+            uint64_t bdesc = bdesc0;
+            for (int t = 0; t < p.T; ++t) {
+              umma_bf16_pair(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              bdesc += tstep >> 4;
+            }
+            adesc += 2048 >> 4;
+            bdesc0 += 2048 >> 4;
+          }
+          umma_commit_pair(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit_pair(done_bar);
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int mrow = a_base + quad * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after_sync();
+    for (int t = 0; t < p.T; ++t) {
+      const int tap = tg * p.T + t;
+      float* orow = p.out + ((static_cast<size_t>(split) * p.taps_total + tap) * p.Ca + mrow) * p.Nb + n_tile * BNW;
+      for (int c = 0; c < BNW; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + t * BNW + c, v);
+        tmem_ld_wait();
+        if (mrow < p.Ca) {
+          float4* o4 = reinterpret_cast<float4*>(orow + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem_base, p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------ 64-output-channel variant
 // conv3x3 layers with Cout = 64 (the three full-resolution layers = the largest pixel counts) would
 // waste half of an M=128 tile on dY.  Here the roles are swapped: N = the 64 dY channels, and M = 128 =
@@ -367,6 +518,7 @@ struct WgPlan {
   int shifted;
   int kp;
   int stacked;     // wgrad64_kernel
+  int pair;        // wgrad_gemm_pair_kernel (cta_group::2)
 };
 
 static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
@@ -384,6 +536,8 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   w->BNW = (a->b0_channels % 128 == 0 && (!a->b1 || a->b1_channels % 128 == 0)) ? 128 : 64;
   w->m_tiles = (a->a_channels + 127) / 128;
   w->n_tiles = w->Nb / w->BNW;
+  w->pair = (a->a_channels % 256 == 0 && w->BNW == 128 && getenv("SUNET_WGRAD_NO_PAIR") == nullptr) ? 1 : 0;
+  if (w->pair) w->m_tiles = a->a_channels / 256;
   const int B = a->batch, H = a->height, W = a->width;
   w->stacked = (a->b_mode == SUNET_A_CONV3X3 && a->a_channels == 64 && W % 64 == 0 &&
                 getenv("SUNET_WGRAD_NO_STACK") == nullptr) ? 1 : 0;
@@ -430,7 +584,7 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   w->tiles_n = (B + w->nb - 1) / w->nb;
   w->kb_total = w->tiles_x * w->tiles_y * w->tiles_n;
   w->shifted = (a->b_mode == SUNET_A_CONV3X3 && w->tw == kp && getenv("SUNET_WGRAD_NO_SHIFT") == nullptr) ? 1 : 0;
-  const int base_items = w->m_tiles * w->n_tiles * w->tap_groups;
+  const int base_items = w->m_tiles * w->n_tiles * w->tap_groups * (w->pair ? 2 : 1);   // CTAs per split
   // two full waves of CTAs (one CTA per SM at a time): round DOWN so no third, nearly empty wave appears
   int want = (2 * num_sms()) / base_items;
   // short problems: one wave of longer CTAs (prologue + partial-store epilogue cost ~10 us per CTA)
@@ -551,14 +705,15 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
   p.shifted = w.shifted;
   p.kp = w.kp;
   p.abox = w.kp * 128;
+  const int nb64_cta = w.pair ? p.nb64 / 2 : p.nb64;   // 64-channel B boxes each CTA loads per tap
   if (w.shifted) {
     p.b_tx = (w.kp + 2) * 128;                       // kp + 2 halo pixels
     p.bslot = (p.b_tx + 1023) / 1024 * 1024;         // padded to the 1024-byte swizzle atom
-    p.bboxes = p.nb64;
+    p.bboxes = nb64_cta;
   } else {
     p.bslot = p.abox;
     p.b_tx = p.abox;
-    p.bboxes = w.T * p.nb64;
+    p.bboxes = w.T * nb64_cta;
   }
   const int stage_bytes = 2 * p.abox + p.bboxes * p.bslot;
   const int bar_bytes = (2 * MAX_STAGES + 2) * 8;
@@ -576,6 +731,31 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     attr_set = true;
   }
   const int grid = w.m_tiles * w.n_tiles * w.tap_groups * w.splits;
+  if (w.pair) {
+    static bool attr_pair = false;
+    if (!attr_pair) {
+      if ((e = check_cuda(cudaFuncSetAttribute(wgrad_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               227 * 1024), "cudaFuncSetAttribute(wgrad_gemm_pair)")))
+        return e;
+      attr_pair = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid * 2);
+    cfg.blockDim = dim3(WG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if ((e = check_cuda(cudaLaunchKernelEx(&cfg, wgrad_gemm_pair_kernel, mA, mB0, mB1, p, stage_bytes),
+                        "cudaLaunchKernelEx(wgrad_gemm_pair)")))
+      return e;
+    return check_launch("wgrad_gemm_pair_kernel");
+  }
   wgrad_gemm_kernel<<<grid, WG_THREADS, smem, stream>>>(mA, mB0, mB1, p, stage_bytes);
   return check_launch("wgrad_gemm_kernel");
 }
