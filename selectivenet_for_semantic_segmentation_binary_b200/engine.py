@@ -19,6 +19,7 @@ H/2^(L-1), channels 64*2^(L-1)):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -124,7 +125,13 @@ class SUNetPlan:
 
         # ---- backward scratch
         self.gA = {L: act(L, _CH[L]) for L in (1, 2, 3, 4)}
-        self.gB = {L: act(L, _CH[L]) for L in (1, 2, 3, 4)}
+        # dY buffers, two per level: the weight-gradient GEMM of layer L runs on a side stream while the main
+        # stream already produces dY of layer L-1 into the other buffer
+        self.gB = {L: (act(L, _CH[L]), act(L, _CH[L])) for L in (1, 2, 3, 4)}
+        self._gB_next = {L: 0 for L in (1, 2, 3, 4)}
+        self._gB_busy = {L: [None, None] for L in (1, 2, 3, 4)}      # event: last wgrad that read the buffer
+        self.side = torch.cuda.Stream(device=dev)
+        self.overlap_wgrad = os.environ.get("SUNET_OVERLAP_WGRAD", "1") != "0"
         self.dcat = {L: act(L, 2 * _CH[L]) for L in (1, 2, 3)}
         self.dpool = {L: act(L + 1, _CH[L]) for L in (1, 2, 3)}
         self.dcat_stats = {}
@@ -144,7 +151,7 @@ class SUNetPlan:
         B = self.B
         for ly in self.order:
             h, w = self.hw[ly.level]
-            dy = self.gB[ly.level]
+            dy = self.gB[ly.level][0]
             if ly.kind == "first":
                 s = K.wgrad_splits((B, h, w), dy, K.A_PLAIN, self.col)
                 need = max(need, s * 1 * ly.cout * 64)
@@ -273,26 +280,52 @@ class SUNetPlan:
         return self.logits
 
     # ------------------------------------------------------------------ backward
+    def _on_side(self, fn):
+        """Run fn() (weight-gradient launches) on the side stream, ordered after everything enqueued so far on
+        the current stream.  Returns the completion event (None when overlap is off)."""
+        if not self.overlap_wgrad:
+            fn()
+            return None
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self.side)
+        return done
+
     def _cbr_bwd(self, ly: _Layer, dA: Optional[torch.Tensor], dPool: Optional[torch.Tensor], params, grads,
                  dgrad_out: Optional[torch.Tensor], dgrad_stats: Optional[torch.Tensor] = None):
-        """dA/dPool -> (dgamma, dbeta, dy) -> weight grad, and the input gradient into dgrad_out."""
+        """dA/dPool -> (dgamma, dbeta, dy) -> weight grad (side stream), and the input gradient into dgrad_out."""
         B = self.B
         h, w = self.hw[ly.level]
         grid = (B, h, w)
         n = ly.name
-        dy = self.gB[ly.level][..., :ly.cout] if ly.cout != self.gB[ly.level].shape[3] else self.gB[ly.level]
+        lvl = ly.level
+        idx = self._gB_next[lvl]
+        self._gB_next[lvl] = idx ^ 1
+        dy = self.gB[lvl][idx]
+        busy = self._gB_busy[lvl][idx]
+        if busy is not None:                       # the wgrad that last read this buffer must be finished
+            torch.cuda.current_stream().wait_event(busy)
         K.bn_relu_pool_bwd(dA, dPool, ly.y, ly.scale, ly.shift, ly.mean, ly.invstd, params[f"{n}.1.weight"],
                            grads[f"{n}.1.weight"], grads[f"{n}.1.bias"], dy, self.ws)
         gw = grads[f"{n}.0.weight"]
-        if ly.kind == "first":
-            s = K.wgrad_gemm(grid, dy, K.A_PLAIN, self.col, self.partials)
-            K.wgrad_reduce(self.partials, s, 1, ly.cout, 64, 2, gw, real_cin=ly.cin)
-        elif ly.kind == "cat":
-            s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self.up[ly.level], self.partials, self._skip(ly.level))
-            K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
-        else:
-            s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self._conv_src(ly), self.partials)
-            K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
+
+        def wgrad():
+            if ly.kind == "first":
+                s = K.wgrad_gemm(grid, dy, K.A_PLAIN, self.col, self.partials)
+                K.wgrad_reduce(self.partials, s, 1, ly.cout, 64, 2, gw, real_cin=ly.cin)
+            elif ly.kind == "cat":
+                s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self.up[ly.level], self.partials, self._skip(ly.level))
+                K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
+            else:
+                s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self._conv_src(ly), self.partials)
+                K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
+
+        self._gB_busy[lvl][idx] = self._on_side(wgrad)
         if dgrad_out is not None:
             K.conv_gemm(K.A_CONV3X3, grid, dy, ly.wd, dgrad_out, stats=dgrad_stats)
 
@@ -305,7 +338,14 @@ class SUNetPlan:
         parameters has all its gradients enqueued — 'dec1', 'dec2', 'dec3', 'dec4', 'enc3', 'enc2',
         'enc1' in that order; each group is a contiguous suffix slice of the flat gradient buffer,
         which is what the data-parallel trainer all-reduces while the rest of backward runs."""
-        done = on_group_done if on_group_done is not None else (lambda tag: None)
+        def done(tag):
+            if on_group_done is not None:
+                # the group's weight gradients are produced on the side stream
+                torch.cuda.current_stream().wait_stream(self.side)
+                on_group_done(tag)
+
+        for lv in self._gB_busy:
+            self._gB_busy[lv] = [None, None]
         L = self.layers
         B = self.B
         heads = ["conv1x1"] + (["conv_select", "conv_aux"] if self.selective else [])
@@ -324,8 +364,11 @@ class SUNetPlan:
             K.colsum_finalize(st, rows, 2 * c, 0, c, grads[f"unpool{lvl}.bias"])
             hh, ww = self.hw[lvl + 1]
             xin = L[self._convT_input(lvl)].a
-            s = K.wgrad_gemm((B, hh, ww), xin, K.A_GATHER2X2, dup, self.partials)
-            K.wgrad_reduce(self.partials, s, 4, _CH[lvl + 1], c, 1, grads[f"unpool{lvl}.weight"])
+            def wgrad_t(lvl=lvl, c=c, hh=hh, ww=ww, xin=xin, dup=dup):
+                s = K.wgrad_gemm((B, hh, ww), xin, K.A_GATHER2X2, dup, self.partials)
+                K.wgrad_reduce(self.partials, s, 4, _CH[lvl + 1], c, 1, grads[f"unpool{lvl}.weight"])
+
+            self._on_side(wgrad_t)
             K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1])
             dA = self.gA[lvl + 1]
             done(f"dec{lvl}")
@@ -340,6 +383,8 @@ class SUNetPlan:
             self._cbr_bwd(L[n2], self.dcat[lvl][..., c:], self.dpool[lvl], params, grads, self.gA[lvl])
             self._cbr_bwd(L[n1], self.gA[lvl], None, params, grads, self.dpool[lvl - 1] if lvl > 1 else None)
             done(f"enc{lvl}")
+        # every weight gradient is complete before anything after backward (Adam, all-reduce) runs
+        torch.cuda.current_stream().wait_stream(self.side)
 
 
 def param_order(selective: bool) -> List[str]:
