@@ -1,0 +1,74 @@
+"""Achieved HBM bandwidth of the stream kernels around the convolutions, at step-sized tensors.
+
+    python scripts/ew_bw.py [batch]
+
+Times each C-ABI call with CUDA events (tensors >> L2) and prints algorithmic GB/s
+(bytes per element of each kernel) next to the measured HBM peak.
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from selectivenet_for_semantic_segmentation_binary_b200 import kernels as K  # noqa: E402
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    dev = "cuda"
+    peak = 6533.8
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = json.load(open(p)).get("hbm_gbs", peak)
+    ws = K.new_workspace(dev)
+    bf = torch.bfloat16
+    rows = []
+    for (H, C) in [(256, 64), (128, 128), (64, 256), (32, 512)]:
+        n = B * H * H * C
+        y = (torch.randn(B, H, H, C, device=dev) * 1.5 + 0.3).to(bf)
+        a = torch.empty_like(y)
+        dA = torch.randn(B, H, H, C, device=dev).to(bf)
+        dy = torch.empty_like(y)
+        scale = torch.rand(C, device=dev) + 0.5
+        shift = torch.randn(C, device=dev) * 0.2
+        mean = torch.randn(C, device=dev) * 0.1
+        invstd = torch.rand(C, device=dev) + 0.5
+        dgamma, dbeta = torch.empty(C, device=dev), torch.empty(C, device=dev)
+        t = timeit(lambda: K.bn_relu_pool(y, scale, shift, a, None))
+        rows.append((f"bn_relu flat        {H}x{H}x{C}", 4 * n, t))
+        t = timeit(lambda: K.bn_relu_pool_bwd(dA, None, y, scale, shift, mean, invstd, scale, dgamma, dbeta, dy, ws))
+        rows.append((f"bn_bwd flat (r+a)   {H}x{H}x{C}", 10 * n, t))
+        if C < 512:
+            pooled = torch.empty(B, H // 2, H // 2, C, dtype=bf, device=dev)
+            dP = torch.randn(B, H // 2, H // 2, C, device=dev).to(bf)
+            dcat = torch.randn(B, H, H, 2 * C, device=dev).to(bf)
+            t = timeit(lambda: K.bn_relu_pool(y, scale, shift, a, pooled))
+            rows.append((f"bn_relu pool        {H}x{H}x{C}", int(4.5 * n), t))
+            t = timeit(lambda: K.bn_relu_pool_bwd(dcat[..., C:], dP, y, scale, shift, mean, invstd, scale, dgamma,
+                                                  dbeta, dy, ws))
+            rows.append((f"bn_bwd pool (r+a)   {H}x{H}x{C}", 11 * n, t))
+            del pooled, dP, dcat
+        del y, a, dA, dy
+    for name, nbytes, t in rows:
+        gbs = nbytes / t / 1e6
+        print(f"{name:34s} {t:8.4f} ms  {gbs:8.1f} GB/s  {100 * gbs / peak:5.1f}% of {peak:.0f}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -262,11 +262,9 @@ def ew_bn(K):
             ok &= report("   pooled", nchw(pooled), pref, 1e-2)
             dP = torch.randn(B, Cc, H // 2, W // 2, generator=g).to(dev)
             dPb = nhwc(dP)
-            # reference backward on bf16-rounded activations so the argmax agrees
-            a_round = aref.to(torch.bfloat16).float()
-            # straight-through: pool over rounded values, gradient routed to aref
-            pool_in = aref + (a_round - aref).detach()
-            total = (pool_in * nchw(dAb)).sum() + (F.max_pool2d(pool_in, 2) * nchw(dPb)).sum()
+            # plain fp32 reference: the pooled gradient goes to the first maximum of the fp32 activations
+            # (model.py:31 semantics); the kernel takes the argmax on fmaf(y, scale, shift) in fp32 too
+            total = (aref * nchw(dAb)).sum() + (F.max_pool2d(aref, 2) * nchw(dPb)).sum()
             total.backward()
         else:
             dPb = None

@@ -264,11 +264,15 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __
   const long long total = (long long)B * HW * WW * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    const long long wpix = i / G;
-    const int wx = (int)(wpix % WW);
-    const int wy = (int)((wpix / WW) % HW);
-    const int n = (int)(wpix / ((long long)WW * HW));
+    // item counts fit 32 bits (checked by the launcher): unsigned 32-bit divisions, not 64-bit ones
+    const uint32_t i32 = (uint32_t)i;
+    const uint32_t wpix32 = i32 / (uint32_t)G;
+    const int g = (int)(i32 - wpix32 * (uint32_t)G);
+    const long long wpix = wpix32;
+    const uint32_t rowi = wpix32 / (uint32_t)WW;
+    const int wx = (int)(wpix32 - rowi * (uint32_t)WW);
+    const int n = (int)(rowi / (uint32_t)HW);
+    const int wy = (int)(rowi - (uint32_t)n * (uint32_t)HW);
     float sc[8], sh[8];
     *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
     *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
@@ -499,6 +503,7 @@ __global__ void __launch_bounds__(256)
 bn_relu_flat_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int as, long long total, int G) {
   const int g = threadIdx.x % G;                 // 256 % G == 0 and every stride below is a multiple of 256
+  const int lg = __ffs(G) - 1;                   // G divides 256, so it is a power of two: i / G is a shift
   const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
   for (long long i0 = blockIdx.x * (long long)(256 * EW_U) + threadIdx.x; i0 < total;
        i0 += (long long)gridDim.x * 256 * EW_U) {
@@ -506,7 +511,7 @@ bn_relu_flat_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __
 #pragma unroll
     for (int u = 0; u < EW_U; ++u) {
       const long long i = i0 + u * 256;
-      if (i < total) v[u] = *reinterpret_cast<const bf16x8*>(y + (i / G) * ys + g * 8);
+      if (i < total) v[u] = *reinterpret_cast<const bf16x8*>(y + (i >> lg) * ys + g * 8);
     }
 #pragma unroll
     for (int u = 0; u < EW_U; ++u) {
@@ -516,7 +521,7 @@ bn_relu_flat_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __
         unpack8(v[u], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc.v[j], sh.v[j]), 0.f);
-        *reinterpret_cast<bf16x8*>(a + (i / G) * as + g * 8) = pack8(f);
+        *reinterpret_cast<bf16x8*>(a + (i >> lg) * as + g * 8) = pack8(f);
       }
     }
   }
@@ -530,7 +535,8 @@ bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
   __shared__ float red[256][17];
   const int G = C >> 3;
   const int g = threadIdx.x % G;
-  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g), mu = load_chan(mean, g), is = load_chan(invstd, g);
+  const int lg = __ffs(G) - 1;
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g), mu = load_chan(mean, g);
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
@@ -541,8 +547,8 @@ bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
     for (int u = 0; u < EW_U; ++u) {
       const long long i = i0 + u * 256;
       if (i < total) {
-        vy[u] = *reinterpret_cast<const bf16x8*>(y + (i / G) * ys + g * 8);
-        vg[u] = *reinterpret_cast<const bf16x8*>(dA + (i / G) * das + g * 8);
+        vy[u] = *reinterpret_cast<const bf16x8*>(y + (i >> lg) * ys + g * 8);
+        vg[u] = *reinterpret_cast<const bf16x8*>(dA + (i >> lg) * das + g * 8);
       }
     }
 #pragma unroll
@@ -554,13 +560,17 @@ bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
         unpack8(vg[u], fg);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float act = round_bf16(fmaxf(fmaf(fy[j], sc.v[j], sh.v[j]), 0.f));
-          const float gg = act > 0.f ? fg[j] : 0.f;
+          const float gg = fmaf(fy[j], sc.v[j], sh.v[j]) > 0.f ? fg[j] : 0.f;
           acc[j] += gg;
-          acc[8 + j] = fmaf(gg, (fy[j] - mu.v[j]) * is.v[j], acc[8 + j]);
+          acc[8 + j] = fmaf(gg, fy[j] - mu.v[j], acc[8 + j]);     // x invstd after the loop
         }
       }
     }
+  }
+  {
+    const ChanVec is = load_chan(invstd, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[8 + j] *= is.v[j];
   }
 #pragma unroll
   for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = acc[j];
@@ -582,6 +592,7 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
                          int C) {
   const int G = C >> 3;
   const int g = threadIdx.x % G;
+  const int lg = __ffs(G) - 1;
   const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
   const ChanVec kg = load_chan(coef, g), k1 = load_chan(coef + C, g), k0 = load_chan(coef + 2 * C, g);
   for (long long i0 = blockIdx.x * (long long)(256 * EW_U) + threadIdx.x; i0 < total;
@@ -591,8 +602,8 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
     for (int u = 0; u < EW_U; ++u) {
       const long long i = i0 + u * 256;
       if (i < total) {
-        vy[u] = *reinterpret_cast<const bf16x8*>(y + (i / G) * ys + g * 8);
-        vg[u] = *reinterpret_cast<const bf16x8*>(dA + (i / G) * das + g * 8);
+        vy[u] = *reinterpret_cast<const bf16x8*>(y + (i >> lg) * ys + g * 8);
+        vg[u] = *reinterpret_cast<const bf16x8*>(dA + (i >> lg) * das + g * 8);
       }
     }
 #pragma unroll
@@ -604,11 +615,10 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
         unpack8(vg[u], fg);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float act = round_bf16(fmaxf(fmaf(fy[j], sc.v[j], sh.v[j]), 0.f));
-          const float gg = act > 0.f ? fg[j] : 0.f;
+          const float gg = fmaf(fy[j], sc.v[j], sh.v[j]) > 0.f ? fg[j] : 0.f;
           o[j] = fmaf(kg.v[j], gg, fmaf(k1.v[j], fy[j], k0.v[j]));
         }
-        *reinterpret_cast<bf16x8*>(dy + (i / G) * dys + g * 8) = pack8(o);
+        *reinterpret_cast<bf16x8*>(dy + (i >> lg) * dys + g * 8) = pack8(o);
       }
     }
   }
@@ -616,56 +626,60 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
 
 // ------------------------------------------------------------------ pooled-layer backward, lean form
 // The three encoder outputs feed both a skip connection and a 2x2 max-pool.  One thread = one 2x2 window
-// x 8 channels; operands stay packed (bf16x8) and the per-channel decisions (ReLU mask, first-max winner)
-// are bit masks, so the kernel fits two 256-thread blocks per SM (the template version above needs 159
-// registers and ran at 1.4 TB/s).
+// x 8 channels.  Operands stay packed (bf16x8) and are unpacked one channel at a time, so only ~12 fp32
+// values are live; per channel and window the work is 4 FFMA (activations), 3 FMNMX (window max), 4+4
+// compares and 8 selects (first-max routing + ReLU mask).  The first maximum is taken on the fp32
+// activations fmaf(y, scale, shift): identical to the bf16-pooled forward wherever the window maximum is
+// unique after rounding, and the reference's own (fp32) choice where bf16 rounding made a tie.  Earlier
+// forms of this kernel (bit-mask decisions, 64-bit index math) were instruction-bound at ~45 % of HBM peak.
 struct PoolWin {
   bf16x8 vy[4], vg[4], vp;
   long long pix[4];
-  uint32_t pos;     // bit (k*8 + j): activation of pixel k, channel j is > 0
-  uint32_t best;    // 2 bits per channel j: index of the first maximum of the window
 };
 __device__ __forceinline__ void pool_win_load(PoolWin& w, long long win, int g, const __nv_bfloat16* __restrict__ dA,
                                               int das, const __nv_bfloat16* __restrict__ dP, int dps,
                                               const __nv_bfloat16* __restrict__ y, int ys, int H, int W) {
-  const int HW = H >> 1, WW = W >> 1;
-  const int wx = (int)(win % WW);
-  const int wy = (int)((win / WW) % HW);
-  const int n = (int)(win / ((long long)WW * HW));
+  // window counts fit 32 bits (checked by the launcher): unsigned 32-bit divisions instead of 64-bit ones
+  const uint32_t HW = (uint32_t)H >> 1, WW = (uint32_t)W >> 1;
+  const uint32_t w32 = (uint32_t)win;
+  const uint32_t rowi = w32 / WW;
+  const int wx = (int)(w32 - rowi * WW);
+  const int n = (int)(rowi / HW);
+  const int wy = (int)(rowi - (uint32_t)n * HW);
+  const long long p00 = ((long long)n * H + wy * 2) * W + wx * 2;
+  w.pix[0] = p00;
+  w.pix[1] = p00 + 1;
+  w.pix[2] = p00 + W;
+  w.pix[3] = p00 + W + 1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w.vy[k] = *reinterpret_cast<const bf16x8*>(y + w.pix[k] * ys + g * 8);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    w.pix[k] = ((long long)n * H + (wy * 2 + (k >> 1))) * W + (wx * 2 + (k & 1));
-    w.vy[k] = *reinterpret_cast<const bf16x8*>(y + w.pix[k] * ys + g * 8);
     if (dA) w.vg[k] = *reinterpret_cast<const bf16x8*>(dA + w.pix[k] * das + g * 8);
     else w.vg[k] = bf16x8{{0u, 0u, 0u, 0u}};
   }
   w.vp = *reinterpret_cast<const bf16x8*>(dP + win * dps + g * 8);
 }
-__device__ __forceinline__ void pool_win_decide(PoolWin& w, const ChanVec& sc, const ChanVec& sh) {
-  uint32_t pos = 0, best = 0;
+// channel j of the window: yv[k] = conv outputs, gv[k] = gradient reaching y's activation (skip + routed pool
+// gradient, ReLU-masked)
+__device__ __forceinline__ void pool_win_chan(const PoolWin& w, int j, float sc, float sh, float* yv, float* gv) {
+  float a[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float bv = 0.f;
-    int bk = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float act = round_bf16(fmaxf(fmaf(bf16_elem(w.vy[k], j), sc.v[j], sh.v[j]), 0.f));
-      if (act > 0.f) pos |= 1u << (k * 8 + j);
-      if (k == 0 || act > bv) {
-        bv = act;
-        bk = k;
-      }
-    }
-    best |= (uint32_t)bk << (2 * j);
+  for (int k = 0; k < 4; ++k) {
+    yv[k] = bf16_elem(w.vy[k], j);
+    gv[k] = bf16_elem(w.vg[k], j);
+    a[k] = fmaf(yv[k], sc, sh);
   }
-  w.pos = pos;
-  w.best = best;
-}
-__device__ __forceinline__ float pool_win_grad(const PoolWin& w, int k, int j) {
-  if (!((w.pos >> (k * 8 + j)) & 1u)) return 0.f;
-  float g = bf16_elem(w.vg[k], j);
-  if (((w.best >> (2 * j)) & 3u) == (uint32_t)k) g += bf16_elem(w.vp, j);
-  return g;
+  const float dp = bf16_elem(w.vp, j);
+  const float m = fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3]));
+  const bool w0 = a[0] == m;
+  const bool w1 = !w0 && a[1] == m;
+  const bool w2 = !w0 && !w1 && a[2] == m;
+  const bool w3 = !w0 && !w1 && !w2;
+  gv[0] = a[0] > 0.f ? gv[0] + (w0 ? dp : 0.f) : 0.f;
+  gv[1] = a[1] > 0.f ? gv[1] + (w1 ? dp : 0.f) : 0.f;
+  gv[2] = a[2] > 0.f ? gv[2] + (w2 ? dp : 0.f) : 0.f;
+  gv[3] = a[3] > 0.f ? gv[3] + (w3 ? dp : 0.f) : 0.f;
 }
 
 __global__ void __launch_bounds__(256, 2)
@@ -676,24 +690,32 @@ bn_bwd_pool_reduce_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
   __shared__ float red[256][17];
   const int G = C >> 3;
   const int g = threadIdx.x % G;
+  const int lg = __ffs(G) - 1;
   const long long total = (long long)B * (H >> 1) * (W >> 1) * G;
-  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g), mu = load_chan(mean, g), is = load_chan(invstd, g);
-  float acc[16];
+  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g), mu = load_chan(mean, g);
+  float acc[16];        // [0,8): sum g      [8,16): sum g * (y - mean)   (x invstd at the end)
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     PoolWin w;
-    pool_win_load(w, i / G, g, dA, das, dP, dps, y, ys, H, W);
-    pool_win_decide(w, sc, sh);
+    pool_win_load(w, i >> lg, g, dA, das, dP, dps, y, ys, H, W);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int j = 0; j < 8; ++j) {
+      float yv[4], gv[4];
+      pool_win_chan(w, j, sc.v[j], sh.v[j], yv, gv);
+      acc[j] += (gv[0] + gv[1]) + (gv[2] + gv[3]);
+      float t = gv[0] * (yv[0] - mu.v[j]);
+      t = fmaf(gv[1], yv[1] - mu.v[j], t);
+      t = fmaf(gv[2], yv[2] - mu.v[j], t);
+      t = fmaf(gv[3], yv[3] - mu.v[j], t);
+      acc[8 + j] += t;
+    }
+  }
+  {
+    const ChanVec is = load_chan(invstd, g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gg = pool_win_grad(w, k, j);
-        acc[j] += gg;
-        acc[8 + j] = fmaf(gg, (bf16_elem(w.vy[k], j) - mu.v[j]) * is.v[j], acc[8 + j]);
-      }
+    for (int j = 0; j < 8; ++j) acc[8 + j] *= is.v[j];
   }
 #pragma unroll
   for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = acc[j];
@@ -715,22 +737,36 @@ bn_bwd_pool_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
                          __nv_bfloat16* __restrict__ dy, int dys, int B, int H, int W, int C) {
   const int G = C >> 3;
   const int g = threadIdx.x % G;
+  const int lg = __ffs(G) - 1;
   const long long total = (long long)B * (H >> 1) * (W >> 1) * G;
   const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
   const ChanVec kg = load_chan(coef, g), k1 = load_chan(coef + C, g), k0 = load_chan(coef + 2 * C, g);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     PoolWin w;
-    pool_win_load(w, i / G, g, dA, das, dP, dps, y, ys, H, W);
-    pool_win_decide(w, sc, sh);
+    pool_win_load(w, i >> lg, g, dA, das, dP, dps, y, ys, H, W);
+    bf16x8 o[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float o[8];
+    for (int jj = 0; jj < 4; ++jj) {
+      float lo[4], hi[4];
+      {
+        float yv[4], gv[4];
+        pool_win_chan(w, 2 * jj, sc.v[2 * jj], sh.v[2 * jj], yv, gv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = fmaf(kg.v[j], pool_win_grad(w, k, j), fmaf(k1.v[j], bf16_elem(w.vy[k], j), k0.v[j]));
-      *reinterpret_cast<bf16x8*>(dy + w.pix[k] * dys + g * 8) = pack8(o);
+        for (int k = 0; k < 4; ++k) lo[k] = fmaf(kg.v[2 * jj], gv[k], fmaf(k1.v[2 * jj], yv[k], k0.v[2 * jj]));
+      }
+      {
+        float yv[4], gv[4];
+        pool_win_chan(w, 2 * jj + 1, sc.v[2 * jj + 1], sh.v[2 * jj + 1], yv, gv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          hi[k] = fmaf(kg.v[2 * jj + 1], gv[k], fmaf(k1.v[2 * jj + 1], yv[k], k0.v[2 * jj + 1]));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k].w[jj] = pack_bf16x2(lo[k], hi[k]);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<bf16x8*>(dy + w.pix[k] * dys + g * 8) = o[k];
   }
 }
 
@@ -882,11 +918,13 @@ extern "C" int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* 
     if ((height | width) & 1) return set_error(SUNET_ERR_INVALID, "bn_relu_pool: odd size %d x %d", height, width);
     if ((e = check_act("bn_relu_pool(pooled)", pooled_pix_stride, channels))) return e;
     const long long total = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
+    if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool: tensor too large (%lld items)", total);
     bn_relu_pool_kernel<true><<<ew_grid(total, 256), 256, 0, STREAM>>>(
         yp, y_pix_stride, scale, shift, ap, a_pix_stride, reinterpret_cast<__nv_bfloat16*>(pooled), pooled_pix_stride,
         batch, height, width, channels);
   } else {
     const long long total = (long long)batch * height * width * (channels / 8);
+    if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool: tensor too large (%lld items)", total);
     if (256 % (channels / 8) == 0)
       bn_relu_flat_kernel<<<flat_grid(total), 256, 0, STREAM>>>(yp, y_pix_stride, scale, shift, ap, a_pix_stride, total,
                                                                 channels / 8);
@@ -916,6 +954,7 @@ extern "C" int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const v
   const bool pool = dPool != nullptr;
   if (pool && ((height | width) & 1)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool_bwd: odd size");
   const long long total = (long long)batch * (pool ? height / 2 : height) * (pool ? width / 2 : width) * G;
+  if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool_bwd: tensor too large (%lld items)", total);
   int blocks = ew_grid(total, 256);
   const int max_blocks = num_sms() * 2;
   if (blocks > max_blocks) blocks = max_blocks;

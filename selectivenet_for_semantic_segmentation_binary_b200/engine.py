@@ -130,7 +130,10 @@ class SUNetPlan:
         self.gB = {L: (act(L, _CH[L]), act(L, _CH[L])) for L in (1, 2, 3, 4)}
         self._gB_next = {L: 0 for L in (1, 2, 3, 4)}
         self._gB_busy = {L: [None, None] for L in (1, 2, 3, 4)}      # event: last wgrad that read the buffer
-        self.side = torch.cuda.Stream(device=dev)
+        # SUNET_WGRAD_AFTER_DGRAD=1: the side-stream wgrad of layer l starts when dgrad(l) has finished, so it runs
+        # beside the HBM-bound BN backward of layer l-1 instead of competing with dgrad(l) for the SMs
+        self.wgrad_after_dgrad = os.environ.get("SUNET_WGRAD_AFTER_DGRAD", "1") != "0"
+        self.side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("SUNET_SIDE_PRIO", "0")))
         self.overlap_wgrad = os.environ.get("SUNET_OVERLAP_WGRAD", "1") != "0"
         self.dcat = {L: act(L, 2 * _CH[L]) for L in (1, 2, 3)}
         self.dpool = {L: act(L + 1, _CH[L]) for L in (1, 2, 3)}
@@ -325,6 +328,10 @@ class SUNetPlan:
                 s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self._conv_src(ly), self.partials)
                 K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
 
+        if self.wgrad_after_dgrad and dgrad_out is not None:
+            K.conv_gemm(K.A_CONV3X3, grid, dy, ly.wd, dgrad_out, stats=dgrad_stats)
+            self._gB_busy[lvl][idx] = self._on_side(wgrad)
+            return
         self._gB_busy[lvl][idx] = self._on_side(wgrad)
         if dgrad_out is not None:
             K.conv_gemm(K.A_CONV3X3, grid, dy, ly.wd, dgrad_out, stats=dgrad_stats)
@@ -368,8 +375,12 @@ class SUNetPlan:
                 s = K.wgrad_gemm((B, hh, ww), xin, K.A_GATHER2X2, dup, self.partials)
                 K.wgrad_reduce(self.partials, s, 4, _CH[lvl + 1], c, 1, grads[f"unpool{lvl}.weight"])
 
-            self._on_side(wgrad_t)
-            K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1])
+            if self.wgrad_after_dgrad:
+                K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1])
+                self._on_side(wgrad_t)
+            else:
+                self._on_side(wgrad_t)
+                K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1])
             dA = self.gA[lvl + 1]
             done(f"dec{lvl}")
         # bottleneck
