@@ -328,6 +328,10 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
     use_graph = tr.use_graph
     tr.use_graph = False
     K.conv_gemm, K.wgrad_gemm = conv_gemm, wgrad_gemm
+    plans = list(tr.net._plans.values())
+    overlap = [p.overlap_wgrad for p in plans]
+    for p in plans:
+        p.overlap_wgrad = False          # per-launch timings: every GEMM alone on the main stream
     try:
         torch.cuda.synchronize()
         t0 = torch.cuda.Event(enable_timing=True)
@@ -340,6 +344,8 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
     finally:
         K.conv_gemm, K.wgrad_gemm = orig_conv, orig_wgrad
         tr.use_graph = use_graph
+        for p, o in zip(plans, overlap):
+            p.overlap_wgrad = o
     table = []
     for name, flops, e0, e1, desc in pending:
         dt = e0.elapsed_time(e1) * 1e-3

@@ -64,11 +64,24 @@ typedef struct sunet_conv_gemm_args {
   int d_mode;
   float* stats;                /* optional fp32 [sunet_conv_gemm_stat_rows(args)][n_total][2]:    */
                                /*   per-CTA partial (sum, sum of squares) of the bf16 outputs     */
+  /* Optional fused BatchNorm-backward reduction (CBR_2D backward, model.py:9-15 via train.py:208): when this
+   * launch is the backward-data conv whose output dA is the gradient w.r.t. relu(bn(y)), pass y (NHWC bf16,
+   * n_total channels) and that BN's per-channel scale/shift/mean/invstd.  `stats` then receives per-CTA partial
+   * (sum g, sum g*xhat) with g = dA * (scale*y+shift > 0), xhat = (y-mean)*invstd — exactly the rows
+   * sunet_bn_bwd_apply() folds.  dst is stored unmasked.  Only where sunet_conv_gemm_bnb_supported() != 0. */
+  const void* bnb_y;
+  int bnb_y_pix_stride;
+  const float* bnb_scale;
+  const float* bnb_shift;
+  const float* bnb_mean;
+  const float* bnb_invstd;
 } sunet_conv_gemm_args;
 
 int sunet_conv_gemm(const sunet_conv_gemm_args* args, sunet_stream_t stream);
 /* rows of `stats` the call described by args will write (args->stats itself is ignored) */
 int sunet_conv_gemm_stat_rows(const sunet_conv_gemm_args* args);
+/* 1 if the kernel variant this shape dispatches to implements the bnb_* epilogue, else 0 */
+int sunet_conv_gemm_bnb_supported(const sunet_conv_gemm_args* args);
 
 /* ------------------------------------------------------------------------------------------
  * G2: weight-gradient GEMM over pixels, split-K with fp32 partials.
@@ -155,6 +168,14 @@ int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const void* dPool,
                            const float* invstd, const float* gamma, float* dgamma, float* dbeta, void* dy,
                            int dy_pix_stride, int batch, int height, int width, int channels, void* workspace,
                            size_t workspace_bytes, sunet_stream_t stream);
+/* Second half of sunet_bn_relu_pool_bwd for a non-pooled block whose reduction was fused into the producer of
+ * dA (sunet_conv_gemm with bnb_y, or sunet_heads_bwd with bnb_y): folds `partial_rows` rows of
+ * [channels][2] = (sum g, sum g*xhat) into dgamma / dbeta and writes dy.  dA may be stored unmasked. */
+int sunet_bn_bwd_apply(const void* dA, int dA_pix_stride, const void* y, int y_pix_stride, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, const float* partials,
+                       int partial_rows, float* dgamma, float* dbeta, void* dy, int dy_pix_stride, int batch,
+                       int height, int width, int channels, void* workspace, size_t workspace_bytes,
+                       sunet_stream_t stream);
 /* out[c] = sum_rows stats[row][col_offset + c][0]  (column sums from the G1 epilogue; ConvT bias grad) */
 int sunet_colsum_finalize(const float* stats, int rows, int n_total, int col_offset, int channels, float* out,
                           sunet_stream_t stream);

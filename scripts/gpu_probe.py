@@ -77,6 +77,55 @@ def conv3x3_case(K, B, H, W, Cin, Cout, dual=False, stats=True):
     return ok
 
 
+def g1_bnb(K):
+    """dgrad conv with the fused BatchNorm-backward reduction in its epilogue (conv_gemm bnb=...), followed by
+    bn_bwd_apply: against the unfused pair (conv_gemm + bn_relu_pool_bwd) and against plain torch."""
+    dev = "cuda"
+    ok = True
+    ws = K.new_workspace(dev)
+    for (B, H, W, Cd, Cn) in [(2, 32, 32, 64, 64), (3, 16, 16, 128, 128), (1, 16, 48, 256, 256), (2, 16, 16, 512, 512),
+                              (5, 16, 16, 64, 128), (9, 64, 64, 64, 64)]:
+        g = torch.Generator().manual_seed(B * 100 + Cd + Cn)
+        # dy of the producer layer (Cd channels) -> dA of the consumer block (Cn channels)
+        w = (torch.randn(Cd, Cn, 3, 3, generator=g) / (3 * Cn ** 0.5)).to(dev)
+        wf = torch.empty(Cd, 9 * Cn, dtype=torch.bfloat16, device=dev)
+        wd = torch.empty(Cn, 9 * Cd, dtype=torch.bfloat16, device=dev)
+        K.pack_conv3x3_weights(w, wf, wd)
+        dyb = nhwc(torch.randn(B, Cd, H, W, generator=g).to(dev))
+        yb = nhwc((torch.randn(B, Cn, H, W, generator=g) * 1.5 + 0.3).to(dev))
+        scale = (torch.rand(Cn, generator=g) + 0.5).to(dev) * torch.where(torch.rand(Cn, generator=g) < 0.1, -1.0, 1.0).to(dev)
+        shift = (torch.randn(Cn, generator=g) * 0.5).to(dev)
+        mean = (torch.randn(Cn, generator=g) * 0.3).to(dev)
+        invstd = (torch.rand(Cn, generator=g) + 0.5).to(dev)
+        if not K.conv_gemm_bnb_supported(K.A_CONV3X3, (B, H, W), dyb, wd, torch.empty_like(yb)):
+            print(f"   bnb unsupported for B{B} {H}x{W} {Cd}->{Cn}: skipped")
+            continue
+        rows = K.conv_gemm_stat_rows(B, H, W, Cn)
+        st = torch.full((rows, Cn, 2), float("nan"), device=dev)
+        dA = torch.full((B, H, W, Cn), float("nan"), dtype=torch.bfloat16, device=dev)
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), dyb, wd, dA, stats=st, bnb=(yb, scale, shift, mean, invstd))
+        dA0 = torch.full_like(dA, float("nan"))
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), dyb, wd, dA0)
+        torch.cuda.synchronize()
+        tag = f"bnb B{B} {H}x{W} {Cd}->{Cn}"
+        ok &= bool(torch.equal(dA, dA0))
+        print(f"  [{'OK ' if torch.equal(dA, dA0) else 'BAD'}] {tag}: dA identical to the unfused dgrad")
+        gm = dA.float() * ((yb.float() * scale + shift) > 0)
+        xhat = (yb.float() - mean) * invstd
+        ok &= report(f"   {tag} sum g", st[..., 0].sum(0), gm.reshape(-1, Cn).sum(0), 1e-3)
+        ok &= report(f"   {tag} sum g*xhat", st[..., 1].sum(0), (gm * xhat).reshape(-1, Cn).sum(0), 1e-3)
+        # end to end: fused rows + bn_bwd_apply  ==  bn_relu_pool_bwd on the same dA
+        dg1, db1, dg2, db2 = (torch.empty(Cn, device=dev) for _ in range(4))
+        dy1, dy2 = torch.empty_like(yb), torch.empty_like(yb)
+        K.bn_bwd_apply(dA, yb, scale, shift, mean, invstd, st, rows, dg1, db1, dy1, ws)
+        K.bn_relu_pool_bwd(dA0, None, yb, scale, shift, mean, invstd, scale, dg2, db2, dy2, ws)
+        torch.cuda.synchronize()
+        ok &= report(f"   {tag} dgamma", dg1, dg2, 1e-4)
+        ok &= report(f"   {tag} dbeta", db1, db2, 1e-4)
+        ok &= report(f"   {tag} dy", dy1.float(), dy2.float(), 4e-3)
+    return ok
+
+
 def g1_plain(K):
     dev = "cuda"
     ok = True
@@ -420,7 +469,7 @@ def swizzle_exp(K):
     return True
 
 
-GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g2_wgrad": g2_wgrad,
+GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g1_bnb": g1_bnb, "g2_wgrad": g2_wgrad,
           "ew_bn": ew_bn, "ew_heads_loss": ew_heads_loss}
 
 

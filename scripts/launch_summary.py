@@ -1,0 +1,40 @@
+"""Per-kernel summary of an ncu launch list (scripts/ncu_launches.sh): launches per step, time per step and
+share, DRAM bytes and GB/s.  usage: python scripts/launch_summary.py launches.csv [steps_in_capture]"""
+import collections
+import csv
+import re
+import sys
+
+
+def main():
+    path = sys.argv[1]
+    rows = list(csv.reader(open(path, errors="replace")))
+    hdr = None
+    per = collections.defaultdict(lambda: collections.defaultdict(float))
+    cnt = collections.Counter()
+    for r in rows:
+        if hdr is None:
+            if "Kernel Name" in r:
+                hdr = r
+                ki, vi, mi, ii = r.index("Kernel Name"), r.index("Metric Value"), r.index("Metric Name"), r.index("ID")
+            continue
+        if len(r) <= vi:
+            continue
+        name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("sunet::", "")
+        v = float(r[vi].replace(",", ""))
+        per[name][r[mi]] += v
+        if r[mi].startswith("gpu__time"):
+            cnt[name] += 1
+    steps = float(sys.argv[2]) if len(sys.argv) > 2 else float(cnt.get("adam_kernel", 1))
+    tot = sum(v["gpu__time_duration.sum"] for v in per.values())
+    print(f"# {path}: {sum(cnt.values())} launches, {steps:g} steps, {tot / 1e6 / steps:.3f} ms/step (serialised, cold)")
+    print(f"{'kernel':40s} {'n/step':>7s} {'ms/step':>8s} {'share':>6s} {'MB/launch':>10s} {'GB/s':>8s}")
+    for k, v in sorted(per.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
+        t = v["gpu__time_duration.sum"]
+        b = v.get("dram__bytes_read.sum", 0.0) + v.get("dram__bytes_write.sum", 0.0)
+        print(f"{k[:40]:40s} {cnt[k] / steps:7.1f} {t / 1e6 / steps:8.3f} {100 * t / tot:5.1f}% {b / cnt[k] / 1e6:10.1f} "
+              f"{b / t:8.1f}")
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,8 @@ class ConvGemmArgs(C.Structure):
         ("bias", C.c_void_p),
         ("dst", C.c_void_p), ("dst_pix_stride", C.c_int), ("d_mode", C.c_int),
         ("stats", C.c_void_p),
+        ("bnb_y", C.c_void_p), ("bnb_y_pix_stride", C.c_int),
+        ("bnb_scale", C.c_void_p), ("bnb_shift", C.c_void_p), ("bnb_mean", C.c_void_p), ("bnb_invstd", C.c_void_p),
     ]
 
 
@@ -68,6 +70,7 @@ SIGNATURES = {
     "sunet_launch_count": [],
     "sunet_conv_gemm":[C.POINTER(ConvGemmArgs), _vp],
     "sunet_conv_gemm_stat_rows": [C.POINTER(ConvGemmArgs)],
+    "sunet_conv_gemm_bnb_supported": [C.POINTER(ConvGemmArgs)],
     "sunet_wgrad_gemm": [C.POINTER(WgradGemmArgs), _vp],
     "sunet_wgrad_gemm_splits": [C.POINTER(WgradGemmArgs)],
     "sunet_wgrad_reduce": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
@@ -81,6 +84,8 @@ SIGNATURES = {
     "sunet_bn_relu_pool": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "sunet_bn_relu_pool_bwd": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
                                _vp, _sz, _vp],
+    "sunet_bn_bwd_apply": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz,
+                           _vp],
     "sunet_colsum_finalize": [_vp, _i, _i, _i, _i, _vp, _vp],
     "sunet_heads_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp],
     "sunet_bn_relu_heads": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp],

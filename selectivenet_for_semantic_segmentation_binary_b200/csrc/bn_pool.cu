@@ -989,3 +989,32 @@ extern "C" int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const v
                                                                     coef, dyp, dy_pix_stride, total, channels);
   return check_launch("bn_bwd_apply");
 }
+
+extern "C" int sunet_bn_bwd_apply(const void* dA, int dA_pix_stride, const void* y, int y_pix_stride,
+                                  const float* scale, const float* shift, const float* mean, const float* invstd,
+                                  const float* partials, int partial_rows, float* dgamma, float* dbeta, void* dy,
+                                  int dy_pix_stride, int batch, int height, int width, int channels, void* workspace,
+                                  size_t workspace_bytes, sunet_stream_t stream_) {
+  if (!dA || !y || !scale || !shift || !mean || !invstd || !partials || partial_rows <= 0 || !dy || !workspace)
+    return set_error(SUNET_ERR_INVALID, "bn_bwd_apply: bad arguments");
+  int e;
+  if ((e = check_act("bn_bwd_apply(y)", y_pix_stride, channels))) return e;
+  if ((e = check_act("bn_bwd_apply(dy)", dy_pix_stride, channels))) return e;
+  if ((e = check_act("bn_bwd_apply(dA)", dA_pix_stride, channels))) return e;
+  const int G = channels / 8;
+  if (256 % G) return set_error(SUNET_ERR_INVALID, "bn_bwd_apply: channels %d unsupported", channels);
+  const long long total = (long long)batch * height * width * G;
+  if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_bwd_apply: tensor too large (%lld items)", total);
+  const size_t need = 3 * (size_t)channels * sizeof(float);
+  if (workspace_bytes < need)
+    return set_error(SUNET_ERR_WORKSPACE, "bn_bwd_apply: workspace %zu < %zu", workspace_bytes, need);
+  float* coef = reinterpret_cast<float*>(workspace);
+  const double count = (double)batch * height * width;
+  bn_bwd_finalize_par_kernel<<<(channels + 7) / 8, 256, 0, STREAM>>>(partials, partial_rows, channels, count, scale,
+                                                                      mean, invstd, dgamma, dbeta, coef);
+  if ((e = check_launch("bn_bwd_finalize"))) return e;
+  bn_bwd_apply_flat_kernel<<<flat_grid(total), 256, 0, STREAM>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dA), dA_pix_stride, reinterpret_cast<const __nv_bfloat16*>(y),
+      y_pix_stride, scale, shift, coef, reinterpret_cast<__nv_bfloat16*>(dy), dy_pix_stride, total, channels);
+  return check_launch("bn_bwd_apply");
+}

@@ -25,10 +25,18 @@ struct Halo2Params {
   int m_blocks, n_tiles;
   float* stats;              // [gridDim.x / n_tiles][n_total][2] or nullptr (one row per CTA)
   int n_total;
+  // BNB (fused BatchNorm-backward reduction): per-channel constants of the BN whose input gradient this launch
+  // produces; stats then holds (sum g, sum g * xhat) with g = dst masked by relu(bn(y)) > 0
+  const float* bnb_scale;
+  const float* bnb_shift;
+  const float* bnb_mean;
+  const float* bnb_invstd;
 };
 
 // TILES = M=128 tiles per CTA and block: 2 (16x16 block) for BN <= 128, 1 (8 wide x 16 tall) for BN = 256
-template <int BN>
+// BNB = fused BN-backward reduction in the epilogue: two extra 16 KB slots hold the matching tiles of y (the
+// conv output the BN normalised), paid for with one or two weight stages.
+template <int BN, bool BNB = false>
 struct H2Cfg {
   static constexpr int TILES = (BN == 256) ? 1 : 2;
   static constexpr int PITCH = 8 * TILES + 2;
@@ -36,33 +44,37 @@ struct H2Cfg {
   static constexpr int A_SLOT = (A_TX + 1023) / 1024 * 1024;
   static constexpr int A_STAGES = 2;
   static constexpr int B_HALF = (BN / 2) * 128;      // this CTA's half of one weight tile
-  static constexpr int B_STAGES = (BN == 256) ? 8 : 10;
+  static constexpr int B_STAGES = (BN == 256) ? (BNB ? 7 : 8) : ((BNB && BN == 128) ? 9 : 10);
   static constexpr int STG_BYTES = 128 * 128;
-  static constexpr int SMEM = A_STAGES * A_SLOT + B_STAGES * B_HALF + 2 * STG_BYTES + 1024 + 512;
+  static constexpr int Y_SLOTS = BNB ? ((BN == 64) ? 4 : 2) : 0;      // power of two
+  static constexpr int SMEM = A_STAGES * A_SLOT + B_STAGES * B_HALF + (2 + Y_SLOTS) * STG_BYTES + 1024 + 512;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr int TMEM_COLS = 2 * TILES * BN;   // TILES x BN columns x 2 accumulator stages
 };
 
 constexpr int kH2Threads = 192;
 
-template <int BN>
+template <int BN, bool BNB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
 conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
-                   const Halo2Params p) {
-  using C = H2Cfg<BN>;
+                   const __grid_constant__ CUtensorMap mapY, const Halo2Params p) {
+  using C = H2Cfg<BN, BNB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + C::A_STAGES * C::A_SLOT;
   uint8_t* sStg = sB + C::B_STAGES * C::B_HALF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * C::STG_BYTES);
+  uint8_t* sY = sStg + 2 * C::STG_BYTES;                  // BNB: 2 slots of y tiles (same box / swizzle as mapD)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + C::Y_SLOTS * C::STG_BYTES);
   uint64_t* afull = bars;
   uint64_t* aempty = afull + C::A_STAGES;
   uint64_t* bfull = aempty + C::A_STAGES;
   uint64_t* bempty = bfull + C::B_STAGES;
   uint64_t* tfull = bempty + C::B_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* yfull = tempty + 2;                           // [4], BNB only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,10 +93,12 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8);     // 4 epilogue warps x 2 CTAs (only the leader's copy is waited on)
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&yfull[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapB);
     tma_prefetch_desc(&mapD);
+    if (BNB) tma_prefetch_desc(&mapY);
   }
   __syncthreads();
   cluster_sync_all();               // both CTAs' barriers exist before anything signals across the pair
@@ -196,9 +210,61 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     const int row = quad * 32 + lane;
     const bool issuer = (threadIdx.x == 64);
     constexpr int NCHUNK = BN / 64;
+    constexpr int CPB = C::TILES * NCHUNK;       // 64-channel output chunks per block
     float ssum[NCHUNK][2], ssq[NCHUNK][2];
 #pragma unroll
     for (int q = 0; q < NCHUNK; ++q) ssum[q][0] = ssum[q][1] = ssq[q][0] = ssq[q][1] = 0.f;
+
+    // BNB: this thread's two columns of every chunk (channel = n_tile*BN + q*64 + 2*lane + {0,1})
+    float csc[NCHUNK][2], csh[NCHUNK][2], cmu[NCHUNK][2];
+    if (BNB) {
+#pragma unroll
+      for (int q = 0; q < NCHUNK; ++q) {
+        const int c = n_tile * BN + q * 64 + lane * 2;
+        csc[q][0] = __ldg(p.bnb_scale + c);
+        csc[q][1] = __ldg(p.bnb_scale + c + 1);
+        csh[q][0] = __ldg(p.bnb_shift + c);
+        csh[q][1] = __ldg(p.bnb_shift + c + 1);
+        cmu[q][0] = __ldg(p.bnb_mean + c);
+        cmu[q][1] = __ldg(p.bnb_mean + c + 1);
+      }
+    }
+    // BNB y-tile pipeline (issuer thread): chunk number k of this CTA = (block k / CPB of its sequence, tile
+    // (k % CPB) / NCHUNK, channel chunk k % NCHUNK); slot k % YS.  Loads run YS-1 chunks ahead of the consumer
+    // (the slot of chunk k-1 is free once every thread has passed the staging barrier of chunk k); L2
+    // prefetches run kPfAhead chunks further ahead so the smem fill is an L2 hit.
+    constexpr uint32_t YS = C::Y_SLOTS > 0 ? C::Y_SLOTS : 1;
+    constexpr uint32_t YS_LOG = (YS == 4) ? 2 : ((YS == 2) ? 1 : 0);
+    constexpr int kPfAhead = 4;
+    uint32_t y_issued = 0, y_prefetched = 0;
+    const uint32_t my_blocks = (m_first < m_pairs) ? (uint32_t)((m_pairs - 1 - m_first) / m_step + 1) : 0u;
+    const uint32_t y_total = my_blocks * CPB;
+    auto y_coords = [&](uint32_t k, int& c0, int& x0, int& y0, int& nn) {
+      const int blk = (int)(k / CPB), rem = (int)(k % CPB);
+      const int mb_ = 2 * (m_first + blk * m_step) + (int)rank;
+      c0 = n_tile * BN + (rem % NCHUNK) * 64;
+      x0 = (mb_ % p.blocks_x) * (8 * C::TILES) + 8 * (rem / NCHUNK);
+      y0 = ((mb_ / p.blocks_x) % p.blocks_y) * 16;
+      nn = mb_ / (p.blocks_x * p.blocks_y);
+    };
+    auto y_pump = [&](uint32_t upto) {      // issuer only: smem loads up to chunk `upto` (exclusive), prefetch beyond
+      while (y_issued < upto && y_issued < y_total) {
+        int c0, x0, y0, nn;
+        y_coords(y_issued, c0, x0, y0, nn);
+        uint64_t* bar = &yfull[y_issued & (YS - 1)];
+        mbar_arrive_expect_tx(bar, C::STG_BYTES);
+        tma_load_5d(sY + (y_issued & (YS - 1)) * C::STG_BYTES, &mapY, bar, c0, x0, y0, nn, 0);
+        ++y_issued;
+      }
+      if (y_prefetched < y_issued) y_prefetched = y_issued;
+      while (y_prefetched < y_issued + kPfAhead && y_prefetched < y_total) {
+        int c0, x0, y0, nn;
+        y_coords(y_prefetched, c0, x0, y0, nn);
+        tma_prefetch_5d(&mapY, c0, x0, y0, nn, 0);
+        ++y_prefetched;
+      }
+    };
+    if (BNB && issuer) y_pump(YS);
 
     int it = 0;
     uint32_t chunk_ctr = 0;
@@ -239,8 +305,34 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           if (issuer) {
             tma_store_5d(&mapD, stg, ncol0, bx * (8 * C::TILES) + 8 * t, by * 16, n, 0);   // out-of-range n: clipped
             tma_store_commit();
+            if (BNB) y_pump(chunk_ctr + YS);     // everyone is past the stats loop of chunk_ctr-1: its slot is free
           }
-          if (p.stats != nullptr) {
+          if (BNB) {
+            // (sum g, sum g*(y-mean)) over this quad's 32 rows for this thread's two columns; g = dA where
+            // relu(bn(y)) > 0.  dA itself is stored unmasked: the apply kernel masks with the same expression.
+            mbar_wait(&yfull[chunk_ctr & (YS - 1)], (chunk_ctr >> YS_LOG) & 1);
+            const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
+            const uint32_t* ywords = reinterpret_cast<const uint32_t*>(sY + (chunk_ctr & (YS - 1)) * C::STG_BYTES);
+            const float sc0 = csc[q][0], sc1 = csc[q][1], sh0 = csh[q][0], sh1 = csh[q][1];
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;     // sum g, sum g*y (mean folded in after the loop)
+#pragma unroll 16
+            for (int r = 0; r < 32; ++r) {
+              const int rr = quad * 32 + r;
+              const int idx = rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
+              const uint32_t w = words[idx], yw = ywords[idx];
+              const float ya = bf16lo(yw), yb = bf16hi(yw);
+              const float ga = fmaf(ya, sc0, sh0) > 0.f ? bf16lo(w) : 0.f;
+              const float gb = fmaf(yb, sc1, sh1) > 0.f ? bf16hi(w) : 0.f;
+              s0 += ga;
+              s1 += gb;
+              q0 = fmaf(ga, ya, q0);
+              q1 = fmaf(gb, yb, q1);
+            }
+            ssum[q][0] += s0;
+            ssum[q][1] += s1;
+            ssq[q][0] += fmaf(-cmu[q][0], s0, q0);             // 32-row partial of sum g*(y-mean)
+            ssq[q][1] += fmaf(-cmu[q][1], s1, q1);
+          } else if (p.stats != nullptr) {
             const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
@@ -283,7 +375,11 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       const int t = threadIdx.x - 64;
       const int srow = m_first * 2 + (int)rank;      // one partial row per CTA
       float* dst = p.stats + (static_cast<size_t>(srow) * p.n_total + n_tile * BN) * 2;
-      for (int i = t; i < BN * 2; i += 128) dst[i] = red[i] + red[BN * 2 + i] + red[2 * BN * 2 + i] + red[3 * BN * 2 + i];
+      for (int i = t; i < BN * 2; i += 128) {
+        float v = red[i] + red[BN * 2 + i] + red[2 * BN * 2 + i] + red[3 * BN * 2 + i];
+        if (BNB && (i & 1)) v *= __ldg(p.bnb_invstd + n_tile * BN + (i >> 1));     // sum g*(y-mean) -> sum g*xhat
+        dst[i] = v;
+      }
     }
   }
 
@@ -303,18 +399,18 @@ static int halo2_map(CUtensorMap* m, const void* base, int C, int S, int B, int 
   return make_tmap_bf16_5d(m, base, dims, str, box);
 }
 
-template <int BN>
+template <int BN, bool BNB>
 static int halo2_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d,
-                          const Halo2Params& p, int grid, cudaStream_t stream) {
+                          const CUtensorMap& y, const Halo2Params& p, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    int e = check_cuda(cudaFuncSetAttribute(conv3_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            H2Cfg<BN>::SMEM),
+    int e = check_cuda(cudaFuncSetAttribute(conv3_halo2_kernel<BN, BNB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            H2Cfg<BN, BNB>::SMEM),
                        "cudaFuncSetAttribute(conv3_halo2)");
     if (e) return e;
     attr_set = true;
   }
-  conv3_halo2_kernel<BN><<<grid, kH2Threads, H2Cfg<BN>::SMEM, stream>>>(a0, a1, b, d, p);
+  conv3_halo2_kernel<BN, BNB><<<grid, kH2Threads, H2Cfg<BN, BNB>::SMEM, stream>>>(a0, a1, b, d, y, p);
   return check_launch("conv3_halo2_kernel");
 }
 
@@ -351,8 +447,11 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   const int B = a->batch, H = a->height, W = a->width;
   const int bn = halo2_bn(a->n_total);
   const int bw = (bn == 256) ? 8 : 16;
-  CUtensorMap mA0, mA1, mB, mD;
+  CUtensorMap mA0, mA1, mB, mD, mY;
   int e;
+  const bool bnb = a->bnb_y != nullptr;
+  if (bnb && (!a->stats || !a->bnb_scale || !a->bnb_shift || !a->bnb_mean || !a->bnb_invstd))
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: bnb_y needs stats and the four bnb_* vectors");
   if ((e = halo2_map(&mA0, a->src0, a->src0_channels, a->src0_pix_stride, B, H, W, bw + 2, 18))) return e;
   if (a->src1) {
     if ((e = halo2_map(&mA1, a->src1, a->src1_channels, a->src1_pix_stride, B, H, W, bw + 2, 18))) return e;
@@ -363,6 +462,13 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
                              (uint32_t)(bn / 2))))
     return e;
   if ((e = halo2_map(&mD, a->dst, a->n_total, a->dst_pix_stride, B, H, W, 8, 16))) return e;
+  if (bnb) {
+    if (a->bnb_y_pix_stride < a->n_total || (a->bnb_y_pix_stride % 8))
+      return set_error(SUNET_ERR_INVALID, "conv_gemm: bad bnb_y_pix_stride %d", a->bnb_y_pix_stride);
+    if ((e = halo2_map(&mY, a->bnb_y, a->n_total, a->bnb_y_pix_stride, B, H, W, 8, 16))) return e;
+  } else {
+    mY = mD;
+  }
   Halo2Params p;
   p.cpt0 = a->src0_channels / 64;
   p.cpt1 = a->src1 ? a->src1_channels / 64 : 0;
@@ -372,10 +478,19 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   p.n_tiles = a->n_total / bn;
   p.stats = a->stats;
   p.n_total = a->n_total;
+  p.bnb_scale = a->bnb_scale;
+  p.bnb_shift = a->bnb_shift;
+  p.bnb_mean = a->bnb_mean;
+  p.bnb_invstd = a->bnb_invstd;
   const int grid = halo2_slots(B, H, W, p.n_tiles, bw) * p.n_tiles * 2;
-  if (bn == 256) return halo2_launch_t<256>(mA0, mA1, mB, mD, p, grid, stream);
-  if (bn == 128) return halo2_launch_t<128>(mA0, mA1, mB, mD, p, grid, stream);
-  return halo2_launch_t<64>(mA0, mA1, mB, mD, p, grid, stream);
+  if (bnb) {
+    if (bn == 256) return halo2_launch_t<256, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    if (bn == 128) return halo2_launch_t<128, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    return halo2_launch_t<64, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  }
+  if (bn == 256) return halo2_launch_t<256, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  if (bn == 128) return halo2_launch_t<128, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  return halo2_launch_t<64, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
 }
 
 }  // namespace sunet

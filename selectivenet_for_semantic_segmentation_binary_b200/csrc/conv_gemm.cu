@@ -417,6 +417,11 @@ extern "C" int sunet_conv_gemm_stat_rows(const sunet_conv_gemm_args* a) {
   return conv_gemm_grid(g.m_tiles, n_tiles) / n_tiles;
 }
 
+extern "C" int sunet_conv_gemm_bnb_supported(const sunet_conv_gemm_args* a) {
+  if (!a || a->batch <= 0 || a->height <= 0 || a->width <= 0 || a->n_total <= 0 || a->n_total % 64) return 0;
+  return conv3_halo2_eligible(a) ? 1 : 0;
+}
+
 extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!a) return set_error(SUNET_ERR_INVALID, "conv_gemm: null args");
@@ -447,6 +452,9 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
     return set_error(SUNET_ERR_INVALID, "conv_gemm: scatter store needs n_total = 4 x (multiple of 64)");
 
   if (conv3_halo2_eligible(a)) return conv3_halo2_launch(a, stream);
+  if (a->bnb_y != nullptr)
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: the fused BN-backward epilogue (bnb_y) is not available for this "
+                                        "shape/mode; check sunet_conv_gemm_bnb_supported()");
   if (conv3_halo_eligible(a)) return conv3_halo_launch(a, stream);
 
   TileGeom g = tile_geom(B, H, W, 128);

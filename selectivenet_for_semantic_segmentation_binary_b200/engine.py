@@ -55,6 +55,8 @@ class _Layer:
         self.stats = None
         self.stat_rows = 0
         self.scale = self.shift = self.mean = self.invstd = None
+        self.bnb_stats = None      # rows of (sum g, sum g*xhat) written by the dgrad that produces this block's dA
+        self.bnb_rows = 0
 
 
 class SUNetPlan:
@@ -132,7 +134,7 @@ class SUNetPlan:
         self._gB_busy = {L: [None, None] for L in (1, 2, 3, 4)}      # event: last wgrad that read the buffer
         # SUNET_WGRAD_AFTER_DGRAD=1: the side-stream wgrad of layer l starts when dgrad(l) has finished, so it runs
         # beside the HBM-bound BN backward of layer l-1 instead of competing with dgrad(l) for the SMs
-        self.wgrad_after_dgrad = os.environ.get("SUNET_WGRAD_AFTER_DGRAD", "1") != "0"
+        self.wgrad_after_dgrad = os.environ.get("SUNET_WGRAD_AFTER_DGRAD", "0") != "0"
         self.side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("SUNET_SIDE_PRIO", "0")))
         self.overlap_wgrad = os.environ.get("SUNET_OVERLAP_WGRAD", "1") != "0"
         self.dcat = {L: act(L, 2 * _CH[L]) for L in (1, 2, 3)}
@@ -142,6 +144,23 @@ class SUNetPlan:
             h, w = self.hw[L]
             rows = K.conv_gemm_stat_rows(B, h, w, 2 * _CH[L])
             self.dcat_stats[L] = (torch.zeros(rows, 2 * _CH[L], 2, device=dev), rows)
+        # Fused BN-backward reduction: the dgrad conv of layer p that produces dA of a non-pooled block c also
+        # emits c's (sum g, sum g*xhat) rows from its epilogue (producer name -> consumer layer)
+        self.bnb_of: Dict[str, _Layer] = {}
+        if os.environ.get("SUNET_FUSE_BNB", "1") != "0":
+            pairs = [("decoder_layer_1_1", "decoder_layer_1_2"), ("decoder_layer_2_1", "decoder_layer_2_2"),
+                     ("decoder_layer_3_1", "decoder_layer_3_2"), ("decoder_layer_4_1", "decoder_layer_4_2"),
+                     ("encoder_layer_3_2", "encoder_layer_3_1"), ("encoder_layer_2_2", "encoder_layer_2_1"),
+                     ("encoder_layer_1_2", "encoder_layer_1_1")]
+            for pn, cn in pairs:
+                pl, cl = self.layers[pn], self.layers[cn]
+                h, w = self.hw[pl.level]
+                dy, out = self.gB[pl.level][0], self.gA[pl.level]
+                if K.conv_gemm_bnb_supported(K.A_CONV3X3, (B, h, w), dy, pl.wd, out):
+                    rows = K.conv_gemm_stat_rows(B, h, w, cl.cout)
+                    cl.bnb_rows = rows
+                    cl.bnb_stats = torch.zeros(rows, cl.cout, 2, device=dev)
+                    self.bnb_of[pn] = cl
         self.ws = K.new_workspace(dev)
         self.partials = None      # sized lazily from the wgrad split plan
         self._partials_bytes = 0
@@ -300,8 +319,11 @@ class SUNetPlan:
         return done
 
     def _cbr_bwd(self, ly: _Layer, dA: Optional[torch.Tensor], dPool: Optional[torch.Tensor], params, grads,
-                 dgrad_out: Optional[torch.Tensor], dgrad_stats: Optional[torch.Tensor] = None):
-        """dA/dPool -> (dgamma, dbeta, dy) -> weight grad (side stream), and the input gradient into dgrad_out."""
+                 dgrad_out: Optional[torch.Tensor], dgrad_stats: Optional[torch.Tensor] = None,
+                 fused_reduce: bool = False) -> bool:
+        """dA/dPool -> (dgamma, dbeta, dy) -> weight grad (side stream), and the input gradient into dgrad_out.
+        fused_reduce: this block's BN-backward reduction rows were already written by the producer of dA.
+        Returns True if the dgrad launched here wrote the reduction rows of the block consuming dgrad_out."""
         B = self.B
         h, w = self.hw[ly.level]
         grid = (B, h, w)
@@ -313,8 +335,13 @@ class SUNetPlan:
         busy = self._gB_busy[lvl][idx]
         if busy is not None:                       # the wgrad that last read this buffer must be finished
             torch.cuda.current_stream().wait_event(busy)
-        K.bn_relu_pool_bwd(dA, dPool, ly.y, ly.scale, ly.shift, ly.mean, ly.invstd, params[f"{n}.1.weight"],
+        if fused_reduce:
+            assert dPool is None and ly.bnb_stats is not None
+            K.bn_bwd_apply(dA, ly.y, ly.scale, ly.shift, ly.mean, ly.invstd, ly.bnb_stats, ly.bnb_rows,
                            grads[f"{n}.1.weight"], grads[f"{n}.1.bias"], dy, self.ws)
+        else:
+            K.bn_relu_pool_bwd(dA, dPool, ly.y, ly.scale, ly.shift, ly.mean, ly.invstd, params[f"{n}.1.weight"],
+                               grads[f"{n}.1.weight"], grads[f"{n}.1.bias"], dy, self.ws)
         gw = grads[f"{n}.0.weight"]
 
         def wgrad():
@@ -328,13 +355,22 @@ class SUNetPlan:
                 s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self._conv_src(ly), self.partials)
                 K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
 
-        if self.wgrad_after_dgrad and dgrad_out is not None:
-            K.conv_gemm(K.A_CONV3X3, grid, dy, ly.wd, dgrad_out, stats=dgrad_stats)
+        nxt = self.bnb_of.get(n) if dgrad_stats is None else None
+        bnb = None if nxt is None else (nxt.y, nxt.scale, nxt.shift, nxt.mean, nxt.invstd)
+        if nxt is not None:
+            dgrad_stats = nxt.bnb_stats
+
+        def dgrad():
+            if dgrad_out is not None:
+                K.conv_gemm(K.A_CONV3X3, grid, dy, ly.wd, dgrad_out, stats=dgrad_stats, bnb=bnb)
+
+        if self.wgrad_after_dgrad:
+            dgrad()
             self._gB_busy[lvl][idx] = self._on_side(wgrad)
-            return
-        self._gB_busy[lvl][idx] = self._on_side(wgrad)
-        if dgrad_out is not None:
-            K.conv_gemm(K.A_CONV3X3, grid, dy, ly.wd, dgrad_out, stats=dgrad_stats)
+        else:
+            self._gB_busy[lvl][idx] = self._on_side(wgrad)
+            dgrad()
+        return nxt is not None
 
     def backward(self, dlogits: torch.Tensor, params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor],
                  on_group_done=None) -> None:
@@ -363,9 +399,9 @@ class SUNetPlan:
                               (2, ("decoder_layer_2_2", "decoder_layer_2_1")),
                               (3, ("decoder_layer_3_2", "decoder_layer_3_1"))):
             c = _CH[lvl]
-            self._cbr_bwd(L[n1], dA, None, params, grads, self.gA[lvl])
+            f = self._cbr_bwd(L[n1], dA, None, params, grads, self.gA[lvl])
             st, rows = self.dcat_stats[lvl]
-            self._cbr_bwd(L[n2], self.gA[lvl], None, params, grads, self.dcat[lvl], st)
+            self._cbr_bwd(L[n2], self.gA[lvl], None, params, grads, self.dcat[lvl], st, fused_reduce=f)
             # ConvTranspose backward: bias (column sums of d_up), weight, input
             dup = self.dcat[lvl][..., :c]
             K.colsum_finalize(st, rows, 2 * c, 0, c, grads[f"unpool{lvl}.bias"])
@@ -384,15 +420,16 @@ class SUNetPlan:
             dA = self.gA[lvl + 1]
             done(f"dec{lvl}")
         # bottleneck
-        self._cbr_bwd(L["decoder_layer_4_1"], self.gA[4], None, params, grads, self.gA[4])
-        self._cbr_bwd(L["decoder_layer_4_2"], self.gA[4], None, params, grads, self.dpool[3])
+        f = self._cbr_bwd(L["decoder_layer_4_1"], self.gA[4], None, params, grads, self.gA[4])
+        self._cbr_bwd(L["decoder_layer_4_2"], self.gA[4], None, params, grads, self.dpool[3], fused_reduce=f)
         done("dec4")
         # encoder, deepest first; skip gradient = second half of dcat, pooled gradient = dpool
         for lvl in (3, 2, 1):
             c = _CH[lvl]
             n2, n1 = f"encoder_layer_{lvl}_2", f"encoder_layer_{lvl}_1"
-            self._cbr_bwd(L[n2], self.dcat[lvl][..., c:], self.dpool[lvl], params, grads, self.gA[lvl])
-            self._cbr_bwd(L[n1], self.gA[lvl], None, params, grads, self.dpool[lvl - 1] if lvl > 1 else None)
+            f = self._cbr_bwd(L[n2], self.dcat[lvl][..., c:], self.dpool[lvl], params, grads, self.gA[lvl])
+            self._cbr_bwd(L[n1], self.gA[lvl], None, params, grads, self.dpool[lvl - 1] if lvl > 1 else None,
+                          fused_reduce=f)
             done(f"enc{lvl}")
         # every weight gradient is complete before anything after backward (Adam, all-reduce) runs
         torch.cuda.current_stream().wait_stream(self.side)

@@ -58,11 +58,8 @@ def conv_gemm_stat_rows(batch: int, height: int, width: int, n_total: int, a_mod
     return r
 
 
-def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst: torch.Tensor, *,
-              src1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-              stats: Optional[torch.Tensor] = None, d_mode: int = D_NHWC) -> None:
-    """grid = (batch, height, width) of the GEMM-M pixel grid."""
-    lib = _lib.load()
+def _conv_gemm_args(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst: torch.Tensor,
+                    src1: Optional[torch.Tensor], bias: Optional[torch.Tensor], d_mode: int) -> _lib.ConvGemmArgs:
     a = _lib.ConvGemmArgs()
     a.batch, a.height, a.width = grid
     a.a_mode = a_mode
@@ -75,10 +72,33 @@ def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst:
     a.bias = _f32(bias)
     a.dst, _, a.dst_pix_stride = _act(dst)
     a.d_mode = d_mode
+    return a
+
+
+def conv_gemm_bnb_supported(a_mode: int, grid, src0, weights, dst, *, src1=None, bias=None,
+                            d_mode: int = D_NHWC) -> bool:
+    """True if conv_gemm(..., bnb=...) is available for this shape (the CTA-pair halo kernel serves it)."""
+    a = _conv_gemm_args(a_mode, grid, src0, weights, dst, src1, bias, d_mode)
+    return bool(_lib.load().sunet_conv_gemm_bnb_supported(C.byref(a)))
+
+
+def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst: torch.Tensor, *,
+              src1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+              stats: Optional[torch.Tensor] = None, d_mode: int = D_NHWC, bnb=None) -> None:
+    """grid = (batch, height, width) of the GEMM-M pixel grid.
+    bnb = (y, scale, shift, mean, invstd): fuse the BatchNorm-backward reduction of the block whose input
+    gradient this launch produces into the epilogue; `stats` then receives (sum g, sum g*xhat) rows."""
+    lib = _lib.load()
+    a = _conv_gemm_args(a_mode, grid, src0, weights, dst, src1, bias, d_mode)
     if stats is not None:
         rows = _lib.load().sunet_conv_gemm_stat_rows(C.byref(a))
         assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= rows * a.n_total * 2
         a.stats = stats.data_ptr()
+    if bnb is not None:
+        y, scale, shift, mean, invstd = bnb
+        assert stats is not None and y.shape == dst.shape
+        a.bnb_y, _, a.bnb_y_pix_stride = _act(y)
+        a.bnb_scale, a.bnb_shift, a.bnb_mean, a.bnb_invstd = _f32(scale), _f32(shift), _f32(mean), _f32(invstd)
     _lib.check(lib.sunet_conv_gemm(C.byref(a), _stream()), "sunet_conv_gemm")
 
 
@@ -188,6 +208,19 @@ def bn_relu_pool_bwd(dA, dPool, y, scale, shift, mean, invstd, gamma, dgamma, db
                                                   _f32(invstd), _f32(gamma), _f32(dgamma), _f32(dbeta), dyp, dys, B,
                                                   H, W, Cc, workspace.data_ptr(), workspace.numel(), _stream()),
                "sunet_bn_relu_pool_bwd")
+
+
+def bn_bwd_apply(dA, y, scale, shift, mean, invstd, partials, partial_rows, dgamma, dbeta, dy, workspace) -> None:
+    """Finalize + apply half of the BN/ReLU backward when the reduction rows come from the producer of dA."""
+    B, H, W, Cc = y.shape
+    yp, _, ys = _act(y)
+    dyp, _, dys = _act(dy)
+    dAp, _, das = _act(dA)
+    assert partials.dtype == torch.float32 and partials.is_contiguous() and partials.numel() >= partial_rows * Cc * 2
+    _lib.check(_lib.load().sunet_bn_bwd_apply(dAp, das, yp, ys, _f32(scale), _f32(shift), _f32(mean), _f32(invstd),
+                                              partials.data_ptr(), partial_rows, _f32(dgamma), _f32(dbeta), dyp, dys,
+                                              B, H, W, Cc, workspace.data_ptr(), workspace.numel(), _stream()),
+               "sunet_bn_bwd_apply")
 
 
 def colsum_finalize(stats, rows, n_total, col_offset, channels, out) -> None:

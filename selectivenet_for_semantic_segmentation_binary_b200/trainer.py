@@ -64,6 +64,8 @@ class SUNetTrainer:
         self._warm = 0
         self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self._ranges = self.fg.group_ranges()
+        import os
+        self._buckets = bucket_plan(self._ranges, self.fg.total, os.environ.get("SUNET_DP_BUCKETS", DEFAULT_BUCKETS))
         self.launches_per_step = 0
         self.global_pixels_override = 0
 
@@ -97,7 +99,9 @@ class SUNetTrainer:
             comm, cur = self._comm, torch.cuda.current_stream()
 
             def reduce_group(tag):
-                lo, hi = self._ranges[tag]
+                if tag not in self._buckets:
+                    return
+                lo, hi = self._buckets[tag]
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 comm.wait_event(ev)
@@ -161,6 +165,30 @@ class SUNetTrainer:
             # capture does not execute: replay once so this call is a real step
         self._graph.replay()
         return self.results
+
+
+GROUP_ORDER = ("dec1", "dec2", "dec3", "dec4", "enc3", "enc2", "enc1")     # order SUNetPlan.backward reports them
+DEFAULT_BUCKETS = "dec1,dec2,dec3,dec4,enc3,enc2,enc1"
+
+
+def bucket_plan(ranges, total: int, spec: str):
+    """Gradient buckets of the data-parallel exchange.  `ranges` = FlatGrads.group_ranges(): the 7 groups are
+    contiguous slices whose union, taken in GROUP_ORDER, is a suffix of the flat buffer growing towards 0.
+    `spec` = comma list of group tags after which a bucket closes ('enc1' always closes the last one).
+    Returns {tag: (lo, hi)}: when backward reports `tag`, all-reduce flat[lo:hi]."""
+    close = set(t.strip() for t in spec.split(",") if t.strip()) | {"enc1"}
+    unknown = close - set(GROUP_ORDER)
+    if unknown:
+        raise ValueError(f"SUNET_DP_BUCKETS: unknown group tags {sorted(unknown)}")
+    out, hi = {}, total
+    for tag in GROUP_ORDER:
+        lo, ghi = ranges[tag]
+        assert ghi <= hi, "groups must arrive from the end of the flat buffer towards its start"
+        if tag in close:
+            out[tag] = (lo, hi)
+            hi = lo
+    assert hi == 0
+    return out
 
 
 def chunk_bounds(total: int, world: int, rank: int):

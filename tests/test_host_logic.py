@@ -94,3 +94,28 @@ def test_evaluator_metrics_formulas_without_gpu():
         Evaluator(3, False)
     ev.reset()
     assert ev.confusion_matrix.sum() == 0
+
+
+def test_dp_bucket_plan_tiles_the_flat_gradient_buffer():
+    """Every bucket plan must cover each gradient element exactly once, in arrival order (trainer.bucket_plan)."""
+    from selectivenet_for_semantic_segmentation_binary_b200.engine import FlatGrads, param_order
+    from selectivenet_for_semantic_segmentation_binary_b200.model import UNet_B
+    from selectivenet_for_semantic_segmentation_binary_b200.trainer import GROUP_ORDER, bucket_plan
+    net = UNet_B("RGB", selective=True)
+    shapes = {n: tuple(p.shape) for n, p in net.named_parameters()}
+    fg = FlatGrads(shapes, param_order(True), "cpu")
+    ranges = fg.group_ranges()
+    for spec in ("dec1,dec2,dec3,dec4,enc3,enc2,enc1", "enc1", "", "dec3,enc1", "dec2,dec4"):
+        plan = bucket_plan(ranges, fg.total, spec)
+        assert "enc1" in plan
+        covered = torch.zeros(fg.total, dtype=torch.int32)
+        prev_lo = fg.total
+        for tag in GROUP_ORDER:
+            if tag in plan:
+                lo, hi = plan[tag]
+                assert hi == prev_lo and lo == ranges[tag][0]
+                covered[lo:hi] += 1
+                prev_lo = lo
+        assert bool((covered == 1).all())
+    with pytest.raises(ValueError):
+        bucket_plan(ranges, fg.total, "dec9")
