@@ -145,31 +145,54 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __re
 }
 
 // ------------------------------------------------------------------ all weight packs in one launch
-// blockIdx.y = job (one per layer), blockIdx.x strides over that layer's elements.  Replaces 17 tiny
-// launches per forward pass: at 16 patches per GPU the step is launch-latency sensitive.
+// blockIdx.y = job (one per layer), blockIdx.x strides over that layer's 32x32 channel tiles.  Replaces 17
+// tiny launches per forward pass: at 16 patches per GPU the step is launch-latency sensitive.
+// Tiled repack (channel counts are multiples of 32): src[a][b][t] fp32 (t = filter tap, fastest) -> two bf16 operands,
+//   out_b[(a*T + t)*Bn + b]         (b fastest)      conv3x3: forward pack   convT: dgrad pack
+//   out_a[rowA(b, t)*An + a]        (a fastest)      conv3x3: dgrad pack (rowA = b*9 + 8 - t, the flipped tap)
+//                                                     convT: forward pack (rowA = t*Bn + b)
+// A block moves a 32(a) x 32(b) x T tile through shared memory so that the fp32 reads and both bf16 writes are
+// contiguous runs (the element-wise form of this kernel read with stride T and wrote with stride T*An).
+template <int T, bool CONVT>
+__device__ __forceinline__ void pack_tile(const sunet_pack_job& j, float (*tile)[32 * 9 + 1]) {
+  const int An = j.a, Bn = j.b;
+  const int tiles_b = Bn >> 5, tiles = (An >> 5) * tiles_b;
+  __nv_bfloat16* out_b = reinterpret_cast<__nv_bfloat16*>(CONVT ? j.wd : j.wf);
+  __nv_bfloat16* out_a = reinterpret_cast<__nv_bfloat16*>(CONVT ? j.wf : j.wd);
+  for (int tix = blockIdx.x; tix < tiles; tix += gridDim.x) {
+    const int a0 = (tix / tiles_b) << 5, b0 = (tix % tiles_b) << 5;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 32 * T; i += 256) {
+      const int al = i / (32 * T), r = i - al * (32 * T);
+      tile[al][r] = j.w[((size_t)(a0 + al) * Bn + b0) * T + r];
+    }
+    __syncthreads();
+    if (out_b)
+      for (int i = threadIdx.x; i < 32 * 32 * T; i += 256) {
+        const int bl = i & 31, t = (i >> 5) % T, al = (i >> 5) / T;
+        out_b[((size_t)(a0 + al) * T + t) * Bn + b0 + bl] = __float2bfloat16_rn(tile[al][bl * T + t]);
+      }
+    if (out_a)
+      for (int i = threadIdx.x; i < 32 * 32 * T; i += 256) {
+        const int al = i & 31, t = (i >> 5) % T, bl = (i >> 5) / T;
+        const size_t row = CONVT ? ((size_t)t * Bn + b0 + bl) : ((size_t)(b0 + bl) * 9 + (8 - t));
+        out_a[row * An + a0 + al] = __float2bfloat16_rn(tile[al][bl * T + t]);
+      }
+  }
+}
+
+// One launch packs every weight tensor of the network (table of jobs): 17 launches -> 1.
 __global__ void __launch_bounds__(256)
 pack_table_kernel(const sunet_pack_job* __restrict__ jobs) {
+  __shared__ float tile[32][32 * 9 + 1];
   const sunet_pack_job j = jobs[blockIdx.y];
-  const long long start = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long step = (long long)gridDim.x * blockDim.x;
   if (j.kind == 0) {            // conv3x3: a = cout, b = cin
-    const int co_n = j.a, ci_n = j.b;
-    __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
-    __nv_bfloat16* wd = reinterpret_cast<__nv_bfloat16*>(j.wd);
-    const long long total = (long long)co_n * ci_n * 9;
-    for (long long i = start; i < total; i += step) {
-      const int ci = (int)(i % ci_n);
-      const int tap = (int)((i / ci_n) % 9);
-      const int co = (int)(i / ((long long)ci_n * 9));
-      const __nv_bfloat16 b = __float2bfloat16_rn(j.w[((long long)co * ci_n + ci) * 9 + tap]);
-      wf[i] = b;
-      if (wd) wd[((long long)ci * 9 + (8 - tap)) * co_n + co] = b;
-    }
+    pack_tile<9, false>(j, tile);
   } else if (j.kind == 1) {     // first conv: a = cout, b = cin, K padded to 64
     const int co_n = j.a, cin = j.b;
     __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
-    for (long long i = start; i < (long long)co_n * 64; i += step) {
-      const int k = (int)(i & 63), co = (int)(i >> 6);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < co_n * 64; i += gridDim.x * blockDim.x) {
+      const int k = i & 63, co = i >> 6;
       float v = 0.f;
       if (k < 9 * cin) {
         const int tap = k / cin, ci = k - tap * cin;
@@ -178,19 +201,10 @@ pack_table_kernel(const sunet_pack_job* __restrict__ jobs) {
       wf[i] = __float2bfloat16_rn(v);
     }
   } else {                      // ConvTranspose2d: a = cin, b = cout
-    const int ci_n = j.a, co_n = j.b;
-    __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
-    __nv_bfloat16* wd = reinterpret_cast<__nv_bfloat16*>(j.wd);
-    const long long total = (long long)ci_n * co_n * 4;
-    for (long long i = start; i < total; i += step) {
-      const int ci = (int)(i % ci_n);
-      const int row = (int)(i / ci_n);
-      const int co = row % co_n, tap = row / co_n;
-      const __nv_bfloat16 b = __float2bfloat16_rn(j.w[((long long)ci * co_n + co) * 4 + tap]);
-      wf[i] = b;
-      if (wd) wd[(long long)ci * (4 * co_n) + row] = b;
-      if (ci == 0 && j.bias4) j.bias4[row] = j.bias ? j.bias[co] : 0.f;
-    }
+    pack_tile<4, true>(j, tile);
+    if (j.bias4)
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * j.b; i += gridDim.x * blockDim.x)
+        j.bias4[i] = j.bias ? j.bias[i % j.b] : 0.f;
   }
 }
 

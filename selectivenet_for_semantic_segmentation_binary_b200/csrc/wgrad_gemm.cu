@@ -762,29 +762,42 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
 
 // ------------------------------------------------------------------ split-K reduction
 namespace sunet {
+// grad[a][b][tap] = sum_k P[k][tap][a][b]  (layout 0: a = co, b = ci, 9 taps; layout 1: a = ci, b = co, 4 taps).
+// One thread per (tap, a, b) in the PARTIALS' order, so every split is read as contiguous rows; the TAPS-strided
+// 4-byte writes touch each output line TAPS times but the output is 1/splits of the traffic.
+template <int TAPS>
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ P, int splits, int taps, int Ca, int Nb, int layout, int real_cin,
-                    float* __restrict__ grad, long long total) {
-  const long long slab = (long long)taps * Ca * Nb;
+wgrad_reduce_taps_kernel(const float* __restrict__ P, int splits, long long ab, float* __restrict__ grad) {
+  const long long slab = TAPS * ab;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < slab;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i / ab);
+    const long long j = i - tap * ab;
+    const float* src = P + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {
+      s0 += src[(k + 0) * slab];
+      s1 += src[(k + 1) * slab];
+      s2 += src[(k + 2) * slab];
+      s3 += src[(k + 3) * slab];
+    }
+    for (; k < splits; ++k) s0 += src[k * slab];
+    grad[j * TAPS + tap] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+// first layer: grad[co][cin][tap] from P[k][co][tap*cin + ci] (Nb = padded K of the im2col'ed input)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_first_kernel(const float* __restrict__ P, int splits, int Ca, int Nb, int real_cin,
+                          float* __restrict__ grad, long long total) {
+  const long long slab = (long long)Ca * Nb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    long long src;
-    if (layout == 0) {        // grad[co][ci][tap], Ca = co, Nb = ci
-      const int tap = (int)(i % 9);
-      const int ci = (int)((i / 9) % Nb);
-      const int co = (int)(i / (9LL * Nb));
-      src = ((long long)tap * Ca + co) * Nb + ci;
-    } else if (layout == 1) { // grad[ci][co][tap], Ca = ci, Nb = co
-      const int tap = (int)(i % 4);
-      const int co = (int)((i / 4) % Nb);
-      const int ci = (int)(i / (4LL * Nb));
-      src = ((long long)tap * Ca + ci) * Nb + co;
-    } else {                  // grad[co][cin][tap] from P[0][co][tap*cin + ci]
-      const int tap = (int)(i % 9);
-      const int ci = (int)((i / 9) % real_cin);
-      const int co = (int)(i / (9LL * real_cin));
-      src = (long long)co * Nb + tap * real_cin + ci;
-    }
+    const int tap = (int)(i % 9);
+    const int ci = (int)((i / 9) % real_cin);
+    const int co = (int)(i / (9LL * real_cin));
+    const long long src = (long long)co * Nb + tap * real_cin + ci;
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += P[k * slab + src];
     grad[i] = s;
@@ -805,7 +818,13 @@ extern "C" int sunet_wgrad_reduce(const float* partials, int splits, int taps, i
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(partials, splits, taps, a_channels, b_channels, layout, real_cin,
-                                                       grad, total);
+  const long long ab = (long long)a_channels * b_channels;
+  if (layout == 0)
+    wgrad_reduce_taps_kernel<9><<<(int)blocks, 256, 0, stream>>>(partials, splits, ab, grad);
+  else if (layout == 1)
+    wgrad_reduce_taps_kernel<4><<<(int)blocks, 256, 0, stream>>>(partials, splits, ab, grad);
+  else
+    wgrad_reduce_first_kernel<<<(int)blocks, 256, 0, stream>>>(partials, splits, a_channels, b_channels, real_cin,
+                                                               grad, total);
   return check_launch("wgrad_reduce");
 }
