@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsunet_b200.so")
+LIB_PATH = os.environ.get("SUNET_LIB") or os.path.join(_HERE, "libsunet_b200.so")     # SUNET_LIB: experiments only
 
 A_CONV3X3, A_PLAIN, A_GATHER2X2 = 0, 1, 2
 D_NHWC, D_SCATTER2X2 = 0, 1

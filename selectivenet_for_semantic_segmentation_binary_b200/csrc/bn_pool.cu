@@ -43,6 +43,8 @@ __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(_
 // ------------------------------------------------------------------ packing kernels
 __global__ void pack_input_im2col_kernel(const float* __restrict__ x, bf16x8* __restrict__ out, int B, int cin, int H,
                                          int W) {
+  pdl_wait();
+  pdl_trigger();
   // one thread = one pixel x 8 output channels
   const long long total = (long long)B * H * W * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -72,6 +74,8 @@ __global__ void pack_input_im2col_kernel(const float* __restrict__ x, bf16x8* __
 template <int CIN>
 __global__ void __launch_bounds__(256)
 pack_input_im2col_t_kernel(const float* __restrict__ x, bf16x8* __restrict__ out, int B, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)B * H * W;
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
        pix += (long long)gridDim.x * blockDim.x) {
@@ -100,6 +104,8 @@ pack_input_im2col_t_kernel(const float* __restrict__ x, bf16x8* __restrict__ out
 
 __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                     __nv_bfloat16* __restrict__ wd, int co_n, int ci_n) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)co_n * ci_n * 9;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -115,6 +121,8 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* 
 }
 
 __global__ void pack_conv1_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int co_n, int cin) {
+  pdl_wait();
+  pdl_trigger();
   const int total = co_n * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i & 63, co = i >> 6;
@@ -130,6 +138,8 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, __nv_bfloat16* __
 __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                   __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
                                   float* __restrict__ bias4, int ci_n, int co_n) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)ci_n * co_n * 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -184,6 +194,8 @@ __device__ __forceinline__ void pack_tile(const sunet_pack_job& j, float (*tile)
 // One launch packs every weight tensor of the network (table of jobs): 17 launches -> 1.
 __global__ void __launch_bounds__(256)
 pack_table_kernel(const sunet_pack_job* __restrict__ jobs) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][32 * 9 + 1];
   const sunet_pack_job j = jobs[blockIdx.y];
   if (j.kind == 0) {            // conv3x3: a = cout, b = cin
@@ -216,6 +228,8 @@ bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double coun
                    const float* __restrict__ conv_bias, float* running_mean, float* running_var,
                    long long* nbt, float momentum, float eps, float* scale, float* shift, float* mean,
                    float* invstd) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c == 0 && lane == 0 && nbt) *nbt += 1;
@@ -251,6 +265,8 @@ bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double coun
 
 __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* conv_bias,
                                       const float* rm, const float* rv, float eps, float* scale, float* shift, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] / sqrtf(rv[c] + eps);
@@ -259,6 +275,8 @@ __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, con
 }
 
 __global__ void colsum_finalize_kernel(const float* stats, int rows, int n_total, int col_offset, int C, float* out) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0;
@@ -272,6 +290,8 @@ __global__ void __launch_bounds__(256)
 bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int as,
                     __nv_bfloat16* __restrict__ pooled, int ps, int B, int H, int W, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int G = C >> 3;
   // POOL: one item = one 2x2 window x 8 channels; else one pixel x 8 channels
   const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
@@ -402,6 +422,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_b
                      const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ invstd, float* __restrict__ partials, int B, int H, int W, int C) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[256][17];
   const int G = C >> 3;
   const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
@@ -447,6 +469,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_b
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int C, double count,
                                        const float* __restrict__ scale, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double sg = 0.0, sgx = 0.0;
@@ -471,6 +495,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bf
                     const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                     int dys, int B, int H, int W, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int G = C >> 3;
   const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
   const long long total = (long long)B * HW * WW * G;
@@ -516,6 +542,8 @@ __device__ __forceinline__ ChanVec load_chan(const float* __restrict__ p, int g)
 __global__ void __launch_bounds__(256)
 bn_relu_flat_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int as, long long total, int G) {
+  pdl_wait();
+  pdl_trigger();
   const int g = threadIdx.x % G;                 // 256 % G == 0 and every stride below is a multiple of 256
   const int lg = __ffs(G) - 1;                   // G divides 256, so it is a power of two: i / G is a shift
   const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
@@ -546,6 +574,8 @@ bn_bwd_reduce_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
                           const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           float* __restrict__ partials, long long total, int C) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[256][17];
   const int G = C >> 3;
   const int g = threadIdx.x % G;
@@ -604,6 +634,8 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy, int dys, long long total,
                          int C) {
+  pdl_wait();
+  pdl_trigger();
   const int G = C >> 3;
   const int g = threadIdx.x % G;
   const int lg = __ffs(G) - 1;
@@ -701,6 +733,8 @@ bn_bwd_pool_reduce_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
                           const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                           const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, float* __restrict__ partials, int B, int H, int W, int C) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[256][17];
   const int G = C >> 3;
   const int g = threadIdx.x % G;
@@ -749,6 +783,8 @@ bn_bwd_pool_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
                          const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ coef,
                          __nv_bfloat16* __restrict__ dy, int dys, int B, int H, int W, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int G = C >> 3;
   const int g = threadIdx.x % G;
   const int lg = __ffs(G) - 1;
@@ -789,6 +825,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_finalize_par_kernel(const float* __restrict__ partials, int blocks, int C, double count,
                            const float* __restrict__ scale, const float* __restrict__ mean,
                            const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -835,13 +873,13 @@ extern "C" int sunet_pack_input_im2col(const float* x, void* out, int batch, int
     return set_error(SUNET_ERR_INVALID, "pack_input_im2col: bad arguments (cin=%d)", cin);
   const long long total = (long long)batch * height * width * 8;
   if (cin == 3)
-    pack_input_im2col_t_kernel<3><<<ew_grid(total / 8, 256), 256, 0, STREAM>>>(x, reinterpret_cast<bf16x8*>(out), batch,
+    launch_k(pack_input_im2col_t_kernel<3>, dim3(ew_grid(total / 8, 256)), dim3(256), 0, STREAM, x, reinterpret_cast<bf16x8*>(out), batch,
                                                                                height, width);
   else if (cin == 2)
-    pack_input_im2col_t_kernel<2><<<ew_grid(total / 8, 256), 256, 0, STREAM>>>(x, reinterpret_cast<bf16x8*>(out), batch,
+    launch_k(pack_input_im2col_t_kernel<2>, dim3(ew_grid(total / 8, 256)), dim3(256), 0, STREAM, x, reinterpret_cast<bf16x8*>(out), batch,
                                                                                height, width);
   else
-    pack_input_im2col_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(x, reinterpret_cast<bf16x8*>(out), batch, cin,
+    launch_k(pack_input_im2col_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, x, reinterpret_cast<bf16x8*>(out), batch, cin,
                                                                        height, width);
   return check_launch("pack_input_im2col");
 }
@@ -850,7 +888,7 @@ extern "C" int sunet_pack_conv3x3_weights(const float* w, void* wf, void* wd, in
                                           sunet_stream_t stream_) {
   if (!w || !wf || cout <= 0 || cin <= 0) return set_error(SUNET_ERR_INVALID, "pack_conv3x3_weights: bad arguments");
   const long long total = (long long)cout * cin * 9;
-  pack_conv3x3_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(w, reinterpret_cast<__nv_bfloat16*>(wf),
+  launch_k(pack_conv3x3_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, w, reinterpret_cast<__nv_bfloat16*>(wf),
                                                                 reinterpret_cast<__nv_bfloat16*>(wd), cout, cin);
   return check_launch("pack_conv3x3_weights");
 }
@@ -858,7 +896,7 @@ extern "C" int sunet_pack_conv3x3_weights(const float* w, void* wf, void* wd, in
 extern "C" int sunet_pack_conv1_weights(const float* w, void* wf, int cout, int cin, sunet_stream_t stream_) {
   if (!w || !wf || cout <= 0 || cin <= 0 || cin * 9 > 64)
     return set_error(SUNET_ERR_INVALID, "pack_conv1_weights: bad arguments");
-  pack_conv1_kernel<<<ew_grid(cout * 64, 256), 256, 0, STREAM>>>(w, reinterpret_cast<__nv_bfloat16*>(wf), cout, cin);
+  launch_k(pack_conv1_kernel, dim3(ew_grid(cout * 64, 256)), dim3(256), 0, STREAM, w, reinterpret_cast<__nv_bfloat16*>(wf), cout, cin);
   return check_launch("pack_conv1_weights");
 }
 
@@ -866,7 +904,7 @@ extern "C" int sunet_pack_convT_weights(const float* w, const float* bias, void*
                                         int cout, sunet_stream_t stream_) {
   if (!w || !wf || cin <= 0 || cout <= 0) return set_error(SUNET_ERR_INVALID, "pack_convT_weights: bad arguments");
   const long long total = (long long)cin * cout * 4;
-  pack_convT_kernel<<<ew_grid(total, 256), 256, 0, STREAM>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(wf),
+  launch_k(pack_convT_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, w, bias, reinterpret_cast<__nv_bfloat16*>(wf),
                                                               reinterpret_cast<__nv_bfloat16*>(wd), bias4, cin, cout);
   return check_launch("pack_convT_weights");
 }
@@ -874,7 +912,7 @@ extern "C" int sunet_pack_convT_weights(const float* w, const float* bias, void*
 extern "C" int sunet_pack_weights_table(const sunet_pack_job* jobs_dev, int n_jobs, sunet_stream_t stream_) {
   if (!jobs_dev || n_jobs <= 0) return set_error(SUNET_ERR_INVALID, "pack_weights_table: bad arguments");
   dim3 grid(96, (unsigned)n_jobs);
-  pack_table_kernel<<<grid, 256, 0, STREAM>>>(jobs_dev);
+  launch_k(pack_table_kernel, dim3(grid), dim3(256), 0, STREAM, jobs_dev);
   return check_launch("pack_weights_table");
 }
 
@@ -886,7 +924,7 @@ extern "C" int sunet_bn_finalize(const float* stats, int rows, int channels, lon
     return set_error(SUNET_ERR_INVALID, "bn_finalize: bad arguments");
   if ((running_mean == nullptr) != (running_var == nullptr))
     return set_error(SUNET_ERR_INVALID, "bn_finalize: running_mean/var must both be given or both NULL");
-  bn_finalize_kernel<<<(channels + 7) / 8, 256, 0, STREAM>>>(stats, rows, channels, (double)count, gamma, beta,
+  launch_k(bn_finalize_kernel, dim3((channels + 7) / 8), dim3(256), 0, STREAM, stats, rows, channels, (double)count, gamma, beta,
                                                                   conv_bias, running_mean, running_var,
                                                                   num_batches_tracked, momentum, eps, scale, shift,
                                                                   mean, invstd);
@@ -898,7 +936,7 @@ extern "C" int sunet_bn_eval_affine(const float* gamma, const float* beta, const
                                     float* shift, int channels, sunet_stream_t stream_) {
   if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || channels <= 0)
     return set_error(SUNET_ERR_INVALID, "bn_eval_affine: bad arguments");
-  bn_eval_affine_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(gamma, beta, conv_bias, running_mean, running_var,
+  launch_k(bn_eval_affine_kernel, dim3((channels + 127) / 128), dim3(128), 0, STREAM, gamma, beta, conv_bias, running_mean, running_var,
                                                                      eps, scale, shift, channels);
   return check_launch("bn_eval_affine");
 }
@@ -907,7 +945,7 @@ extern "C" int sunet_colsum_finalize(const float* stats, int rows, int n_total, 
                                      float* out, sunet_stream_t stream_) {
   if (!stats || !out || rows <= 0 || channels <= 0 || col_offset < 0 || col_offset + channels > n_total)
     return set_error(SUNET_ERR_INVALID, "colsum_finalize: bad arguments");
-  colsum_finalize_kernel<<<(channels + 127) / 128, 128, 0, STREAM>>>(stats, rows, n_total, col_offset, channels, out);
+  launch_k(colsum_finalize_kernel, dim3((channels + 127) / 128), dim3(128), 0, STREAM, stats, rows, n_total, col_offset, channels, out);
   return check_launch("colsum_finalize");
 }
 
@@ -933,17 +971,17 @@ extern "C" int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* 
     if ((e = check_act("bn_relu_pool(pooled)", pooled_pix_stride, channels))) return e;
     const long long total = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
     if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool: tensor too large (%lld items)", total);
-    bn_relu_pool_kernel<true><<<ew_grid(total, 256), 256, 0, STREAM>>>(
+    launch_k(bn_relu_pool_kernel<true>, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, 
         yp, y_pix_stride, scale, shift, ap, a_pix_stride, reinterpret_cast<__nv_bfloat16*>(pooled), pooled_pix_stride,
         batch, height, width, channels);
   } else {
     const long long total = (long long)batch * height * width * (channels / 8);
     if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool: tensor too large (%lld items)", total);
     if (256 % (channels / 8) == 0)
-      bn_relu_flat_kernel<<<flat_grid(total), 256, 0, STREAM>>>(yp, y_pix_stride, scale, shift, ap, a_pix_stride, total,
+      launch_k(bn_relu_flat_kernel, dim3(flat_grid(total)), dim3(256), 0, STREAM, yp, y_pix_stride, scale, shift, ap, a_pix_stride, total,
                                                                 channels / 8);
     else
-      bn_relu_pool_kernel<false><<<ew_grid(total, 256), 256, 0, STREAM>>>(yp, y_pix_stride, scale, shift, ap,
+      launch_k(bn_relu_pool_kernel<false>, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, yp, y_pix_stride, scale, shift, ap,
                                                                            a_pix_stride, nullptr, 0, batch, height,
                                                                            width, channels);
   }
@@ -983,23 +1021,23 @@ extern "C" int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const v
   __nv_bfloat16* dyp = reinterpret_cast<__nv_bfloat16*>(dy);
   const double count = (double)batch * height * width;
   if (pool)
-    bn_bwd_pool_reduce_kernel<<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, dPp, dPool_pix_stride, yp,
+    launch_k(bn_bwd_pool_reduce_kernel, dim3(blocks), dim3(256), 0, STREAM, dAp, dA_pix_stride, dPp, dPool_pix_stride, yp,
                                                             y_pix_stride, scale, shift, mean, invstd, partials, batch,
                                                             height, width, channels);
   else
-    bn_bwd_reduce_flat_kernel<<<blocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, yp, y_pix_stride, scale, shift, mean,
+    launch_k(bn_bwd_reduce_flat_kernel, dim3(blocks), dim3(256), 0, STREAM, dAp, dA_pix_stride, yp, y_pix_stride, scale, shift, mean,
                                                            invstd, partials, total, channels);
   if ((e = check_launch("bn_bwd_reduce"))) return e;
-  bn_bwd_finalize_par_kernel<<<(channels + 7) / 8, 256, 0, STREAM>>>(partials, blocks, channels, count, scale, mean,
+  launch_k(bn_bwd_finalize_par_kernel, dim3((channels + 7) / 8), dim3(256), 0, STREAM, partials, blocks, channels, count, scale, mean,
                                                                       invstd, dgamma, dbeta, coef);
   if ((e = check_launch("bn_bwd_finalize"))) return e;
   const int ablocks = ew_grid(total, 256);
   if (pool)
-    bn_bwd_pool_apply_kernel<<<ablocks, 256, 0, STREAM>>>(dAp, dA_pix_stride, dPp, dPool_pix_stride, yp, y_pix_stride,
+    launch_k(bn_bwd_pool_apply_kernel, dim3(ablocks), dim3(256), 0, STREAM, dAp, dA_pix_stride, dPp, dPool_pix_stride, yp, y_pix_stride,
                                                             scale, shift, coef, dyp, dy_pix_stride, batch, height,
                                                             width, channels);
   else
-    bn_bwd_apply_flat_kernel<<<flat_grid(total), 256, 0, STREAM>>>(dAp, dA_pix_stride, yp, y_pix_stride, scale, shift,
+    launch_k(bn_bwd_apply_flat_kernel, dim3(flat_grid(total)), dim3(256), 0, STREAM, dAp, dA_pix_stride, yp, y_pix_stride, scale, shift,
                                                                     coef, dyp, dy_pix_stride, total, channels);
   return check_launch("bn_bwd_apply");
 }
@@ -1024,10 +1062,10 @@ extern "C" int sunet_bn_bwd_apply(const void* dA, int dA_pix_stride, const void*
     return set_error(SUNET_ERR_WORKSPACE, "bn_bwd_apply: workspace %zu < %zu", workspace_bytes, need);
   float* coef = reinterpret_cast<float*>(workspace);
   const double count = (double)batch * height * width;
-  bn_bwd_finalize_par_kernel<<<(channels + 7) / 8, 256, 0, STREAM>>>(partials, partial_rows, channels, count, scale,
+  launch_k(bn_bwd_finalize_par_kernel, dim3((channels + 7) / 8), dim3(256), 0, STREAM, partials, partial_rows, channels, count, scale,
                                                                       mean, invstd, dgamma, dbeta, coef);
   if ((e = check_launch("bn_bwd_finalize"))) return e;
-  bn_bwd_apply_flat_kernel<<<flat_grid(total), 256, 0, STREAM>>>(
+  launch_k(bn_bwd_apply_flat_kernel, dim3(flat_grid(total)), dim3(256), 0, STREAM, 
       reinterpret_cast<const __nv_bfloat16*>(dA), dA_pix_stride, reinterpret_cast<const __nv_bfloat16*>(y),
       y_pix_stride, scale, shift, coef, reinterpret_cast<__nv_bfloat16*>(dy), dy_pix_stride, total, channels);
   return check_launch("bn_bwd_apply");

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(kHThreads, 1)
 conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
                   const HaloParams p) {
+  pdl_wait();
+  pdl_trigger();
   using C = HCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -303,7 +305,7 @@ static int halo_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUt
     if (e) return e;
     attr_set = true;
   }
-  conv3_halo_kernel<BN><<<grid, kHThreads, HCfg<BN>::SMEM, stream>>>(a0, a1, b, d, p);
+  launch_k(conv3_halo_kernel<BN>, dim3(grid), dim3(kHThreads), HCfg<BN>::SMEM, stream, a0, a1, b, d, p);
   return check_launch("conv3_halo_kernel");
 }
 

@@ -59,6 +59,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
 conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
                    const __grid_constant__ CUtensorMap mapY, const Halo2Params p) {
+  pdl_wait();
+  pdl_trigger();
   using C = H2Cfg<BN, BNB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -410,7 +412,7 @@ static int halo2_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     if (e) return e;
     attr_set = true;
   }
-  conv3_halo2_kernel<BN, BNB><<<grid, kH2Threads, H2Cfg<BN, BNB>::SMEM, stream>>>(a0, a1, b, d, y, p);
+  launch_k(conv3_halo2_kernel<BN, BNB>, dim3(grid), dim3(kH2Threads), H2Cfg<BN, BNB>::SMEM, stream, a0, a1, b, d, y, p);
   return check_launch("conv3_halo2_kernel");
 }
 

@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
                  const ConvGemmParams p) {
+  pdl_wait();
+  pdl_trigger();
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -388,7 +390,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     if (e) return e;
     attr_set = true;
   }
-  conv_gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::SMEM, stream>>>(a0, a1, b, d, p);
+  launch_k(conv_gemm_kernel<BN>, dim3(grid), dim3(kThreads), Cfg<BN>::SMEM, stream, a0, a1, b, d, p);
   return check_launch("conv_gemm_kernel");
 }
 

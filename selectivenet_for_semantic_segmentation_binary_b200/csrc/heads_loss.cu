@@ -41,6 +41,8 @@ struct HeadW {
 __global__ void __launch_bounds__(256)
 heads_fwd_kernel(const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads, float* __restrict__ logits,
                  long long P) {
+  pdl_wait();
+  pdl_trigger();
   // 8 lanes per pixel, 8 channels per lane
   const int sub = threadIdx.x & 7;
   float w[3][8];
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(256)
 bn_relu_heads_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
                      float* __restrict__ logits, long long P) {
+  pdl_wait();
+  pdl_trigger();
   const int sub = threadIdx.x & 7;
   float w[3][8], bias[3], sc[8], sh[8];
 #pragma unroll
@@ -153,6 +157,8 @@ bn_relu_heads_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* _
 __global__ void __launch_bounds__(256)
 heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
                  __nv_bfloat16* __restrict__ dA, int das, float* __restrict__ partials, long long P) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[256][28];
   const int sub = threadIdx.x & 7;
   float w[3][8];
@@ -235,6 +241,8 @@ struct HeadG {
   float* db[3];
 };
 __global__ void heads_bwd_reduce_kernel(const float* __restrict__ partials, int blocks, int nheads, HeadG hg) {
+  pdl_wait();
+  pdl_trigger();
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= 3 * 65) return;
   const int h = o / 65, c = o % 65;
@@ -258,6 +266,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256)
 loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ sel, const float* __restrict__ aux,
                  const float* __restrict__ tgt, long long P, double* __restrict__ partials) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][3];
   float S = 0.f, R = 0.f, A = 0.f;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
@@ -286,6 +296,8 @@ loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ sel, c
   }
 }
 __global__ void loss_sums_final_kernel(const double* __restrict__ partials, int blocks, double* sums) {
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x < 3) {
     double s = 0.0;
     for (int b = 0; b < blocks; ++b) s += partials[(size_t)b * 3 + threadIdx.x];
@@ -293,6 +305,8 @@ __global__ void loss_sums_final_kernel(const double* __restrict__ partials, int 
   }
 }
 __global__ void loss_finalize_kernel(const double* sums, double P, float lamb, float tc, float* results) {
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const double S = sums[0], R = sums[1], A = sums[2];
     const double c = S / P;
@@ -312,6 +326,8 @@ loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ sel, co
                 const float* __restrict__ tgt, long long P, const double* __restrict__ sums, double Pg, float lamb,
                 float tc, const float* __restrict__ g_sel, const float* __restrict__ g_aux, float* __restrict__ d_out,
                 float* __restrict__ d_sel, float* __restrict__ d_aux) {
+  pdl_wait();
+  pdl_trigger();
   const double S = sums[0], R = sums[1];
   const float gs = g_sel ? *g_sel : 1.f;
   const float ga = g_aux ? *g_aux : 1.f;
@@ -345,6 +361,8 @@ template <int LT>
 __global__ void __launch_bounds__(256)
 metric_hist_kernel(const float* __restrict__ out, const float* __restrict__ sel, const void* __restrict__ label,
                    long long P, float thr_out, float thr_sel, int masked, unsigned long long* __restrict__ counts) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ unsigned int red[8][6];
   unsigned int c[6] = {0, 0, 0, 0, 0, 0};
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
@@ -375,6 +393,8 @@ metric_hist_kernel(const float* __restrict__ out, const float* __restrict__ sel,
 __global__ void __launch_bounds__(256)
 adam_kernel(const sunet_adam_tensor* __restrict__ table, float lr, float b1, float b2, float eps, float wd,
             int step, const float* __restrict__ lr_dev, const int* __restrict__ step_dev) {
+  pdl_wait();
+  pdl_trigger();
   const sunet_adam_tensor t = table[blockIdx.y];
   // hyper-parameters that change per step may live on the device so that a captured CUDA graph
   // of the whole training step stays valid across replays
@@ -410,7 +430,7 @@ extern "C" int sunet_heads_fwd(const void* a, int a_pix_stride, const float* w0,
   HeadW hw = {{w0, w1, w2}, {b0, b1, b2}};
   for (int h = 0; h < nheads; ++h)
     if (!hw.w[h] || !hw.b[h]) return set_error(SUNET_ERR_INVALID, "heads_fwd: missing head %d parameters", h);
-  heads_fwd_kernel<<<grid_for(pixels * 8, 256, 8), 256, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+  launch_k(heads_fwd_kernel, dim3(grid_for(pixels * 8, 256, 8)), dim3(256), 0, STREAM, reinterpret_cast<const __nv_bfloat16*>(a),
                                                                       a_pix_stride, hw, nheads, logits, pixels);
   return check_launch("heads_fwd");
 }
@@ -425,7 +445,7 @@ extern "C" int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float*
   HeadW hw = {{w0, w1, w2}, {b0, b1, b2}};
   for (int h = 0; h < nheads; ++h)
     if (!hw.w[h] || !hw.b[h]) return set_error(SUNET_ERR_INVALID, "bn_relu_heads: missing head %d parameters", h);
-  bn_relu_heads_kernel<<<grid_for(pixels * 2, 256, 8), 256, 0, STREAM>>>(
+  launch_k(bn_relu_heads_kernel, dim3(grid_for(pixels * 2, 256, 8)), dim3(256), 0, STREAM, 
       reinterpret_cast<const __nv_bfloat16*>(y), y_pix_stride, scale, shift, reinterpret_cast<__nv_bfloat16*>(a),
       a_pix_stride, hw, nheads, logits, pixels);
   return check_launch("bn_relu_heads");
@@ -445,13 +465,13 @@ extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_st
   const size_t need = (size_t)blocks * 195 * sizeof(float);
   if (workspace_bytes < need) return set_error(SUNET_ERR_WORKSPACE, "heads_bwd: workspace %zu < %zu", workspace_bytes, need);
   float* partials = reinterpret_cast<float*>(workspace);
-  heads_bwd_kernel<<<blocks, 256, 0, STREAM>>>(dlogits, reinterpret_cast<const __nv_bfloat16*>(a), a_pix_stride, hw,
+  launch_k(heads_bwd_kernel, dim3(blocks), dim3(256), 0, STREAM, dlogits, reinterpret_cast<const __nv_bfloat16*>(a), a_pix_stride, hw,
                                                nheads, reinterpret_cast<__nv_bfloat16*>(dA), dA_pix_stride, partials,
                                                pixels);
   int e = check_launch("heads_bwd");
   if (e) return e;
   HeadG hg = {{dw0, dw1, dw2}, {db0, db1, db2}};
-  heads_bwd_reduce_kernel<<<1, 256, 0, STREAM>>>(partials, blocks, nheads, hg);
+  launch_k(heads_bwd_reduce_kernel, dim3(1), dim3(256), 0, STREAM, partials, blocks, nheads, hg);
   return check_launch("heads_bwd_reduce");
 }
 
@@ -464,17 +484,17 @@ extern "C" int sunet_loss_sums(const float* out, const float* sel, const float* 
   if (workspace_bytes < (size_t)blocks * 3 * sizeof(double))
     return set_error(SUNET_ERR_WORKSPACE, "loss_sums: workspace too small");
   double* partials = reinterpret_cast<double*>(workspace);
-  loss_sums_kernel<<<blocks, 256, 0, STREAM>>>(out, sel, aux, target, pixels, partials);
+  launch_k(loss_sums_kernel, dim3(blocks), dim3(256), 0, STREAM, out, sel, aux, target, pixels, partials);
   int e = check_launch("loss_sums");
   if (e) return e;
-  loss_sums_final_kernel<<<1, 32, 0, STREAM>>>(partials, blocks, sums);
+  launch_k(loss_sums_final_kernel, dim3(1), dim3(32), 0, STREAM, partials, blocks, sums);
   return check_launch("loss_sums_final");
 }
 
 extern "C" int sunet_loss_finalize(const double* sums, long long global_pixels, float lamb, float target_coverage,
                                    float* results, sunet_stream_t stream_) {
   if (!sums || !results || global_pixels <= 0) return set_error(SUNET_ERR_INVALID, "loss_finalize: bad arguments");
-  loss_finalize_kernel<<<1, 32, 0, STREAM>>>(sums, (double)global_pixels, lamb, target_coverage, results);
+  launch_k(loss_finalize_kernel, dim3(1), dim3(32), 0, STREAM, sums, (double)global_pixels, lamb, target_coverage, results);
   return check_launch("loss_finalize");
 }
 
@@ -486,7 +506,7 @@ extern "C" int sunet_loss_bwd(const float* out, const float* sel, const float* a
     return set_error(SUNET_ERR_INVALID, "loss_bwd: bad arguments");
   if ((d_out || d_sel) && (!out || !sel)) return set_error(SUNET_ERR_INVALID, "loss_bwd: d_out/d_sel need out and sel");
   if (d_aux && !aux) return set_error(SUNET_ERR_INVALID, "loss_bwd: d_aux needs aux");
-  loss_bwd_kernel<<<grid_for(pixels, 256, 8), 256, 0, STREAM>>>(out, sel, aux, target, pixels, sums,
+  launch_k(loss_bwd_kernel, dim3(grid_for(pixels, 256, 8)), dim3(256), 0, STREAM, out, sel, aux, target, pixels, sums,
                                                                  (double)global_pixels, lamb, target_coverage, g_sel,
                                                                  g_aux, d_out, d_sel, d_aux);
   return check_launch("loss_bwd");
@@ -500,13 +520,13 @@ extern "C" int sunet_metric_hist(const float* out, const float* sel, const void*
   const int blocks = grid_for(pixels, 256, 8);
   switch (label_dtype) {
     case 0:
-      metric_hist_kernel<0><<<blocks, 256, 0, STREAM>>>(out, sel, label, pixels, thr_out, thr_sel, masked, counts);
+      launch_k(metric_hist_kernel<0>, dim3(blocks), dim3(256), 0, STREAM, out, sel, label, pixels, thr_out, thr_sel, masked, counts);
       break;
     case 1:
-      metric_hist_kernel<1><<<blocks, 256, 0, STREAM>>>(out, sel, label, pixels, thr_out, thr_sel, masked, counts);
+      launch_k(metric_hist_kernel<1>, dim3(blocks), dim3(256), 0, STREAM, out, sel, label, pixels, thr_out, thr_sel, masked, counts);
       break;
     case 2:
-      metric_hist_kernel<2><<<blocks, 256, 0, STREAM>>>(out, sel, label, pixels, thr_out, thr_sel, masked, counts);
+      launch_k(metric_hist_kernel<2>, dim3(blocks), dim3(256), 0, STREAM, out, sel, label, pixels, thr_out, thr_sel, masked, counts);
       break;
     default:
       return set_error(SUNET_ERR_INVALID, "metric_hist: bad label dtype %d", label_dtype);
@@ -523,7 +543,7 @@ extern "C" int sunet_adam_step(const sunet_adam_tensor* table, int n_tensors, lo
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)n_tensors);
-  adam_kernel<<<grid, 256, 0, STREAM>>>(table, lr, beta1, beta2, eps, weight_decay, step, lr_dev, step_dev);
+  launch_k(adam_kernel, dim3(grid), dim3(256), 0, STREAM, table, lr, beta1, beta2, eps, weight_decay, step, lr_dev, step_dev);
   return check_launch("adam_step");
 }
 

@@ -56,6 +56,8 @@ constexpr int MAX_STAGES = 12;
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
                   const __grid_constant__ CUtensorMap mapB1, const WgradParams p, const int stage_bytes) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
@@ -224,6 +226,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
                        const __grid_constant__ CUtensorMap mapB1, const WgradParams p, const int stage_bytes) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
@@ -378,6 +382,8 @@ wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX0,
                const __grid_constant__ CUtensorMap mapX1, const WgradParams p, const int stage_bytes) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
@@ -680,7 +686,7 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
         return e;
       attr64 = true;
     }
-    wgrad64_kernel<<<w.n_tiles * w.splits, WG_THREADS, st * sbytes + 1024 + bbytes, stream>>>(mA, mB0, mB1, q, sbytes);
+    launch_k(wgrad64_kernel, dim3(w.n_tiles * w.splits), dim3(WG_THREADS), st * sbytes + 1024 + bbytes, stream, mA, mB0, mB1, q, sbytes);
     return check_launch("wgrad64_kernel");
   }
   WgradParams p;
@@ -744,19 +750,21 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     cfg.blockDim = dim3(WG_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if ((e = check_cuda(cudaLaunchKernelEx(&cfg, wgrad_gemm_pair_kernel, mA, mB0, mB1, p, stage_bytes),
                         "cudaLaunchKernelEx(wgrad_gemm_pair)")))
       return e;
     return check_launch("wgrad_gemm_pair_kernel");
   }
-  wgrad_gemm_kernel<<<grid, WG_THREADS, smem, stream>>>(mA, mB0, mB1, p, stage_bytes);
+  launch_k(wgrad_gemm_kernel, dim3(grid), dim3(WG_THREADS), smem, stream, mA, mB0, mB1, p, stage_bytes);
   return check_launch("wgrad_gemm_kernel");
 }
 
@@ -768,6 +776,8 @@ namespace sunet {
 template <int TAPS>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_taps_kernel(const float* __restrict__ P, int splits, long long ab, float* __restrict__ grad) {
+  pdl_wait();
+  pdl_trigger();
   const long long slab = TAPS * ab;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < slab;
        i += (long long)gridDim.x * blockDim.x) {
@@ -791,6 +801,8 @@ wgrad_reduce_taps_kernel(const float* __restrict__ P, int splits, long long ab, 
 __global__ void __launch_bounds__(256)
 wgrad_reduce_first_kernel(const float* __restrict__ P, int splits, int Ca, int Nb, int real_cin,
                           float* __restrict__ grad, long long total) {
+  pdl_wait();
+  pdl_trigger();
   const long long slab = (long long)Ca * Nb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -820,11 +832,11 @@ extern "C" int sunet_wgrad_reduce(const float* partials, int splits, int taps, i
   if (blocks > cap) blocks = cap;
   const long long ab = (long long)a_channels * b_channels;
   if (layout == 0)
-    wgrad_reduce_taps_kernel<9><<<(int)blocks, 256, 0, stream>>>(partials, splits, ab, grad);
+    launch_k(wgrad_reduce_taps_kernel<9>, dim3((int)blocks), dim3(256), 0, stream, partials, splits, ab, grad);
   else if (layout == 1)
-    wgrad_reduce_taps_kernel<4><<<(int)blocks, 256, 0, stream>>>(partials, splits, ab, grad);
+    launch_k(wgrad_reduce_taps_kernel<4>, dim3((int)blocks), dim3(256), 0, stream, partials, splits, ab, grad);
   else
-    wgrad_reduce_first_kernel<<<(int)blocks, 256, 0, stream>>>(partials, splits, a_channels, b_channels, real_cin,
+    launch_k(wgrad_reduce_first_kernel, dim3((int)blocks), dim3(256), 0, stream, partials, splits, a_channels, b_channels, real_cin,
                                                                grad, total);
   return check_launch("wgrad_reduce");
 }
