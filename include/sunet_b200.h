@@ -187,12 +187,22 @@ int sunet_colsum_finalize(const float* stats, int rows, int n_total, int col_off
 int sunet_heads_fwd(const void* a, int a_pix_stride, const float* w0, const float* b0, const float* w1,
                     const float* b1, const float* w2, const float* b2, int nheads, float* logits, long long pixels,
                     sunet_stream_t stream);
-/* last block fused: a = relu(y*scale + shift) (64 channels, written for backward) and the heads' logits
- * from the same registers (model.py:12-13 of decoder_layer_1_1 + :96-101) */
+/* last block fused: a = relu(y*scale + shift) (64 channels) and the heads' logits from the same registers
+ * (model.py:12-13 of decoder_layer_1_1 + :96-101).  a may be NULL when the backward pass recomputes the
+ * activation from y (sunet_heads_bwd_bn): the tensor is then never written. */
 int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
                         int a_pix_stride, const float* w0, const float* b0, const float* w1, const float* b1,
                         const float* w2, const float* b2, int nheads, float* logits, long long pixels,
                         sunet_stream_t stream);
+/* sunet_heads_bwd with the activation recomputed from y = the last block's conv output (nothing but y is read),
+ * plus that block's BatchNorm-backward reduction: bn_partials[sunet_heads_bwd_bn_rows(pixels)][64][2] receives
+ * per-block (sum g, sum g*xhat), g = dA where relu(bn(y)) > 0 — the rows sunet_bn_bwd_apply() folds. */
+int sunet_heads_bwd_bn_rows(long long pixels);
+int sunet_heads_bwd_bn(const float* dlogits, const void* y, int y_pix_stride, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, const float* w0, const float* w1, const float* w2,
+                       int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0, float* dw1, float* db1,
+                       float* dw2, float* db2, float* bn_partials, long long pixels, void* workspace,
+                       size_t workspace_bytes, sunet_stream_t stream);
 /* dA[p][c] = sum_h dl[h][p]*w_h[c] (bf16);  dw_h[c] = sum_p dl[h][p]*a[p][c];  db_h = sum_p dl[h][p] */
 int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,
                     const float* w2, int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0, float* dw1,

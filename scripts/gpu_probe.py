@@ -390,6 +390,34 @@ def ew_heads_loss(K):
     for h in range(3):
         ok &= report(f"heads bwd dw{h}", dws[h].reshape(64), dl[h] @ af, 1e-4)
         ok &= report(f"heads bwd db{h}", dbs[h], dl[h].sum().reshape(1), 1e-4)
+    # heads bwd on y with the BN-backward reduction fused (activation never stored): identical head gradients
+    # and dA as heads_bwd on a1 = relu(bn(yraw)); rows + bn_bwd_apply == bn_relu_pool_bwd on that dA
+    mean_ = (torch.randn(64, generator=g) * 0.3).to(dev)
+    istd_ = (torch.rand(64, generator=g) + 0.5).to(dev)
+    dA1, dA2 = torch.empty_like(dA), torch.empty_like(dA)
+    dws1, dbs1 = [torch.empty_like(w) for w in ws_], [torch.empty_like(b) for b in bs_]
+    dws2, dbs2 = [torch.empty_like(w) for w in ws_], [torch.empty_like(b) for b in bs_]
+    K.heads_bwd(dl, a1, ws_, dA1, dws1, dbs1, ws)
+    lgn = torch.empty(3, P, device=dev)
+    K.bn_relu_heads(yraw, sc_, sh_, None, ws_, bs_, lgn)          # a not stored
+    rows = K.heads_bwd_bn_rows(P)
+    part = torch.full((rows, 64, 2), float("nan"), device=dev)
+    K.heads_bwd_bn(dl, yraw, sc_, sh_, mean_, istd_, ws_, dA2, dws2, dbs2, part, ws)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(dA1, dA2)) and bool(torch.equal(lgn, lg2))
+    print(f"  [{'OK ' if same else 'BAD'}] heads_bwd_bn: dA and logits identical to the stored-activation path")
+    ok &= same
+    for h in range(3):
+        ok &= report(f"heads_bwd_bn dw{h}", dws2[h], dws1[h], 1e-5)
+        ok &= report(f"heads_bwd_bn db{h}", dbs2[h], dbs1[h], 1e-5)
+    dg1, db1, dg2, db2 = (torch.empty(64, device=dev) for _ in range(4))
+    dy1, dy2 = torch.empty_like(yraw), torch.empty_like(yraw)
+    K.bn_bwd_apply(dA2, yraw, sc_, sh_, mean_, istd_, part, rows, dg1, db1, dy1, ws)
+    K.bn_relu_pool_bwd(dA1, None, yraw, sc_, sh_, mean_, istd_, sc_, dg2, db2, dy2, ws)
+    torch.cuda.synchronize()
+    ok &= report("heads_bwd_bn -> dgamma", dg1, dg2, 1e-4)
+    ok &= report("heads_bwd_bn -> dbeta", db1, db2, 1e-4)
+    ok &= report("heads_bwd_bn -> dy", dy1.float(), dy2.float(), 4e-3)
     # metric
     counts = torch.zeros(6, dtype=torch.int64, device=dev)
     K.metric_hist(logits[0], logits[1], tgt, 0.0, 0.0, True, counts)

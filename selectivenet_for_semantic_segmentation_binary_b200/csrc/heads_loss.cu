@@ -130,7 +130,7 @@ bn_relu_heads_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* _
       bf16x8 o;
 #pragma unroll
       for (int i = 0; i < 4; ++i) o.w[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-      if (p < P) *reinterpret_cast<bf16x8*>(a + p * as + sub * 8) = o;
+      if (a != nullptr && p < P) *reinterpret_cast<bf16x8*>(a + p * as + sub * 8) = o;
       float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -154,9 +154,22 @@ bn_relu_heads_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* _
 }
 
 // ------------------------------------------------------------------ heads backward
-__global__ void __launch_bounds__(256)
+// BN = true: `a` holds y, the raw conv output of the last block; the activation relu(bn(y)) is recomputed (bit-
+// identical to what bn_relu_heads produced, which then need not be stored at all), and the BatchNorm-backward
+// reduction of that block is accumulated on the way: bnb[block][64][2] = (sum g, sum g*xhat) with
+// g = dA (bf16-rounded, as stored) where the activation is > 0.
+struct HeadBN {
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  float* partials;     // [gridDim.x][64][2]
+};
+
+template <bool BN>
+__global__ void __launch_bounds__(256, 2)
 heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
-                 __nv_bfloat16* __restrict__ dA, int das, float* __restrict__ partials, long long P) {
+                 __nv_bfloat16* __restrict__ dA, int das, float* __restrict__ partials, long long P, HeadBN bn) {
   pdl_wait();
   pdl_trigger();
   __shared__ float red[256][28];
@@ -166,14 +179,24 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
   for (int h = 0; h < 3; ++h)
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[h][j] = (h < nheads) ? __ldg(hw.w[h] + sub * 8 + j) : 0.f;
+  float sc[8], sh[8], mu[8], sg[8], sgy[8];
+  if (BN) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(bn.scale + sub * 8 + j);
+      sh[j] = __ldg(bn.shift + sub * 8 + j);
+      mu[j] = __ldg(bn.mean + sub * 8 + j);
+      sg[j] = sgy[j] = 0.f;
+    }
+  }
   float dw[3][8];
   float db[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int h = 0; h < 3; ++h)
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw[h][j] = 0.f;
-  // four pixels per thread per trip: all loads are issued before any is consumed
-  constexpr int U = 4;
+  // U pixels per thread per trip: all loads are issued before any is consumed
+  constexpr int U = BN ? 2 : 4;
   const long long ppb = (long long)(blockDim.x >> 3);                 // pixels per block per sub-trip
   for (long long p0 = blockIdx.x * ppb * U + (threadIdx.x >> 3); p0 < P; p0 += (long long)gridDim.x * ppb * U) {
     float g[U][3];
@@ -191,11 +214,24 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
     for (int u = 0; u < U; ++u) {
       const long long p = p0 + u * ppb;
       if (p < P) {
-        float av[8];
+        float av[8], yv[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           av[2 * i] = bf16lo(v[u].w[i]);
           av[2 * i + 1] = bf16hi(v[u].w[i]);
+        }
+        if (BN) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            yv[j] = av[j];
+            av[j] = fmaxf(fmaf(yv[j], sc[j], sh[j]), 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {       // the bf16 rounding bn_relu_heads applied before the dots
+            const uint32_t r = pack_bf16x2(av[2 * i], av[2 * i + 1]);
+            av[2 * i] = bf16lo(r);
+            av[2 * i + 1] = bf16hi(r);
+          }
         }
         float o[8];
 #pragma unroll
@@ -208,6 +244,17 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
 #pragma unroll
         for (int i = 0; i < 4; ++i) ov.w[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
         *reinterpret_cast<bf16x8*>(dA + p * das + sub * 8) = ov;
+        if (BN) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float g0 = av[2 * i] > 0.f ? bf16lo(ov.w[i]) : 0.f;
+            const float g1 = av[2 * i + 1] > 0.f ? bf16hi(ov.w[i]) : 0.f;
+            sg[2 * i] += g0;
+            sg[2 * i + 1] += g1;
+            sgy[2 * i] = fmaf(g0, yv[2 * i] - mu[2 * i], sgy[2 * i]);
+            sgy[2 * i + 1] = fmaf(g1, yv[2 * i + 1] - mu[2 * i + 1], sgy[2 * i + 1]);
+          }
+        }
         if (sub == 0) {
 #pragma unroll
           for (int h = 0; h < 3; ++h) db[h] += g[u][h];
@@ -233,6 +280,23 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
       for (int r = 0; r < 32; ++r) s += red[r * 8][24 + h];
     }
     partials[(size_t)blockIdx.x * 195 + o] = s;
+  }
+  if (BN) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[threadIdx.x][j] = sg[j];
+      red[threadIdx.x][8 + j] = sgy[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int c = threadIdx.x >> 1, which = threadIdx.x & 1;       // channel, (sum g | sum g*(y-mean))
+      const int sb = c >> 3, j = c & 7;
+      float s = 0.f;
+      for (int r = 0; r < 32; ++r) s += red[r * 8 + sb][which * 8 + j];
+      if (which) s *= __ldg(bn.invstd + c);
+      bn.partials[((size_t)blockIdx.x * 64 + c) * 2 + which] = s;
+    }
   }
 }
 
@@ -439,8 +503,8 @@ extern "C" int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float*
                                    int a_pix_stride, const float* w0, const float* b0, const float* w1,
                                    const float* b1, const float* w2, const float* b2, int nheads, float* logits,
                                    long long pixels, sunet_stream_t stream_) {
-  if (!y || !scale || !shift || !a || !logits || pixels <= 0 || (nheads != 1 && nheads != 3) || y_pix_stride < 64 ||
-      y_pix_stride % 8 || a_pix_stride < 64 || a_pix_stride % 8)
+  if (!y || !scale || !shift || !logits || pixels <= 0 || (nheads != 1 && nheads != 3) || y_pix_stride < 64 ||
+      y_pix_stride % 8 || (a && (a_pix_stride < 64 || a_pix_stride % 8)))
     return set_error(SUNET_ERR_INVALID, "bn_relu_heads: bad arguments");
   HeadW hw = {{w0, w1, w2}, {b0, b1, b2}};
   for (int h = 0; h < nheads; ++h)
@@ -450,6 +514,8 @@ extern "C" int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float*
       a_pix_stride, hw, nheads, logits, pixels);
   return check_launch("bn_relu_heads");
 }
+
+static int heads_bwd_blocks(long long pixels, bool bn) { return grid_for(pixels * 8, 256, bn ? 2 : 4); }
 
 extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,
                                const float* w2, int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0,
@@ -461,14 +527,48 @@ extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_st
   HeadW hw = {{w0, w1, w2}, {nullptr, nullptr, nullptr}};
   for (int h = 0; h < nheads; ++h)
     if (!hw.w[h]) return set_error(SUNET_ERR_INVALID, "heads_bwd: missing head %d weights", h);
-  int blocks = grid_for(pixels * 8, 256, 4);
+  int blocks = heads_bwd_blocks(pixels, false);
   const size_t need = (size_t)blocks * 195 * sizeof(float);
   if (workspace_bytes < need) return set_error(SUNET_ERR_WORKSPACE, "heads_bwd: workspace %zu < %zu", workspace_bytes, need);
   float* partials = reinterpret_cast<float*>(workspace);
-  launch_k(heads_bwd_kernel, dim3(blocks), dim3(256), 0, STREAM, dlogits, reinterpret_cast<const __nv_bfloat16*>(a), a_pix_stride, hw,
-                                               nheads, reinterpret_cast<__nv_bfloat16*>(dA), dA_pix_stride, partials,
-                                               pixels);
+  HeadBN nobn = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  launch_k(heads_bwd_kernel<false>, dim3(blocks), dim3(256), 0, STREAM, dlogits,
+           reinterpret_cast<const __nv_bfloat16*>(a), a_pix_stride, hw, nheads, reinterpret_cast<__nv_bfloat16*>(dA),
+           dA_pix_stride, partials, pixels, nobn);
   int e = check_launch("heads_bwd");
+  if (e) return e;
+  HeadG hg = {{dw0, dw1, dw2}, {db0, db1, db2}};
+  launch_k(heads_bwd_reduce_kernel, dim3(1), dim3(256), 0, STREAM, partials, blocks, nheads, hg);
+  return check_launch("heads_bwd_reduce");
+}
+
+extern "C" int sunet_heads_bwd_bn_rows(long long pixels) {
+  return pixels > 0 ? heads_bwd_blocks(pixels, true) : -1;
+}
+
+extern "C" int sunet_heads_bwd_bn(const float* dlogits, const void* y, int y_pix_stride, const float* scale,
+                                  const float* shift, const float* mean, const float* invstd, const float* w0,
+                                  const float* w1, const float* w2, int nheads, void* dA, int dA_pix_stride,
+                                  float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2,
+                                  float* bn_partials, long long pixels, void* workspace, size_t workspace_bytes,
+                                  sunet_stream_t stream_) {
+  if (!dlogits || !y || !dA || !workspace || !scale || !shift || !mean || !invstd || !bn_partials || pixels <= 0 ||
+      (nheads != 1 && nheads != 3) || y_pix_stride < 64 || y_pix_stride % 8 || dA_pix_stride < 64 ||
+      dA_pix_stride % 8)
+    return set_error(SUNET_ERR_INVALID, "heads_bwd_bn: bad arguments");
+  HeadW hw = {{w0, w1, w2}, {nullptr, nullptr, nullptr}};
+  for (int h = 0; h < nheads; ++h)
+    if (!hw.w[h]) return set_error(SUNET_ERR_INVALID, "heads_bwd_bn: missing head %d weights", h);
+  int blocks = heads_bwd_blocks(pixels, true);
+  const size_t need = (size_t)blocks * 195 * sizeof(float);
+  if (workspace_bytes < need)
+    return set_error(SUNET_ERR_WORKSPACE, "heads_bwd_bn: workspace %zu < %zu", workspace_bytes, need);
+  float* partials = reinterpret_cast<float*>(workspace);
+  HeadBN bn = {scale, shift, mean, invstd, bn_partials};
+  launch_k(heads_bwd_kernel<true>, dim3(blocks), dim3(256), 0, STREAM, dlogits,
+           reinterpret_cast<const __nv_bfloat16*>(y), y_pix_stride, hw, nheads, reinterpret_cast<__nv_bfloat16*>(dA),
+           dA_pix_stride, partials, pixels, bn);
+  int e = check_launch("heads_bwd_bn");
   if (e) return e;
   HeadG hg = {{dw0, dw1, dw2}, {db0, db1, db2}};
   launch_k(heads_bwd_reduce_kernel, dim3(1), dim3(256), 0, STREAM, partials, blocks, nheads, hg);

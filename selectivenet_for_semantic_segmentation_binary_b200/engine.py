@@ -161,6 +161,14 @@ class SUNetPlan:
                     cl.bnb_rows = rows
                     cl.bnb_stats = torch.zeros(rows, cl.cout, 2, device=dev)
                     self.bnb_of[pn] = cl
+        # the last block: heads_bwd recomputes relu(bn(y)) from y and emits the BN-backward reduction rows, so the
+        # activation of decoder_layer_1_1 is never stored (SUNET_FUSE_HEADS_BN=0 restores the two-pass form)
+        self.fuse_heads_bn = os.environ.get("SUNET_FUSE_HEADS_BN", "1") != "0"
+        if self.fuse_heads_bn:
+            last = self.layers["decoder_layer_1_1"]
+            last.bnb_rows = K.heads_bwd_bn_rows(B * height * width)
+            last.bnb_stats = torch.zeros(last.bnb_rows, last.cout, 2, device=dev)
+            last.a = None
         self.ws = K.new_workspace(dev)
         self.partials = None      # sized lazily from the wgrad split plan
         self._partials_bytes = 0
@@ -392,14 +400,21 @@ class SUNetPlan:
         L = self.layers
         B = self.B
         heads = ["conv1x1"] + (["conv_select", "conv_aux"] if self.selective else [])
-        K.heads_bwd(dlogits, L["decoder_layer_1_1"].a, [params[f"{h}.weight"] for h in heads], self.gA[1],
-                    [grads[f"{h}.weight"] for h in heads], [grads[f"{h}.bias"] for h in heads], self.ws)
+        last = L["decoder_layer_1_1"]
+        if self.fuse_heads_bn:
+            K.heads_bwd_bn(dlogits, last.y, last.scale, last.shift, last.mean, last.invstd,
+                           [params[f"{h}.weight"] for h in heads], self.gA[1], [grads[f"{h}.weight"] for h in heads],
+                           [grads[f"{h}.bias"] for h in heads], last.bnb_stats, self.ws)
+        else:
+            K.heads_bwd(dlogits, last.a, [params[f"{h}.weight"] for h in heads], self.gA[1],
+                        [grads[f"{h}.weight"] for h in heads], [grads[f"{h}.bias"] for h in heads], self.ws)
         dA = self.gA[1]
         for lvl, (n2, n1) in ((1, ("decoder_layer_1_2", "decoder_layer_1_1")),
                               (2, ("decoder_layer_2_2", "decoder_layer_2_1")),
                               (3, ("decoder_layer_3_2", "decoder_layer_3_1"))):
             c = _CH[lvl]
-            f = self._cbr_bwd(L[n1], dA, None, params, grads, self.gA[lvl])
+            f = self._cbr_bwd(L[n1], dA, None, params, grads, self.gA[lvl],
+                              fused_reduce=(lvl == 1 and self.fuse_heads_bn))
             st, rows = self.dcat_stats[lvl]
             self._cbr_bwd(L[n2], self.gA[lvl], None, params, grads, self.dcat[lvl], st, fused_reduce=f)
             # ConvTranspose backward: bias (column sums of d_up), weight, input

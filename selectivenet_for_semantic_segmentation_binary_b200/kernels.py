@@ -242,8 +242,9 @@ def heads_fwd(a, weights, biases, logits) -> None:
 
 
 def bn_relu_heads(y, scale, shift, a, weights, biases, logits) -> None:
+    """a may be None: the activation is then not stored (heads_bwd_bn recomputes it from y)."""
     yp, _, ys = _act(y)
-    ap, _, as_ = _act(a)
+    ap, as_ = (None, 0) if a is None else _act(a)[::2]
     n = len(weights)
     w = [_f32(t.reshape(-1)) for t in weights] + [None] * (3 - n)
     b = [_f32(t.reshape(-1)) for t in biases] + [None] * (3 - n)
@@ -265,6 +266,28 @@ def heads_bwd(dlogits, a, weights, dA, dws, dbs, workspace) -> None:
     _lib.check(_lib.load().sunet_heads_bwd(dlogits.data_ptr(), ap, as_, w[0], w[1], w[2], n, dp, ds, dw[0], db[0],
                                            dw[1], db[1], dw[2], db[2], P, workspace.data_ptr(), workspace.numel(),
                                            _stream()), "sunet_heads_bwd")
+
+
+def heads_bwd_bn_rows(pixels: int) -> int:
+    return int(_lib.load().sunet_heads_bwd_bn_rows(pixels))
+
+
+def heads_bwd_bn(dlogits, y, scale, shift, mean, invstd, weights, dA, dws, dbs, bn_partials, workspace) -> None:
+    """heads_bwd on y (activation recomputed) + the last block's BN-backward reduction rows into bn_partials."""
+    yp, _, ys = _act(y)
+    dp, _, ds = _act(dA)
+    n = len(weights)
+    w = [_f32(t.reshape(-1)) for t in weights] + [None] * (3 - n)
+    dw = [_f32(t.reshape(-1)) for t in dws] + [None] * (3 - n)
+    db = [_f32(t.reshape(-1)) for t in dbs] + [None] * (3 - n)
+    P = y.shape[0] * y.shape[1] * y.shape[2]
+    assert y.shape[3] == 64 and dlogits.dtype == torch.float32 and dlogits.is_contiguous() and dlogits.numel() == n * P
+    assert bn_partials.dtype == torch.float32 and bn_partials.is_contiguous()
+    assert bn_partials.numel() >= heads_bwd_bn_rows(P) * 64 * 2
+    _lib.check(_lib.load().sunet_heads_bwd_bn(dlogits.data_ptr(), yp, ys, _f32(scale), _f32(shift), _f32(mean),
+                                              _f32(invstd), w[0], w[1], w[2], n, dp, ds, dw[0], db[0], dw[1], db[1],
+                                              dw[2], db[2], bn_partials.data_ptr(), P, workspace.data_ptr(),
+                                              workspace.numel(), _stream()), "sunet_heads_bwd_bn")
 
 
 def loss_sums(out, sel, aux, target, sums, workspace) -> None:
