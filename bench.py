@@ -327,8 +327,13 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
     def conv_gemm(a_mode, grid, src0, weights, dst, **kw):
         m = grid[0] * grid[1] * grid[2]
         n, k = weights.shape
-        if a_mode == K.A_PLAIN and k == 64 and src0 is tr.net._plans[next(iter(tr.net._plans))].col:
+        plan0 = tr.net._plans[next(iter(tr.net._plans))]
+        if a_mode == K.A_PLAIN and k == 64 and src0 is plan0.col:
             k = 27                                   # first layer: 9*3 real taps*channels, rest is zero padding
+        elif a_mode == K.A_PLAIN and k == 64 and n == 128 and getattr(plan0, "first_pair", False) and \
+                src0.data_ptr() == plan0.col.data_ptr():
+            n, k = 64, 27 * 2                        # paired-pixel first layer: m counts pixel PAIRS; real work is
+            #                                          2 pixels x 64 outputs x 27 taps*channels per GEMM row
         DESC[0] = f"mode{a_mode} grid{tuple(grid)} C{src0.shape[3]}{'+' + str(kw['src1'].shape[3]) if kw.get('src1') is not None else ''} N{n} K{k}"
         return timed("conv_gemm", 2.0 * m * n * k, orig_conv, a_mode, grid, src0, weights, dst, **kw)
 

@@ -107,7 +107,9 @@ int sunet_wgrad_gemm_splits(const sunet_wgrad_gemm_args* args); /* how many spli
 /* sum the split-K partials into the reference's parameter-gradient layout.
  *   layout 0: conv3x3  grad[co][ci][3][3]   from P[s][r*3+q][co][ci]
  *   layout 1: convT    grad[ci][co][2][2]   from P[s][a*2+b][ci][co]
- *   layout 2: first conv (im2col'ed input)  grad[co][cin][3][3] from P[s][0][co][(r*3+q)*cin+ci] */
+ *   layout 2: first conv (im2col'ed input)  grad[co][cin][3][3] from P[s][0][co][(r*3+q)*cin+ci]
+ *   layout 3: first conv, paired-pixel form (a_channels 128, b_channels 64): the two diagonal 64x32 blocks of
+ *             P[s][0][128][64] summed (see sunet_pack_input_im2col32) */
 int sunet_wgrad_reduce(const float* partials, int splits, int taps, int a_channels, int b_channels, int layout,
                        int real_cin, float* grad, sunet_stream_t stream);
 
@@ -117,6 +119,16 @@ int sunet_wgrad_reduce(const float* partials, int splits, int taps, int a_channe
 /* x: fp32 NCHW [B][cin][H][W] (cin*9 <= 64) -> bf16 [B][H][W][64], channel tap*cin+ci = x[.., y+r-1, x+q-1] */
 int sunet_pack_input_im2col(const float* x, void* out, int batch, int cin, int height, int width,
                             sunet_stream_t stream);
+/* Paired-pixel form of the first layer (cin = 2 or 3, even width): bf16 [B][H][W][32], channel tap*cin+ci, rest 0.
+ * Viewed as [B][H][W/2][64], a row holds two adjacent pixels; with the weights of
+ * sunet_pack_conv1_pair_weights ([128][64]: rows 0..63 = [w | 0], rows 64..127 = [0 | w]) one PLAIN
+ * sunet_conv_gemm over the (B, H, W/2) grid with n_total = 128 writes the NHWC [B][H][W][64] output viewed as
+ * [B][H][W/2][128] — half the im2col traffic of the 64-wide form and no new GEMM kernel.  The matching weight
+ * gradient is a PLAIN sunet_wgrad_gemm with A = dY viewed [..][W/2][128], B = this tensor, folded by
+ * sunet_wgrad_reduce(layout 3). */
+int sunet_pack_input_im2col32(const float* x, void* out, int batch, int cin, int height, int width,
+                              sunet_stream_t stream);
+int sunet_pack_conv1_pair_weights(const float* w, void* wf, int cout, int cin, sunet_stream_t stream);
 /* Conv2d weight [co][ci][3][3] -> wf [co][9*ci] (k = tap*ci_total + ci) and, if wd != NULL,
  * the dgrad operand wd [ci][9*co] (k = flipped_tap*co_total + co) */
 int sunet_pack_conv3x3_weights(const float* w, void* wf, void* wd, int cout, int cin, sunet_stream_t stream);
@@ -130,6 +142,7 @@ int sunet_pack_convT_weights(const float* w, const float* bias, void* wf, void* 
 /* every pack of one forward pass in ONE launch: a DEVICE table of jobs.
  *   kind 0: conv3x3  (a = cout, b = cin; wf, wd as sunet_pack_conv3x3_weights)
  *   kind 1: first conv (a = cout, b = cin; wf as sunet_pack_conv1_weights)
+ *   kind 3: first conv, paired-pixel form (a = 64, b = cin; wf as sunet_pack_conv1_pair_weights)
  *   kind 2: ConvTranspose2d (a = cin, b = cout; wf, wd, bias, bias4 as sunet_pack_convT_weights) */
 typedef struct sunet_pack_job {
   int kind, a, b, pad_;

@@ -255,6 +255,34 @@ def g2_wgrad(K):
     wref = torch.zeros(Cout, Cin, 3, 3, device=dev, requires_grad=True)
     F.conv2d(x.to(torch.bfloat16).float(), wref, padding=1).backward(nchw(dyb))
     ok &= report("wgrad first layer (im2col)", grad, wref.grad, 1e-2)
+    # paired-pixel first layer: im2col32 + PLAIN GEMM over pixel pairs with block-diagonal weights
+    col32 = torch.empty(B, H, W, 32, dtype=torch.bfloat16, device=dev)
+    K.pack_input_im2col32(x, col32)
+    same = bool(torch.equal(col32[..., :27], col[..., :27])) and bool((col32[..., 27:] == 0).all())
+    print(f"  [{'OK ' if same else 'BAD'}] im2col32 == first 27 channels of im2col, zero padded")
+    ok &= same
+    w1q = (torch.randn(Cout, Cin, 3, 3, generator=torch.Generator().manual_seed(10)) / 5).to(dev)
+    w1pp = torch.empty(128, 64, dtype=torch.bfloat16, device=dev)
+    K.pack_conv1_pair_weights(w1q, w1pp)
+    ypair = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
+    rows = K.conv_gemm_stat_rows(B, H, W // 2, 128, K.A_PLAIN)
+    stp = torch.zeros(rows, 128, 2, device=dev)
+    K.conv_gemm(K.A_PLAIN, (B, H, W // 2), col32.view(B, H, W // 2, 64), w1pp, ypair.view(B, H, W // 2, 128), stats=stp)
+    torch.cuda.synchronize()
+    refp = F.conv2d(x.to(torch.bfloat16).float(), w1q.to(torch.bfloat16).float(), padding=1)
+    ok &= report("first layer fwd (paired pixels)", nchw(ypair), refp)
+    yf = ypair.float().reshape(-1, Cout)
+    st2 = stp.view(2 * rows, 64, 2)
+    ok &= report("   stats sum (rows x2 view)", st2[..., 0].sum(0), yf.sum(0), 1e-3)
+    ok &= report("   stats sumsq", st2[..., 1].sum(0), (yf * yf).sum(0), 1e-3)
+    dy2 = dyb.view(B, H, W // 2, 128)
+    sp = K.wgrad_splits((B, H, W // 2), dy2, K.A_PLAIN, col32.view(B, H, W // 2, 64))
+    partp = torch.empty(sp, 1, 128, 64, device=dev)
+    K.wgrad_gemm((B, H, W // 2), dy2, K.A_PLAIN, col32.view(B, H, W // 2, 64), partp)
+    gradp = torch.empty(Cout, Cin, 3, 3, device=dev)
+    K.wgrad_reduce(partp, sp, 1, 128, 64, 3, gradp, real_cin=Cin)
+    torch.cuda.synchronize()
+    ok &= report("wgrad first layer (paired pixels)", gradp, wref.grad, 1e-2)
     # first-layer forward through the im2col + plain GEMM
     w1 = (torch.randn(Cout, Cin, 3, 3, generator=g) / 5).to(dev)
     w1p = torch.empty(Cout, 64, dtype=torch.bfloat16, device=dev)

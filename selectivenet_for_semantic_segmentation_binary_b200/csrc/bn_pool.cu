@@ -102,6 +102,55 @@ pack_input_im2col_t_kernel(const float* __restrict__ x, bf16x8* __restrict__ out
   }
 }
 
+// Paired-pixel first layer (see sunet_pack_input_im2col32): 32 channels per pixel (9*CIN real, rest zero), so two
+// horizontally adjacent pixels share one 128-byte row.  One thread = one pixel: 9*CIN coalesced fp32 loads,
+// four 16-byte stores.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+pack_input_im2col32_kernel(const float* __restrict__ x, bf16x8* __restrict__ out, int B, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
+  static_assert(9 * CIN <= 32, "im2col32 holds at most 32 channels per pixel");
+  const uint32_t total = (uint32_t)B * H * W;
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+    const uint32_t rowi = pix / (uint32_t)W;
+    const int xx = (int)(pix - rowi * (uint32_t)W);
+    const int n = (int)(rowi / (uint32_t)H);
+    const int yy = (int)(rowi - (uint32_t)n * (uint32_t)H);
+    float f[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) f[k] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      const bool in = sy >= 0 && sy < H && sx >= 0 && sx < W;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+        if (in) f[tap * CIN + ci] = __ldg(x + (((long long)n * CIN + ci) * H + sy) * W + sx);
+    }
+    bf16x8* o = out + (size_t)pix * 4;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) o[g] = pack8(f + g * 8);
+  }
+}
+
+// weights of the paired-pixel first layer: wf[128][64]; row n < 64: [w_n (k = tap*cin+ci, 32 wide) | 0],
+// row 64 + n: [0 | w_n] — a plain GEMM over pixel PAIRS then yields both pixels' 64 outputs side by side.
+__device__ __forceinline__ float conv1_pair_weight(const float* __restrict__ w, int cin, int i) {
+  const int k = i & 63, nrow = i >> 6;
+  const int half = nrow >> 6, co = nrow & 63;
+  const int kk = k - 32 * half;
+  if (kk < 0 || kk >= 9 * cin) return 0.f;
+  const int tap = kk / cin, ci = kk - tap * cin;
+  return w[((long long)co * cin + ci) * 9 + tap];
+}
+__global__ void pack_conv1_pair_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int cin) {
+  pdl_wait();
+  pdl_trigger();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 64; i += gridDim.x * blockDim.x)
+    wf[i] = __float2bfloat16_rn(conv1_pair_weight(w, cin, i));
+}
+
 __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                     __nv_bfloat16* __restrict__ wd, int co_n, int ci_n) {
   pdl_wait();
@@ -212,6 +261,10 @@ pack_table_kernel(const sunet_pack_job* __restrict__ jobs) {
       }
       wf[i] = __float2bfloat16_rn(v);
     }
+  } else if (j.kind == 3) {     // first conv, paired-pixel form: a = 64 (cout), b = cin
+    __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 64; i += gridDim.x * blockDim.x)
+      wf[i] = __float2bfloat16_rn(conv1_pair_weight(j.w, j.b, i));
   } else {                      // ConvTranspose2d: a = cin, b = cout
     pack_tile<4, true>(j, tile);
     if (j.bias4)
@@ -882,6 +935,28 @@ extern "C" int sunet_pack_input_im2col(const float* x, void* out, int batch, int
     launch_k(pack_input_im2col_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, x, reinterpret_cast<bf16x8*>(out), batch, cin,
                                                                        height, width);
   return check_launch("pack_input_im2col");
+}
+
+extern "C" int sunet_pack_input_im2col32(const float* x, void* out, int batch, int cin, int height, int width,
+                                         sunet_stream_t stream_) {
+  if (!x || !out || batch <= 0 || (cin != 2 && cin != 3) || height <= 0 || width <= 0 || (width & 1))
+    return set_error(SUNET_ERR_INVALID, "pack_input_im2col32: bad arguments (cin=%d, width=%d)", cin, width);
+  const long long total = (long long)batch * height * width;
+  if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "pack_input_im2col32: tensor too large");
+  if (cin == 3)
+    launch_k(pack_input_im2col32_kernel<3>, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, x,
+             reinterpret_cast<bf16x8*>(out), batch, height, width);
+  else
+    launch_k(pack_input_im2col32_kernel<2>, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, x,
+             reinterpret_cast<bf16x8*>(out), batch, height, width);
+  return check_launch("pack_input_im2col32");
+}
+
+extern "C" int sunet_pack_conv1_pair_weights(const float* w, void* wf, int cout, int cin, sunet_stream_t stream_) {
+  if (!w || !wf || cout != 64 || cin <= 0 || cin * 9 > 32)
+    return set_error(SUNET_ERR_INVALID, "pack_conv1_pair_weights: needs cout = 64 and 9*cin <= 32");
+  launch_k(pack_conv1_pair_kernel, dim3(32), dim3(256), 0, STREAM, w, reinterpret_cast<__nv_bfloat16*>(wf), cin);
+  return check_launch("pack_conv1_pair_weights");
 }
 
 extern "C" int sunet_pack_conv3x3_weights(const float* w, void* wf, void* wd, int cout, int cin,

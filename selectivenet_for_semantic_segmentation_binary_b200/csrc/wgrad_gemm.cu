@@ -815,6 +815,25 @@ wgrad_reduce_first_kernel(const float* __restrict__ P, int splits, int Ca, int N
     grad[i] = s;
   }
 }
+// paired-pixel first layer: P[k][128][64] with A = (pixel parity, co), B = (pixel parity, 32-wide k);
+// grad[co][cin][tap] = sum_k P[k][co][tap*cin+ci] + P[k][64+co][32 + tap*cin+ci]   (the two diagonal blocks)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_first_pair_kernel(const float* __restrict__ P, int splits, int real_cin, float* __restrict__ grad,
+                               int total) {
+  pdl_wait();
+  pdl_trigger();
+  const int slab = 128 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9;
+    const int ci = (i / 9) % real_cin;
+    const int co = i / (9 * real_cin);
+    const int k = tap * real_cin + ci;
+    const int s0 = co * 64 + k, s1 = (64 + co) * 64 + 32 + k;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += P[(size_t)sp * slab + s0] + P[(size_t)sp * slab + s1];
+    grad[i] = s;
+  }
+}
 }  // namespace sunet
 
 extern "C" int sunet_wgrad_reduce(const float* partials, int splits, int taps, int a_channels, int b_channels,
@@ -826,6 +845,8 @@ extern "C" int sunet_wgrad_reduce(const float* partials, int splits, int taps, i
   if (layout == 0 && taps == 9) total = 9LL * a_channels * b_channels;
   else if (layout == 1 && taps == 4) total = 4LL * a_channels * b_channels;
   else if (layout == 2 && taps == 1 && real_cin > 0 && real_cin * 9 <= b_channels) total = 9LL * a_channels * real_cin;
+  else if (layout == 3 && taps == 1 && a_channels == 128 && b_channels == 64 && real_cin > 0 && real_cin * 9 <= 32)
+    total = 9LL * 64 * real_cin;
   else return set_error(SUNET_ERR_INVALID, "wgrad_reduce: layout %d / taps %d mismatch", layout, taps);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
@@ -835,6 +856,9 @@ extern "C" int sunet_wgrad_reduce(const float* partials, int splits, int taps, i
     launch_k(wgrad_reduce_taps_kernel<9>, dim3((int)blocks), dim3(256), 0, stream, partials, splits, ab, grad);
   else if (layout == 1)
     launch_k(wgrad_reduce_taps_kernel<4>, dim3((int)blocks), dim3(256), 0, stream, partials, splits, ab, grad);
+  else if (layout == 3)
+    launch_k(wgrad_reduce_first_pair_kernel, dim3((int)blocks), dim3(256), 0, stream, partials, splits, real_cin, grad,
+             (int)total);
   else
     launch_k(wgrad_reduce_first_kernel, dim3((int)blocks), dim3(256), 0, stream, partials, splits, a_channels, b_channels, real_cin,
                                                                grad, total);

@@ -101,7 +101,15 @@ class SUNetPlan:
         add("decoder_layer_1_1", 1, "conv", 64, 64)
         self.order = order
 
-        self.col = act(1, 64)                                   # im2col'ed input (9*in_ch real channels)
+        # First layer (Cin = 2 or 3), paired-pixel form: im2col to 32 channels per pixel, so a 128-byte row holds two
+        # adjacent pixels; a PLAIN GEMM over the (B, H, W/2) pair grid with block-diagonal weights [128][64] then
+        # writes both pixels' 64 outputs side by side = the NHWC output itself.  SUNET_FIRST_PAIR=0: 64-wide form.
+        self.first_pair = os.environ.get("SUNET_FIRST_PAIR", "1") != "0" and 9 * in_ch <= 32 and width % 2 == 0
+        if self.first_pair:
+            self.col = torch.empty(B, height, width, 32, dtype=bf, device=dev)
+            self.col2 = self.col.view(B, height, width // 2, 64)
+        else:
+            self.col = act(1, 64)                               # im2col'ed input (9*in_ch real channels)
         for ly in order:
             h, w = self.hw[ly.level]
             ly.y = act(ly.level, ly.cout)
@@ -109,7 +117,12 @@ class SUNetPlan:
             kdim = 64 if ly.kind == "first" else 9 * ly.cin
             ly.wf = torch.empty(ly.cout, kdim, dtype=bf, device=dev)
             ly.wd = None if ly.kind == "first" else torch.empty(ly.cin, 9 * ly.cout, dtype=bf, device=dev)
-            ly.stat_rows = K.conv_gemm_stat_rows(B, h, w, ly.cout, K.A_PLAIN if kind_first(ly) else K.A_CONV3X3)
+            if kind_first(ly) and self.first_pair:
+                ly.wf = torch.empty(128, 64, dtype=bf, device=dev)
+                # [rows][128][2] partials == [2*rows][64][2]: the finalize kernel just sees twice the rows
+                ly.stat_rows = 2 * K.conv_gemm_stat_rows(B, h, w // 2, 128, K.A_PLAIN)
+            else:
+                ly.stat_rows = K.conv_gemm_stat_rows(B, h, w, ly.cout, K.A_PLAIN if kind_first(ly) else K.A_CONV3X3)
             ly.stats = torch.zeros(ly.stat_rows, ly.cout, 2, device=dev)
             ly.scale, ly.shift, ly.mean, ly.invstd = (torch.empty(ly.cout, device=dev) for _ in range(4))
         self.pool = {L: act(L + 1, _CH[L]) for L in (1, 2, 3)}   # pooled encoder output of level L
@@ -182,7 +195,10 @@ class SUNetPlan:
         for ly in self.order:
             h, w = self.hw[ly.level]
             dy = self.gB[ly.level][0]
-            if ly.kind == "first":
+            if ly.kind == "first" and self.first_pair:
+                s = K.wgrad_splits((B, h, w // 2), dy.view(B, h, w // 2, 128), K.A_PLAIN, self.col2)
+                need = max(need, s * 128 * 64)
+            elif ly.kind == "first":
                 s = K.wgrad_splits((B, h, w), dy, K.A_PLAIN, self.col)
                 need = max(need, s * 1 * ly.cout * 64)
             elif ly.kind == "cat":
@@ -230,7 +246,7 @@ class SUNetPlan:
             for i, ly in enumerate(self.order):
                 w = params[f"{ly.name}.0.weight"]
                 assert w.dtype == torch.float32 and w.is_contiguous()
-                jobs[i].kind = 1 if ly.kind == "first" else 0
+                jobs[i].kind = (3 if self.first_pair else 1) if ly.kind == "first" else 0
                 jobs[i].a, jobs[i].b = ly.cout, ly.cin
                 jobs[i].w, jobs[i].wf = w.data_ptr(), ly.wf.data_ptr()
                 jobs[i].wd = None if ly.wd is None else ly.wd.data_ptr()
@@ -262,7 +278,9 @@ class SUNetPlan:
         h, w = self.hw[ly.level]
         grid = (B, h, w)
         stats = ly.stats if training else None
-        if ly.kind == "first":
+        if ly.kind == "first" and self.first_pair:
+            K.conv_gemm(K.A_PLAIN, (B, h, w // 2), self.col2, ly.wf, ly.y.view(B, h, w // 2, 128), stats=stats)
+        elif ly.kind == "first":
             K.conv_gemm(K.A_PLAIN, grid, self.col, ly.wf, ly.y, stats=stats)
         elif ly.kind == "cat":
             K.conv_gemm(K.A_CONV3X3, grid, self.up[ly.level], ly.wf, ly.y, src1=self._skip(ly.level), stats=stats)
@@ -291,7 +309,10 @@ class SUNetPlan:
         """x: fp32 NCHW on this plan's device.  Returns the plan-owned logits buffer [nheads, P]."""
         assert x.shape == (self.B, self.in_ch, self.H, self.W), (x.shape, (self.B, self.in_ch, self.H, self.W))
         self.pack_weights(params)
-        K.pack_input_im2col(x, self.col)
+        if self.first_pair:
+            K.pack_input_im2col32(x, self.col)
+        else:
+            K.pack_input_im2col(x, self.col)
         L = self.layers
         for name in ("encoder_layer_1_1", "encoder_layer_1_2", "encoder_layer_2_1", "encoder_layer_2_2",
                      "encoder_layer_3_1", "encoder_layer_3_2", "decoder_layer_4_2", "decoder_layer_4_1"):
@@ -353,7 +374,10 @@ class SUNetPlan:
         gw = grads[f"{n}.0.weight"]
 
         def wgrad():
-            if ly.kind == "first":
+            if ly.kind == "first" and self.first_pair:
+                s = K.wgrad_gemm((B, h, w // 2), dy.view(B, h, w // 2, 128), K.A_PLAIN, self.col2, self.partials)
+                K.wgrad_reduce(self.partials, s, 1, 128, 64, 3, gw, real_cin=ly.cin)
+            elif ly.kind == "first":
                 s = K.wgrad_gemm(grid, dy, K.A_PLAIN, self.col, self.partials)
                 K.wgrad_reduce(self.partials, s, 1, ly.cout, 64, 2, gw, real_cin=ly.cin)
             elif ly.kind == "cat":

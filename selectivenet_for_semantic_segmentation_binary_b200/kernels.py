@@ -155,6 +155,22 @@ def pack_conv3x3_weights(w, wf, wd=None) -> None:
                "sunet_pack_conv3x3_weights")
 
 
+def pack_input_im2col32(x: torch.Tensor, out: torch.Tensor) -> None:
+    """fp32 NCHW -> bf16 [B,H,W,32] (paired-pixel first layer)."""
+    B, Cin, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and tuple(out.shape) == (B, H, W, 32)
+    _lib.check(_lib.load().sunet_pack_input_im2col32(x.data_ptr(), out.data_ptr(), B, Cin, H, W, _stream()),
+               "sunet_pack_input_im2col32")
+
+
+def pack_conv1_pair_weights(w, wf) -> None:
+    co, ci = w.shape[0], w.shape[1]
+    assert wf.dtype == torch.bfloat16 and wf.is_contiguous() and tuple(wf.shape) == (128, 64)
+    _lib.check(_lib.load().sunet_pack_conv1_pair_weights(_f32(w), wf.data_ptr(), co, ci, _stream()),
+               "sunet_pack_conv1_pair_weights")
+
+
 def pack_conv1_weights(w, wf) -> None:
     co, ci = w.shape[0], w.shape[1]
     _lib.check(_lib.load().sunet_pack_conv1_weights(_f32(w), wf.data_ptr(), co, ci, _stream()),
