@@ -126,6 +126,50 @@ def g1_bnb(K):
     return ok
 
 
+def g1_bnb_convT(K):
+    """ConvTranspose backward-data GEMM (2x2 gather) with the fused BN-backward reduction."""
+    dev = "cuda"
+    ok = True
+    ws = K.new_workspace(dev)
+    for (B, h, w_, Cin, Cout) in [(2, 8, 8, 512, 256), (3, 16, 16, 256, 128), (5, 16, 32, 128, 64)]:
+        g = torch.Generator().manual_seed(B + Cin)
+        wT = (torch.randn(Cin, Cout, 2, 2, generator=g) / (2 * Cout ** 0.5)).to(dev)
+        bias = torch.zeros(Cout, device=dev)
+        wf = torch.empty(4 * Cout, Cin, dtype=torch.bfloat16, device=dev)
+        wd = torch.empty(Cin, 4 * Cout, dtype=torch.bfloat16, device=dev)
+        b4 = torch.empty(4 * Cout, device=dev)
+        K.pack_convT_weights(wT, bias, wf, wd, b4)
+        dup = nhwc(torch.randn(B, Cout, 2 * h, 2 * w_, generator=g).to(dev))
+        yb = nhwc((torch.randn(B, Cin, h, w_, generator=g) * 1.5 + 0.3).to(dev))
+        scale = (torch.rand(Cin, generator=g) + 0.5).to(dev)
+        shift = (torch.randn(Cin, generator=g) * 0.5).to(dev)
+        mean = (torch.randn(Cin, generator=g) * 0.3).to(dev)
+        invstd = (torch.rand(Cin, generator=g) + 0.5).to(dev)
+        dA = torch.full((B, h, w_, Cin), float("nan"), dtype=torch.bfloat16, device=dev)
+        dA0 = torch.full_like(dA, float("nan"))
+        if not K.conv_gemm_bnb_supported(K.A_GATHER2X2, (B, h, w_), dup, wd, dA):
+            print(f"   convT bnb unsupported for {Cin}->{Cout}: skipped")
+            continue
+        rows = K.conv_gemm_stat_rows(B, h, w_, Cin, K.A_GATHER2X2)
+        st = torch.full((rows, Cin, 2), float("nan"), device=dev)
+        K.conv_gemm(K.A_GATHER2X2, (B, h, w_), dup, wd, dA, stats=st, bnb=(yb, scale, shift, mean, invstd))
+        K.conv_gemm(K.A_GATHER2X2, (B, h, w_), dup, wd, dA0)
+        torch.cuda.synchronize()
+        tag = f"convT-dgrad bnb B{B} {h}x{w_} {Cin}<-{Cout}"
+        same = bool(torch.equal(dA, dA0))
+        print(f"  [{'OK ' if same else 'BAD'}] {tag}: dA identical to the unfused launch")
+        ok &= same
+        dg1, db1, dg2, db2 = (torch.empty(Cin, device=dev) for _ in range(4))
+        dy1, dy2 = torch.empty_like(yb), torch.empty_like(yb)
+        K.bn_bwd_apply(dA, yb, scale, shift, mean, invstd, st, rows, dg1, db1, dy1, ws)
+        K.bn_relu_pool_bwd(dA0, None, yb, scale, shift, mean, invstd, scale, dg2, db2, dy2, ws)
+        torch.cuda.synchronize()
+        ok &= report(f"   {tag} dgamma", dg1, dg2, 1e-4)
+        ok &= report(f"   {tag} dbeta", db1, db2, 1e-4)
+        ok &= report(f"   {tag} dy", dy1.float(), dy2.float(), 4e-3)
+    return ok
+
+
 def g1_plain(K):
     dev = "cuda"
     ok = True
@@ -525,7 +569,7 @@ def swizzle_exp(K):
     return True
 
 
-GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g1_bnb": g1_bnb, "g2_wgrad": g2_wgrad,
+GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g1_bnb": g1_bnb, "g1_bnb_convT": g1_bnb_convT, "g2_wgrad": g2_wgrad,
           "ew_bn": ew_bn, "ew_heads_loss": ew_heads_loss}
 
 

@@ -38,44 +38,55 @@ struct ConvGemmParams {
   const float* bias;
   float* stats;     // [gridDim.x / n_tiles][n_total][2] or nullptr
   int n_total;
+  // BNB: fused BatchNorm-backward reduction (see conv3_halo2.cu); NHWC store only
+  const float* bnb_scale;
+  const float* bnb_shift;
+  const float* bnb_mean;
+  const float* bnb_invstd;
   int dbg_shift, dbg_boff;  // SUNET_DBG_SHIFT / SUNET_DBG_BOFF: descriptor-swizzle experiment (scripts/gpu_probe.py)
 };
 
-template <int BN>
+template <int BN, bool BNB = false>
 struct Cfg {
   // KSP = 64-wide K steps per pipeline stage.  The narrow tiles finish a K step in 128 (BN=64) or 256
   // (BN=128) tensor-core cycles, which is less than one mbarrier round trip of the single issuing thread;
   // two K steps per stage halve the number of round trips.
   static constexpr int KSP = (BN == 256) ? 1 : 2;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  // BNB: two 16 KB slots for y tiles are paid for with one pipeline stage
+  static constexpr int STAGES = BNB ? ((BN == 256) ? 3 : 2) : ((BN == 256) ? 4 : (BN == 128 ? 3 : 4));
+  static constexpr int Y_SLOTS = BNB ? 2 : 0;
   static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 bf16
   static constexpr int B_BYTES = BN * 128;       // BN rows x 64 bf16
   static constexpr int STG_BYTES = 128 * 128;    // one 64-column output chunk
-  static constexpr int SMEM = STAGES * KSP * (A_BYTES + B_BYTES) + 2 * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM =
+      STAGES * KSP * (A_BYTES + B_BYTES) + (2 + Y_SLOTS) * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
 constexpr int kThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 
-template <int BN>
+template <int BN, bool BNB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
-                 const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap mapY, const ConvGemmParams p) {
   pdl_wait();
   pdl_trigger();
-  using C = Cfg<BN>;
+  using C = Cfg<BN, BNB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + C::STAGES * C::KSP * C::A_BYTES;
   uint8_t* sStg = sB + C::STAGES * C::KSP * C::B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * C::STG_BYTES);
+  uint8_t* sY = sStg + 2 * C::STG_BYTES;          // BNB: 2 slots of y tiles (same box / swizzle as mapD)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + C::Y_SLOTS * C::STG_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]
   uint64_t* tfull_bar = bars + 2 * C::STAGES;     // [2]
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* yfull = bars + 2 * C::STAGES + 4;     // [2], BNB only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,11 +99,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&yfull[i], 1);
     }
     fence_barrier_init();
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapB);
     tma_prefetch_desc(&mapD);
+    if (BNB) tma_prefetch_desc(&mapY);
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before_sync();
@@ -207,6 +220,52 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #pragma unroll
     for (int q = 0; q < NCHUNK; ++q) ssum[q][0] = ssum[q][1] = ssq[q][0] = ssq[q][1] = 0.f;
 
+    // BNB (fused BN-backward reduction, as in conv3_halo2.cu): this thread's two columns of every chunk, and the
+    // y-tile pipeline driven by the issuer thread (chunk k of this CTA = tile k / NCHUNK, channel chunk k % NCHUNK;
+    // slot k & 1; loads one chunk ahead, L2 prefetches four more)
+    float csc[NCHUNK][2], csh[NCHUNK][2], cmu[NCHUNK][2];
+    if (BNB) {
+#pragma unroll
+      for (int q = 0; q < NCHUNK; ++q) {
+        const int c = n_tile * BN + q * 64 + lane * 2;
+        csc[q][0] = __ldg(p.bnb_scale + c);
+        csc[q][1] = __ldg(p.bnb_scale + c + 1);
+        csh[q][0] = __ldg(p.bnb_shift + c);
+        csh[q][1] = __ldg(p.bnb_shift + c + 1);
+        cmu[q][0] = __ldg(p.bnb_mean + c);
+        cmu[q][1] = __ldg(p.bnb_mean + c + 1);
+      }
+    }
+    constexpr int kPfAhead = 4;
+    uint32_t y_issued = 0, y_prefetched = 0;
+    const uint32_t my_tiles = (m_first < p.m_tiles) ? (uint32_t)((p.m_tiles - 1 - m_first) / m_step + 1) : 0u;
+    const uint32_t y_total = my_tiles * NCHUNK;
+    auto y_coords = [&](uint32_t k, int& c0, int& xx, int& yy, int& nn) {
+      const int mt_ = m_first + (int)(k / NCHUNK) * m_step;
+      c0 = n_tile * BN + (int)(k % NCHUNK) * 64;
+      xx = (mt_ % p.tiles_x) * p.tw;
+      yy = ((mt_ / p.tiles_x) % p.tiles_y) * p.th;
+      nn = (mt_ / (p.tiles_x * p.tiles_y)) * p.nb;
+    };
+    auto y_pump = [&](uint32_t upto) {
+      while (y_issued < upto && y_issued < y_total) {
+        int c0, xx, yy, nn;
+        y_coords(y_issued, c0, xx, yy, nn);
+        uint64_t* bar = &yfull[y_issued & 1];
+        mbar_arrive_expect_tx(bar, C::STG_BYTES);
+        tma_load_5d(sY + (y_issued & 1) * C::STG_BYTES, &mapY, bar, c0, xx, yy, nn, 0);
+        ++y_issued;
+      }
+      if (y_prefetched < y_issued) y_prefetched = y_issued;
+      while (y_prefetched < y_issued + kPfAhead && y_prefetched < y_total) {
+        int c0, xx, yy, nn;
+        y_coords(y_prefetched, c0, xx, yy, nn);
+        tma_prefetch_5d(&mapY, c0, xx, yy, nn, 0);
+        ++y_prefetched;
+      }
+    };
+    if (BNB && issuer) y_pump(2);
+
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int mt = m_first; mt < p.m_tiles; mt += m_step, ++it) {
@@ -255,8 +314,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             tma_store_5d(&mapD, stg, ncol0, x0, y0, n0, 0);
           }
           tma_store_commit();
+          if (BNB) y_pump(chunk_ctr + 2);        // everyone is past the stats loop of chunk_ctr-1: its slot is free
         }
-        if (p.stats != nullptr) {
+        if (BNB) {
+          mbar_wait(&yfull[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
+          const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
+          const uint32_t* ywords = reinterpret_cast<const uint32_t*>(sY + (chunk_ctr & 1) * C::STG_BYTES);
+          const float sc0 = csc[q][0], sc1 = csc[q][1], sh0 = csh[q][0], sh1 = csh[q][1];
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;     // sum g, sum g*y (mean folded in after the loop)
+#pragma unroll 16
+          for (int r = 0; r < 32; ++r) {
+            const int rr = quad * 32 + r;
+            const int idx = rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3));
+            const uint32_t w = words[idx], yw = ywords[idx];
+            const float ya = bf16lo(yw), yb = bf16hi(yw);
+            const float ga = fmaf(ya, sc0, sh0) > 0.f ? bf16lo(w) : 0.f;
+            const float gb = fmaf(yb, sc1, sh1) > 0.f ? bf16hi(w) : 0.f;
+            s0 += ga;
+            s1 += gb;
+            q0 = fmaf(ga, ya, q0);
+            q1 = fmaf(gb, yb, q1);
+          }
+          ssum[q][0] += s0;
+          ssum[q][1] += s1;
+          ssq[q][0] += fmaf(-cmu[q][0], s0, q0);
+          ssq[q][1] += fmaf(-cmu[q][1], s1, q1);
+        } else if (p.stats != nullptr) {
           // Column statistics over this warp's own 32 rows (rows it wrote itself -> the
           // named barrier above already ordered the writes).  Lane = channel pair.
           const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
@@ -299,7 +382,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int t = threadIdx.x - 64;
       float* dst = p.stats + (static_cast<size_t>(m_first) * p.n_total + n_tile * BN) * 2;
       for (int i = t; i < BN * 2; i += 128) {
-        dst[i] = red[i] + red[BN * 2 + i] + red[2 * BN * 2 + i] + red[3 * BN * 2 + i];
+        float v = red[i] + red[BN * 2 + i] + red[2 * BN * 2 + i] + red[3 * BN * 2 + i];
+        if (BNB && (i & 1)) v *= __ldg(p.bnb_invstd + n_tile * BN + (i >> 1));     // sum g*(y-mean) -> sum g*xhat
+        dst[i] = v;
       }
     }
   }
@@ -379,18 +464,18 @@ static int conv_gemm_grid(int m_tiles, int n_tiles) {
   return slots * n_tiles;
 }
 
-template <int BN>
+template <int BN, bool BNB>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d,
-                  const ConvGemmParams& p, int grid, cudaStream_t stream) {
+                  const CUtensorMap& y, const ConvGemmParams& p, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    int e = check_cuda(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            Cfg<BN>::SMEM),
+    int e = check_cuda(cudaFuncSetAttribute(conv_gemm_kernel<BN, BNB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg<BN, BNB>::SMEM),
                        "cudaFuncSetAttribute(conv_gemm)");
     if (e) return e;
     attr_set = true;
   }
-  launch_k(conv_gemm_kernel<BN>, dim3(grid), dim3(kThreads), Cfg<BN>::SMEM, stream, a0, a1, b, d, p);
+  launch_k(conv_gemm_kernel<BN, BNB>, dim3(grid), dim3(kThreads), Cfg<BN, BNB>::SMEM, stream, a0, a1, b, d, y, p);
   return check_launch("conv_gemm_kernel");
 }
 
@@ -421,7 +506,9 @@ extern "C" int sunet_conv_gemm_stat_rows(const sunet_conv_gemm_args* a) {
 
 extern "C" int sunet_conv_gemm_bnb_supported(const sunet_conv_gemm_args* a) {
   if (!a || a->batch <= 0 || a->height <= 0 || a->width <= 0 || a->n_total <= 0 || a->n_total % 64) return 0;
-  return conv3_halo2_eligible(a) ? 1 : 0;
+  if (conv3_halo2_eligible(a)) return 1;
+  // the per-tap kernel implements it for its 128- and 256-wide tiles with a plain NHWC store (ConvT backward-data)
+  return (!conv3_halo_eligible(a) && a->d_mode == SUNET_D_NHWC && a->bias == nullptr && a->n_total % 128 == 0) ? 1 : 0;
 }
 
 extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t stream_) {
@@ -454,9 +541,12 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
     return set_error(SUNET_ERR_INVALID, "conv_gemm: scatter store needs n_total = 4 x (multiple of 64)");
 
   if (conv3_halo2_eligible(a)) return conv3_halo2_launch(a, stream);
-  if (a->bnb_y != nullptr)
+  const bool bnb = a->bnb_y != nullptr;
+  if (bnb && !sunet_conv_gemm_bnb_supported(a))
     return set_error(SUNET_ERR_INVALID, "conv_gemm: the fused BN-backward epilogue (bnb_y) is not available for this "
                                         "shape/mode; check sunet_conv_gemm_bnb_supported()");
+  if (bnb && (!a->stats || !a->bnb_scale || !a->bnb_shift || !a->bnb_mean || !a->bnb_invstd))
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: bnb_y needs stats and the four bnb_* vectors");
   if (conv3_halo_eligible(a)) return conv3_halo_launch(a, stream);
 
   TileGeom g = tile_geom(B, H, W, 128);
@@ -465,7 +555,7 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
   const int bn = pick_bn(a->n_total);
   const int n_tiles = a->n_total / bn;
 
-  CUtensorMap mA0, mA1, mB, mD;
+  CUtensorMap mA0, mA1, mB, mD, mY;
   int e;
   const int gs_load = (a->a_mode == SUNET_A_GATHER2X2);
   if ((e = make_act_map(&mA0, a->src0, gs_load, a->src0_channels, a->src0_pix_stride, B, H, W, g, 128))) return e;
@@ -481,6 +571,13 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
   const int dst_c = gs_store ? a->n_total / 4 : a->n_total;
   if (a->dst_pix_stride < dst_c) return set_error(SUNET_ERR_INVALID, "conv_gemm: dst_pix_stride < channels");
   if ((e = make_act_map(&mD, a->dst, gs_store, dst_c, a->dst_pix_stride, B, H, W, g, 128))) return e;
+  if (bnb) {
+    if (a->bnb_y_pix_stride < a->n_total || (a->bnb_y_pix_stride % 8))
+      return set_error(SUNET_ERR_INVALID, "conv_gemm: bad bnb_y_pix_stride %d", a->bnb_y_pix_stride);
+    if ((e = make_act_map(&mY, a->bnb_y, 0, a->n_total, a->bnb_y_pix_stride, B, H, W, g, 128))) return e;
+  } else {
+    mY = mD;
+  }
 
   ConvGemmParams p;
   p.gs_load = gs_load;
@@ -497,6 +594,10 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
   p.bias = a->bias;
   p.stats = a->stats;
   p.n_total = a->n_total;
+  p.bnb_scale = a->bnb_scale;
+  p.bnb_shift = a->bnb_shift;
+  p.bnb_mean = a->bnb_mean;
+  p.bnb_invstd = a->bnb_invstd;
   {
     const char* s = getenv("SUNET_DBG_SHIFT");
     const char* b = getenv("SUNET_DBG_BOFF");
@@ -504,9 +605,11 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
     p.dbg_boff = b ? atoi(b) : 0;
   }
   const int grid = conv_gemm_grid(g.m_tiles, n_tiles);
+  if (bnb) return (bn == 256) ? launch<256, true>(mA0, mA1, mB, mD, mY, p, grid, stream)
+                              : launch<128, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
   switch (bn) {
-    case 256: return launch<256>(mA0, mA1, mB, mD, p, grid, stream);
-    case 128: return launch<128>(mA0, mA1, mB, mD, p, grid, stream);
-    default: return launch<64>(mA0, mA1, mB, mD, p, grid, stream);
+    case 256: return launch<256, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    case 128: return launch<128, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    default: return launch<64, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
   }
 }

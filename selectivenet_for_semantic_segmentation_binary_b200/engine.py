@@ -174,6 +174,17 @@ class SUNetPlan:
                     cl.bnb_rows = rows
                     cl.bnb_stats = torch.zeros(rows, cl.cout, 2, device=dev)
                     self.bnb_of[pn] = cl
+        # ... and the ConvTranspose backward-data GEMM of level L does the same for the block that feeds the ConvT
+        self.bnb_convT: Dict[int, _Layer] = {}
+        if os.environ.get("SUNET_FUSE_BNB", "1") != "0" and os.environ.get("SUNET_FUSE_BNB_CONVT", "1") != "0":
+            for L in (1, 2, 3):
+                cl = self.layers[self._convT_input(L)]
+                hh, ww = self.hw[L + 1]
+                dup = self.dcat[L][..., :_CH[L]]
+                if K.conv_gemm_bnb_supported(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[L]["wd"], self.gA[L + 1]):
+                    cl.bnb_rows = K.conv_gemm_stat_rows(B, hh, ww, cl.cout, K.A_GATHER2X2)
+                    cl.bnb_stats = torch.zeros(cl.bnb_rows, cl.cout, 2, device=dev)
+                    self.bnb_convT[L] = cl
         # the last block: heads_bwd recomputes relu(bn(y)) from y and emits the BN-backward reduction rows, so the
         # activation of decoder_layer_1_1 is never stored (SUNET_FUSE_HEADS_BN=0 restores the two-pass form)
         self.fuse_heads_bn = os.environ.get("SUNET_FUSE_HEADS_BN", "1") != "0"
@@ -433,12 +444,12 @@ class SUNetPlan:
             K.heads_bwd(dlogits, last.a, [params[f"{h}.weight"] for h in heads], self.gA[1],
                         [grads[f"{h}.weight"] for h in heads], [grads[f"{h}.bias"] for h in heads], self.ws)
         dA = self.gA[1]
+        up_fused = self.fuse_heads_bn
         for lvl, (n2, n1) in ((1, ("decoder_layer_1_2", "decoder_layer_1_1")),
                               (2, ("decoder_layer_2_2", "decoder_layer_2_1")),
                               (3, ("decoder_layer_3_2", "decoder_layer_3_1"))):
             c = _CH[lvl]
-            f = self._cbr_bwd(L[n1], dA, None, params, grads, self.gA[lvl],
-                              fused_reduce=(lvl == 1 and self.fuse_heads_bn))
+            f = self._cbr_bwd(L[n1], dA, None, params, grads, self.gA[lvl], fused_reduce=up_fused)
             st, rows = self.dcat_stats[lvl]
             self._cbr_bwd(L[n2], self.gA[lvl], None, params, grads, self.dcat[lvl], st, fused_reduce=f)
             # ConvTranspose backward: bias (column sums of d_up), weight, input
@@ -450,16 +461,19 @@ class SUNetPlan:
                 s = K.wgrad_gemm((B, hh, ww), xin, K.A_GATHER2X2, dup, self.partials)
                 K.wgrad_reduce(self.partials, s, 4, _CH[lvl + 1], c, 1, grads[f"unpool{lvl}.weight"])
 
+            cl = self.bnb_convT.get(lvl)
+            kw = {} if cl is None else dict(stats=cl.bnb_stats, bnb=(cl.y, cl.scale, cl.shift, cl.mean, cl.invstd))
             if self.wgrad_after_dgrad:
-                K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1])
+                K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1], **kw)
                 self._on_side(wgrad_t)
             else:
                 self._on_side(wgrad_t)
-                K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1])
+                K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1], **kw)
             dA = self.gA[lvl + 1]
+            up_fused = cl is not None        # the next block's reduction rows are already written
             done(f"dec{lvl}")
         # bottleneck
-        f = self._cbr_bwd(L["decoder_layer_4_1"], self.gA[4], None, params, grads, self.gA[4])
+        f = self._cbr_bwd(L["decoder_layer_4_1"], self.gA[4], None, params, grads, self.gA[4], fused_reduce=up_fused)
         self._cbr_bwd(L["decoder_layer_4_2"], self.gA[4], None, params, grads, self.dpool[3], fused_reduce=f)
         done("dec4")
         # encoder, deepest first; skip gradient = second half of dcat, pooled gradient = dpool
