@@ -65,6 +65,24 @@ def main():
             rows.append((f"bn_bwd pool (r+a)   {H}x{H}x{C}", 11 * n, t))
             del pooled, dP, dcat
         del y, a, dA, dy
+    # heads: forward (y -> logits, activation not stored) and backward (y, dlogits -> dA + BN reduction rows)
+    P = B * 256 * 256
+    y = (torch.randn(B, 256, 256, 64, device=dev) * 1.5 + 0.3).to(bf)
+    dA = torch.empty_like(y)
+    sc, sh, mu, isd = (torch.rand(64, device=dev) + 0.5 for _ in range(4))
+    wts = [torch.randn(1, 64, 1, 1, device=dev) for _ in range(3)]
+    bss = [torch.randn(1, device=dev) for _ in range(3)]
+    logits = torch.empty(3, P, device=dev)
+    dl = torch.randn(3, P, device=dev)
+    dws, dbs = [torch.empty_like(w) for w in wts], [torch.empty_like(b) for b in bss]
+    part = torch.empty(K.heads_bwd_bn_rows(P), 64, 2, device=dev)
+    t = timeit(lambda: K.bn_relu_heads(y, sc, sh, None, wts, bss, logits))
+    rows.append(("bn_relu_heads (no a)  256x256x64", 2 * y.numel() + 12 * P, t))
+    t = timeit(lambda: K.heads_bwd_bn(dl, y, sc, sh, mu, isd, wts, dA, dws, dbs, part, ws))
+    rows.append(("heads_bwd_bn          256x256x64", 4 * y.numel() + 12 * P, t))
+    a = torch.empty_like(y)
+    t = timeit(lambda: K.heads_bwd(dl, a, wts, dA, dws, dbs, ws))
+    rows.append(("heads_bwd (stored a)  256x256x64", 4 * y.numel() + 12 * P, t))
     for name, nbytes, t in rows:
         gbs = nbytes / t / 1e6
         print(f"{name:34s} {t:8.4f} ms  {gbs:8.1f} GB/s  {100 * gbs / peak:5.1f}% of {peak:.0f}", flush=True)

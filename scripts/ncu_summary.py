@@ -8,11 +8,11 @@ KEYS = [
     ("gpu__time_duration.sum", "time"),
     ("dram__bytes_read.sum", "dram rd"),
     ("dram__bytes_write.sum", "dram wr"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
-    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe %"),
-    ("sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", "bf16 mma ops %"),
-    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem wavefronts %"),
+    ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe % (TPC)"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem->tensor wavefronts %"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem lsu wavefronts %"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
     ("launch__registers_per_thread", "regs"),

@@ -50,6 +50,7 @@ def bn(B, H, W, C, bwd, iters=3):
 
 MODES = {
     "conv64": lambda: conv(128, 256, 256, 64, 64),
+    "conv512": lambda: conv(128, 32, 32, 512, 512),
     "conv128": lambda: conv(128, 128, 128, 128, 128),
     "conv256": lambda: conv(128, 64, 64, 256, 256),
     "wgrad128": lambda: wgrad(128, 128, 128, 128, 128),

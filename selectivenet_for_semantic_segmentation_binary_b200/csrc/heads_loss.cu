@@ -166,6 +166,13 @@ struct HeadBN {
   float* partials;     // [gridDim.x][64][2]
 };
 
+// shared-memory load the compiler may not hoist out of the pixel loop (it would turn back into 48 registers)
+__device__ __forceinline__ float2 lds_f32x2(const float* p) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
+  return v;
+}
+
 template <bool BN>
 __global__ void __launch_bounds__(256, 2)
 heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
@@ -173,30 +180,28 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
   pdl_wait();
   pdl_trigger();
   __shared__ float red[256][28];
+  // per-channel constants live in shared memory and are re-read per pixel (six 16-byte broadcast loads): keeping
+  // 48 of them in registers next to the 40 accumulators left room for only two pixels in flight per thread
+  __shared__ __align__(16) float s_w[3][64];
+  __shared__ __align__(16) float s_bn[3][64];      // scale, shift, mean
   const int sub = threadIdx.x & 7;
-  float w[3][8];
-#pragma unroll
-  for (int h = 0; h < 3; ++h)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) w[h][j] = (h < nheads) ? __ldg(hw.w[h] + sub * 8 + j) : 0.f;
-  float sc[8], sh[8], mu[8], sg[8], sgy[8];
-  if (BN) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = __ldg(bn.scale + sub * 8 + j);
-      sh[j] = __ldg(bn.shift + sub * 8 + j);
-      mu[j] = __ldg(bn.mean + sub * 8 + j);
-      sg[j] = sgy[j] = 0.f;
-    }
+  if (threadIdx.x < 192) {
+    const int h = threadIdx.x >> 6, c = threadIdx.x & 63;
+    s_w[h][c] = (h < nheads) ? __ldg(hw.w[h] + c) : 0.f;
+    if (BN) s_bn[h][c] = __ldg((h == 0 ? bn.scale : (h == 1 ? bn.shift : bn.mean)) + c);
   }
+  __syncthreads();
+  float sg[8], sgy[8];
   float dw[3][8];
   float db[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sg[j] = sgy[j] = 0.f;
 #pragma unroll
   for (int h = 0; h < 3; ++h)
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw[h][j] = 0.f;
   // U pixels per thread per trip: all loads are issued before any is consumed
-  constexpr int U = BN ? 2 : 4;
+  constexpr int U = 4;
   const long long ppb = (long long)(blockDim.x >> 3);                 // pixels per block per sub-trip
   for (long long p0 = blockIdx.x * ppb * U + (threadIdx.x >> 3); p0 < P; p0 += (long long)gridDim.x * ppb * U) {
     float g[U][3];
@@ -214,47 +219,44 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
     for (int u = 0; u < U; ++u) {
       const long long p = p0 + u * ppb;
       if (p < P) {
-        float av[8], yv[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          av[2 * i] = bf16lo(v[u].w[i]);
-          av[2 * i + 1] = bf16hi(v[u].w[i]);
-        }
-        if (BN) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            yv[j] = av[j];
-            av[j] = fmaxf(fmaf(yv[j], sc[j], sh[j]), 0.f);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {       // the bf16 rounding bn_relu_heads applied before the dots
-            const uint32_t r = pack_bf16x2(av[2 * i], av[2 * i + 1]);
-            av[2 * i] = bf16lo(r);
-            av[2 * i + 1] = bf16hi(r);
-          }
-        }
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = g[u][0] * w[0][j] + g[u][1] * w[1][j] + g[u][2] * w[2][j];
-#pragma unroll
-          for (int h = 0; h < 3; ++h) dw[h][j] = fmaf(g[u][h], av[j], dw[h][j]);
-        }
         bf16x8 ov;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ov.w[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
-        *reinterpret_cast<bf16x8*>(dA + p * das + sub * 8) = ov;
-        if (BN) {
+        for (int i = 0; i < 4; ++i) {           // channel pair i of this thread's 8 channels
+          const int c = sub * 8 + 2 * i;
+          const float2 w0 = lds_f32x2(&s_w[0][c]);
+          const float2 w1 = lds_f32x2(&s_w[1][c]);
+          const float2 w2 = lds_f32x2(&s_w[2][c]);
+          float a0 = bf16lo(v[u].w[i]), a1 = bf16hi(v[u].w[i]);
+          float y0 = 0.f, y1 = 0.f;
+          if (BN) {
+            const float2 sc = lds_f32x2(&s_bn[0][c]);
+            const float2 sh = lds_f32x2(&s_bn[1][c]);
+            y0 = a0;
+            y1 = a1;
+            // the activation bn_relu_heads fed to the heads: relu(bn(y)) rounded to bf16
+            const uint32_t r = pack_bf16x2(fmaxf(fmaf(y0, sc.x, sh.x), 0.f), fmaxf(fmaf(y1, sc.y, sh.y), 0.f));
+            a0 = bf16lo(r);
+            a1 = bf16hi(r);
+          }
+          const float o0 = g[u][0] * w0.x + g[u][1] * w1.x + g[u][2] * w2.x;
+          const float o1 = g[u][0] * w0.y + g[u][1] * w1.y + g[u][2] * w2.y;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float g0 = av[2 * i] > 0.f ? bf16lo(ov.w[i]) : 0.f;
-            const float g1 = av[2 * i + 1] > 0.f ? bf16hi(ov.w[i]) : 0.f;
+          for (int h = 0; h < 3; ++h) {
+            dw[h][2 * i] = fmaf(g[u][h], a0, dw[h][2 * i]);
+            dw[h][2 * i + 1] = fmaf(g[u][h], a1, dw[h][2 * i + 1]);
+          }
+          ov.w[i] = pack_bf16x2(o0, o1);
+          if (BN) {
+            const float2 mu = lds_f32x2(&s_bn[2][c]);
+            const float g0 = a0 > 0.f ? bf16lo(ov.w[i]) : 0.f;
+            const float g1 = a1 > 0.f ? bf16hi(ov.w[i]) : 0.f;
             sg[2 * i] += g0;
             sg[2 * i + 1] += g1;
-            sgy[2 * i] = fmaf(g0, yv[2 * i] - mu[2 * i], sgy[2 * i]);
-            sgy[2 * i + 1] = fmaf(g1, yv[2 * i + 1] - mu[2 * i + 1], sgy[2 * i + 1]);
+            sgy[2 * i] = fmaf(g0, y0 - mu.x, sgy[2 * i]);
+            sgy[2 * i + 1] = fmaf(g1, y1 - mu.y, sgy[2 * i + 1]);
           }
         }
+        *reinterpret_cast<bf16x8*>(dA + p * das + sub * 8) = ov;
         if (sub == 0) {
 #pragma unroll
           for (int h = 0; h < 3; ++h) db[h] += g[u][h];
@@ -515,7 +517,10 @@ extern "C" int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float*
   return check_launch("bn_relu_heads");
 }
 
-static int heads_bwd_blocks(long long pixels, bool bn) { return grid_for(pixels * 8, 256, bn ? 2 : 4); }
+static int heads_bwd_blocks(long long pixels, bool bn) {
+  (void)bn;
+  return grid_for(pixels * 8, 256, 4);
+}
 
 extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,
                                const float* w2, int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0,

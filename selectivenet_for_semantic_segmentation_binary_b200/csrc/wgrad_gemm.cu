@@ -775,25 +775,24 @@ namespace sunet {
 // 4-byte writes touch each output line TAPS times but the output is 1/splits of the traffic.
 template <int TAPS>
 __global__ void __launch_bounds__(256)
-wgrad_reduce_taps_kernel(const float* __restrict__ P, int splits, long long ab, float* __restrict__ grad) {
+wgrad_reduce_taps_kernel(const float* __restrict__ P, int splits, int ab, float* __restrict__ grad) {
   pdl_wait();
   pdl_trigger();
-  const long long slab = TAPS * ab;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < slab;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(i / ab);
-    const long long j = i - tap * ab;
+  const int slab = TAPS * ab;                     // < 2^31 (checked by the launcher)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < slab; i += gridDim.x * blockDim.x) {
+    const int tap = i / ab;
+    const int j = i - tap * ab;
     const float* src = P + i;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] = 0.f;
     int k = 0;
-    for (; k + 4 <= splits; k += 4) {
-      s0 += src[(k + 0) * slab];
-      s1 += src[(k + 1) * slab];
-      s2 += src[(k + 2) * slab];
-      s3 += src[(k + 3) * slab];
+    for (; k + 8 <= splits; k += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += src[(size_t)(k + u) * slab];
     }
-    for (; k < splits; ++k) s0 += src[k * slab];
-    grad[j * TAPS + tap] = (s0 + s1) + (s2 + s3);
+    for (; k < splits; ++k) s[0] += src[(size_t)k * slab];
+    grad[(size_t)j * TAPS + tap] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   }
 }
 
@@ -851,7 +850,8 @@ extern "C" int sunet_wgrad_reduce(const float* partials, int splits, int taps, i
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  const long long ab = (long long)a_channels * b_channels;
+  if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "wgrad_reduce: tensor too large");
+  const int ab = a_channels * b_channels;
   if (layout == 0)
     launch_k(wgrad_reduce_taps_kernel<9>, dim3((int)blocks), dim3(256), 0, stream, partials, splits, ab, grad);
   else if (layout == 1)
