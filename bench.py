@@ -290,6 +290,12 @@ def run_ours(args):
             "last_losses": [float(v) for v in res_host.tolist()] if res_host is not None else None,
         }
         if roof is not None:
+            tj = os.path.join(ROOT, "profiles", "r01", "roofline_traffic.json")
+            if os.path.exists(tj):               # DRAM bytes per launch from the committed ncu launch list
+                with open(tj) as f:
+                    t = json.load(f)
+                roof["traffic"] = t["dram_bytes_per_launch"]
+                roof["traffic_source"] = t["source"]
             roof["peak"] = pk["bf16"]
             roof["frac"] = roof["achieved"] / pk["bf16"]
             roof["peak_source"] = pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)"

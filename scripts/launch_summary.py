@@ -36,5 +36,35 @@ def main():
               f"{b / t:8.1f}")
 
 
+def traffic_json(path, out):
+    """Average DRAM bytes per launch of the G1 family (conv3_halo2_kernel*, conv_gemm_kernel*) -> bench.py's
+    roofline.traffic.  usage: python scripts/launch_summary.py launches.csv --traffic-json out.json"""
+    import json
+    rows = list(csv.reader(open(path, errors="replace")))
+    hdr = None
+    tot, n, t = 0.0, 0, 0.0
+    for r in rows:
+        if hdr is None:
+            if "Kernel Name" in r:
+                hdr = r
+                ki, vi, mi = r.index("Kernel Name"), r.index("Metric Value"), r.index("Metric Name")
+            continue
+        if len(r) <= vi or not ("conv3_halo" in r[ki] or "conv_gemm_kernel" in r[ki]):
+            continue
+        v = float(r[vi].replace(",", ""))
+        if r[mi].startswith("dram__bytes"):
+            tot += v
+        elif r[mi].startswith("gpu__time"):
+            n += 1
+            t += v
+    json.dump({"kernel_family": "G1 (conv3_halo2_kernel*, conv_gemm_kernel*)", "launches": n,
+               "dram_bytes_per_launch": tot / n, "avg_launch_ns_under_ncu": t / n,
+               "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
+                         "(scripts/ncu_launches.sh), file " + path.split("/")[-1]}, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic-json":
+        traffic_json(sys.argv[1], sys.argv[3])
+    else:
+        main()
