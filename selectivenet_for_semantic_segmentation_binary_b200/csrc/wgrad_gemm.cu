@@ -53,6 +53,37 @@ struct WgradParams {
 };
 constexpr int MAX_STAGES = 12;
 
+// MMA issue for one pipeline stage, taps unrolled at compile time.  The generic (runtime T) loop spent ~25 SASS
+// instructions of the single issuing thread per UTCHMMA — more than the 64 tensor-core cycles an N=128 MMA takes,
+// which capped these kernels at ~67 % tensor-pipe utilisation (profiles/r01/ncu_full_r01e.md).
+template <int T, bool PAIR>
+__device__ __forceinline__ void wg_issue_stage(uint32_t tmem_base, uint32_t bnw, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t tstep16, uint32_t idesc, int nkk, uint32_t acc_first) {
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    if (PAIR) umma_bf16_pair(tmem_base + t * bnw, adesc, bdesc + t * tstep16, idesc, acc_first);
+    else umma_bf16(tmem_base + t * bnw, adesc, bdesc + t * tstep16, idesc, acc_first);
+  }
+#pragma unroll 1
+  for (int kk = 1; kk < nkk; ++kk) {
+    adesc += 2048 >> 4;               // next 16 pixels (16 rows of 128 B)
+    bdesc += 2048 >> 4;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if (PAIR) umma_bf16_pair(tmem_base + t * bnw, adesc, bdesc + t * tstep16, idesc, 1u);
+      else umma_bf16(tmem_base + t * bnw, adesc, bdesc + t * tstep16, idesc, 1u);
+    }
+  }
+}
+template <bool PAIR>
+__device__ __forceinline__ void wg_issue_stage_T(int T, uint32_t tmem_base, uint32_t bnw, uint64_t adesc,
+                                                 uint64_t bdesc, uint32_t tstep16, uint32_t idesc, int nkk,
+                                                 uint32_t acc_first) {
+  if (T == 3) wg_issue_stage<3, PAIR>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+  else if (T == 4) wg_issue_stage<4, PAIR>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+  else wg_issue_stage<1, PAIR>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
                   const __grid_constant__ CUtensorMap mapB1, const WgradParams p, const int stage_bytes) {
@@ -168,15 +199,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           uint64_t adesc = make_smem_desc_sw128(sa, p.abox, 1024);
           uint64_t bdesc0 = make_smem_desc_sw128(sb + p.dbg_shift * 128, p.bslot, 1024);
           bdesc0 |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;                  // experiment hook, 0 in production
-          for (int kk = 0; kk < nkk; ++kk) {
-            uint64_t bdesc = bdesc0;
-            for (int t = 0; t < p.T; ++t) {
-              umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-              bdesc += tstep >> 4;            // next tap: shifted window (or next box group)
-            }
-            adesc += 2048 >> 4;               // next 16 pixels (16 rows of 128 B)
-            bdesc0 += 2048 >> 4;
-          }
+          // taps: shifted windows of one box (or consecutive box groups), tstep bytes apart
+          if (nkk > 0)
+            wg_issue_stage_T<false>(p.T, tmem_base, (uint32_t)BNW, adesc, bdesc0, tstep >> 4, idesc, nkk,
+                                    kb > kb0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -321,15 +347,8 @@ wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         if (elect_one()) {
           uint64_t adesc = make_smem_desc_sw128(sa, p.abox, 1024);
           uint64_t bdesc0 = make_smem_desc_sw128(sb, p.bslot, 1024);
-          for (int kk = 0; kk < nkk; ++kk) {
-            uint64_t bdesc = bdesc0;
-            for (int t = 0; t < p.T; ++t) {
-              umma_bf16_pair(tmem_base + t * BNW, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-              bdesc += tstep >> 4;
-            }
-            adesc += 2048 >> 4;
-            bdesc0 += 2048 >> 4;
-          }
+          wg_issue_stage_T<true>(p.T, tmem_base, (uint32_t)BNW, adesc, bdesc0, tstep >> 4, idesc, nkk,
+                                 kb > kb0 ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage]);
         }
         __syncwarp();
@@ -463,10 +482,18 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant_
             ad[j] = make_smem_desc_sw128(sx + offa, offb - offa, 1024);
           }
           uint64_t bdesc = make_smem_desc_sw128(sdy, 1024, 1024);
-          for (int kk = 0; kk < p.kp / 16; ++kk) {
+          const uint32_t acc_first = kb > kb0 ? 1u : 0u;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            umma_bf16(tmem_base + j * 64, ad[j], bdesc, idesc, acc_first);
+            ad[j] += 2048 >> 4;
+          }
+          bdesc += 2048 >> 4;
+#pragma unroll 1
+          for (int kk = 1; kk < p.kp / 16; ++kk) {
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-              umma_bf16(tmem_base + j * 64, ad[j], bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              umma_bf16(tmem_base + j * 64, ad[j], bdesc, idesc, 1u);
               ad[j] += 2048 >> 4;
             }
             bdesc += 2048 >> 4;
