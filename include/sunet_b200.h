@@ -75,6 +75,8 @@ typedef struct sunet_conv_gemm_args {
   const float* bnb_shift;
   const float* bnb_mean;
   const float* bnb_invstd;
+  int bnb_col0;                /* the reduction covers output columns [bnb_col0, n_total) (multiple of 64; y and the  */
+                               /* bnb_* vectors then have n_total - bnb_col0 channels); lower columns keep (sum, sq)   */
 } sunet_conv_gemm_args;
 
 int sunet_conv_gemm(const sunet_conv_gemm_args* args, sunet_stream_t stream);
@@ -172,6 +174,13 @@ int sunet_bn_eval_affine(const float* gamma, const float* beta, const float* con
 int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
                        int a_pix_stride, void* pooled, int pooled_pix_stride, int batch, int height, int width,
                        int channels, sunet_stream_t stream);
+/* sunet_bn_relu_pool that also stores ywin[b][y/2][x/2][c] = the conv output y of the window's FIRST maximum of
+ * the fp32 activation (the element MaxPool2d's backward routes the gradient to; model.py:31).  The backward-data
+ * conv that produces the pooled gradient can then take ywin as its bnb_y and reduce the pool-routed part of this
+ * block's BatchNorm backward in its epilogue. */
+int sunet_bn_relu_pool_ywin(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
+                            int a_pix_stride, void* pooled, int pooled_pix_stride, void* ywin, int ywin_pix_stride,
+                            int batch, int height, int width, int channels, sunet_stream_t stream);
 /* backward of [BN(train) -> ReLU -> (skip + MaxPool)]:
  *   g = (dA [+ dPool routed to the first maximum of each 2x2 window]) * (a > 0)
  *   dgamma = sum g*xhat, dbeta = sum g, dy = scale*(g - dbeta/n - xhat*dgamma/n)  -> bf16
@@ -189,6 +198,15 @@ int sunet_bn_bwd_apply(const void* dA, int dA_pix_stride, const void* y, int y_p
                        int partial_rows, float* dgamma, float* dbeta, void* dy, int dy_pix_stride, int batch,
                        int height, int width, int channels, void* workspace, size_t workspace_bytes,
                        sunet_stream_t stream);
+/* Pooled block whose reduction rows were written by the two producers of its gradient (skip part: the decoder
+ * backward-data conv with bnb_col0 = C over [d_up | d_skip]; pooled part: the encoder backward-data conv with
+ * bnb_y = ywin).  Row r, channel c of source i sits at partials_i[(r*stride_i + col_i + c)*2 + {0,1}]. */
+int sunet_bn_pool_bwd_apply(const void* dA, int dA_pix_stride, const void* dPool, int dPool_pix_stride, const void* y,
+                            int y_pix_stride, const float* scale, const float* shift, const float* mean,
+                            const float* invstd, const float* partials0, int rows0, int stride0, int col0,
+                            const float* partials1, int rows1, int stride1, int col1, float* dgamma, float* dbeta,
+                            void* dy, int dy_pix_stride, int batch, int height, int width, int channels,
+                            void* workspace, size_t workspace_bytes, sunet_stream_t stream);
 /* out[c] = sum_rows stats[row][col_offset + c][0]  (column sums from the G1 epilogue; ConvT bias grad) */
 int sunet_colsum_finalize(const float* stats, int rows, int n_total, int col_offset, int channels, float* out,
                           sunet_stream_t stream);

@@ -170,6 +170,75 @@ def g1_bnb_convT(K):
     return ok
 
 
+def g1_bnb_pool(K):
+    """Pooled block: reduction split between the decoder dgrad ([d_up | d_skip], bnb_col0 = C) and the encoder dgrad
+    (d_pool against ywin), folded by bn_pool_bwd_apply — against the un-fused bn_relu_pool_bwd."""
+    dev = "cuda"
+    ok = True
+    ws = K.new_workspace(dev)
+    for (B, H, W, Cc, Cd1, Cd2) in [(2, 32, 32, 64, 64, 128), (3, 32, 64, 128, 128, 256), (2, 32, 32, 256, 256, 512)]:
+        g = torch.Generator().manual_seed(B * 7 + Cc)
+        yb = nhwc((torch.randn(B, Cc, H, W, generator=g) * 1.5 + 0.3).to(dev))
+        scale = (torch.rand(Cc, generator=g) + 0.5).to(dev) * torch.where(torch.rand(Cc, generator=g) < 0.1, -1.0, 1.0).to(dev)
+        shift = (torch.randn(Cc, generator=g) * 0.5).to(dev)
+        mean = (torch.randn(Cc, generator=g) * 0.3).to(dev)
+        invstd = (torch.rand(Cc, generator=g) + 0.5).to(dev)
+        a = torch.empty_like(yb)
+        pooled = torch.empty(B, H // 2, W // 2, Cc, dtype=torch.bfloat16, device=dev)
+        ywin = torch.full_like(pooled, float("nan"))
+        K.bn_relu_pool(yb, scale, shift, a, pooled, ywin=ywin)
+        a2, pooled2 = torch.empty_like(a), torch.empty_like(pooled)
+        K.bn_relu_pool(yb, scale, shift, a2, pooled2)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(a, a2)) and bool(torch.equal(pooled, pooled2))
+        # ywin: y of the first maximum of the fp32 activation in each window
+        act = (yb.float() * scale + shift).permute(0, 3, 1, 2)
+        _, idx = F.max_pool2d(act, 2, return_indices=True)
+        yref = yb.float().permute(0, 3, 1, 2).flatten(2).gather(2, idx.flatten(2)).view_as(idx).permute(0, 2, 3, 1)
+        same &= bool(torch.equal(ywin.float(), yref))
+        print(f"  [{'OK ' if same else 'BAD'}] bn_relu_pool + ywin B{B} {H}x{W} C{Cc}")
+        ok &= same
+        # producer 1: [d_up | d_skip] at level L
+        wd1 = (torch.randn(2 * Cc, 9 * Cd1, generator=g) / (3 * Cd1 ** 0.5)).to(dev).to(torch.bfloat16)
+        dy1 = nhwc(torch.randn(B, Cd1, H, W, generator=g).to(dev))
+        dcat = torch.full((B, H, W, 2 * Cc), float("nan"), dtype=torch.bfloat16, device=dev)
+        dcat0 = torch.full_like(dcat, float("nan"))
+        # producer 2: d_pool at level L+1
+        wd2 = (torch.randn(Cc, 9 * Cd2, generator=g) / (3 * Cd2 ** 0.5)).to(dev).to(torch.bfloat16)
+        dy2 = nhwc(torch.randn(B, Cd2, H // 2, W // 2, generator=g).to(dev))
+        dpool = torch.full((B, H // 2, W // 2, Cc), float("nan"), dtype=torch.bfloat16, device=dev)
+        dpool0 = torch.full_like(dpool, float("nan"))
+        if not (K.conv_gemm_bnb_supported(K.A_CONV3X3, (B, H, W), dy1, wd1, dcat) and
+                K.conv_gemm_bnb_supported(K.A_CONV3X3, (B, H // 2, W // 2), dy2, wd2, dpool)):
+            print("   unsupported shape: skipped")
+            continue
+        rows0 = K.conv_gemm_stat_rows(B, H, W, 2 * Cc)
+        rows1 = K.conv_gemm_stat_rows(B, H // 2, W // 2, Cc)
+        st0 = torch.full((rows0, 2 * Cc, 2), float("nan"), device=dev)
+        st0p = torch.zeros(rows0, 2 * Cc, 2, device=dev)
+        st1 = torch.full((rows1, Cc, 2), float("nan"), device=dev)
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), dy1, wd1, dcat, stats=st0, bnb=(yb, scale, shift, mean, invstd, Cc))
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), dy1, wd1, dcat0, stats=st0p)
+        K.conv_gemm(K.A_CONV3X3, (B, H // 2, W // 2), dy2, wd2, dpool, stats=st1, bnb=(ywin, scale, shift, mean, invstd))
+        K.conv_gemm(K.A_CONV3X3, (B, H // 2, W // 2), dy2, wd2, dpool0)
+        torch.cuda.synchronize()
+        tag = f"pool bnb B{B} {H}x{W} C{Cc}"
+        same = bool(torch.equal(dcat, dcat0)) and bool(torch.equal(dpool, dpool0))
+        print(f"  [{'OK ' if same else 'BAD'}] {tag}: gradients identical to the plain launches")
+        ok &= same
+        ok &= report(f"   {tag} d_up column sums untouched", st0[:, :Cc, 0].sum(0), st0p[:, :Cc, 0].sum(0), 1e-6)
+        dg1, db1, dg2, db2 = (torch.empty(Cc, device=dev) for _ in range(4))
+        o1, o2 = torch.empty_like(yb), torch.empty_like(yb)
+        K.bn_pool_bwd_apply(dcat[..., Cc:], dpool, yb, scale, shift, mean, invstd, (st0, rows0, 2 * Cc, Cc),
+                            (st1, rows1, Cc, 0), dg1, db1, o1, ws)
+        K.bn_relu_pool_bwd(dcat0[..., Cc:], dpool0, yb, scale, shift, mean, invstd, scale, dg2, db2, o2, ws)
+        torch.cuda.synchronize()
+        ok &= report(f"   {tag} dgamma", dg1, dg2, 1e-4)
+        ok &= report(f"   {tag} dbeta", db1, db2, 1e-4)
+        ok &= report(f"   {tag} dy", o1.float(), o2.float(), 4e-3)
+    return ok
+
+
 def g1_plain(K):
     dev = "cuda"
     ok = True
@@ -569,7 +638,7 @@ def swizzle_exp(K):
     return True
 
 
-GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g1_bnb": g1_bnb, "g1_bnb_convT": g1_bnb_convT, "g2_wgrad": g2_wgrad,
+GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g1_bnb": g1_bnb, "g1_bnb_convT": g1_bnb_convT, "g1_bnb_pool": g1_bnb_pool, "g2_wgrad": g2_wgrad,
           "ew_bn": ew_bn, "ew_heads_loss": ew_heads_loss}
 
 

@@ -342,7 +342,8 @@ template <bool POOL>
 __global__ void __launch_bounds__(256)
 bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                     const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int as,
-                    __nv_bfloat16* __restrict__ pooled, int ps, int B, int H, int W, int C) {
+                    __nv_bfloat16* __restrict__ pooled, int ps, __nv_bfloat16* __restrict__ ywin, int yws, int B,
+                    int H, int W, int C) {
   pdl_wait();
   pdl_trigger();
   const int G = C >> 3;
@@ -366,7 +367,9 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __
     *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
     *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
     if (POOL) {
-      float mx[8];
+      // mx = pooled activation; (best, yb) = fp32 pre-ReLU activation and conv output y of the window's FIRST
+      // maximum — the element MaxPool2d's backward routes the gradient to (same rule as pool_win_chan)
+      float mx[8], best[8], yb[8];
       bf16x8 v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -380,13 +383,19 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __
         unpack8(v[k], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+          const float raw = fmaf(f[j], sc[j], sh[j]);
+          if (k == 0 || raw > best[j]) {
+            best[j] = raw;
+            yb[j] = f[j];
+          }
+          f[j] = fmaxf(raw, 0.f);
           mx[j] = (k == 0) ? f[j] : fmaxf(mx[j], f[j]);
         }
         *reinterpret_cast<bf16x8*>(a + pix * as + g * 8) = pack8(f);
       }
       const long long ppix = ((long long)n * HW + wy) * WW + wx;
       *reinterpret_cast<bf16x8*>(pooled + ppix * ps + g * 8) = pack8(mx);
+      if (ywin != nullptr) *reinterpret_cast<bf16x8*>(ywin + ppix * yws + g * 8) = pack8(yb);   // exact: y is bf16
     } else {
       const long long pix = wpix;
       float f[8];
@@ -873,6 +882,50 @@ bn_bwd_pool_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
   }
 }
 
+// Fold of reduction rows that come from up to two producers with their own row strides / column offsets
+// (pooled blocks: skip-gradient rows from the decoder dgrad epilogue, pool-gradient rows from the encoder dgrad
+// epilogue).  One warp per channel.
+struct PartialSrc {
+  const float* p;
+  int rows, stride, col0;     // element (r, c, k) at p[(r * stride + col0 + c) * 2 + k]
+};
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize2_kernel(PartialSrc s0, PartialSrc s1, int C, double count, const float* __restrict__ scale,
+                        const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma, float* dbeta,
+                        float* coef) {
+  pdl_wait();
+  pdl_trigger();
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double sg = 0.0, sgx = 0.0;
+  for (int b = lane; b < s0.rows; b += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(s0.p + ((size_t)b * s0.stride + s0.col0 + c) * 2);
+    sg += (double)v.x;
+    sgx += (double)v.y;
+  }
+  for (int b = lane; b < s1.rows; b += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(s1.p + ((size_t)b * s1.stride + s1.col0 + c) * 2);
+    sg += (double)v.x;
+    sgx += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+  }
+  if (lane == 0) {
+    if (dbeta) dbeta[c] = (float)sg;
+    if (dgamma) dgamma[c] = (float)sgx;
+    const double scv = scale[c];
+    const double k1 = -scv * (double)invstd[c] * sgx / count;
+    const double k0 = -scv * sg / count - k1 * (double)mean[c];
+    coef[c] = (float)scv;
+    coef[C + c] = (float)k1;
+    coef[2 * C + c] = (float)k0;
+  }
+}
+
 // parallel fold of the per-block partial rows: one warp per channel, lanes stride over the rows
 __global__ void __launch_bounds__(256)
 bn_bwd_finalize_par_kernel(const float* __restrict__ partials, int blocks, int C, double count,
@@ -1031,9 +1084,31 @@ static int check_act(const char* what, int stride, int channels) {
   return SUNET_OK;
 }
 
+static int bn_relu_pool_impl(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
+                             int a_pix_stride, void* pooled, int pooled_pix_stride, void* ywin, int ywin_pix_stride,
+                             int batch, int height, int width, int channels, sunet_stream_t stream_);
+
 extern "C" int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
                                   int a_pix_stride, void* pooled, int pooled_pix_stride, int batch, int height,
                                   int width, int channels, sunet_stream_t stream_) {
+  return bn_relu_pool_impl(y, y_pix_stride, scale, shift, a, a_pix_stride, pooled, pooled_pix_stride, nullptr, 0, batch,
+                           height, width, channels, stream_);
+}
+
+extern "C" int sunet_bn_relu_pool_ywin(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
+                                       int a_pix_stride, void* pooled, int pooled_pix_stride, void* ywin,
+                                       int ywin_pix_stride, int batch, int height, int width, int channels,
+                                       sunet_stream_t stream_) {
+  if (!pooled || !ywin) return set_error(SUNET_ERR_INVALID, "bn_relu_pool_ywin: pooled and ywin are required");
+  int e = check_act("bn_relu_pool_ywin(ywin)", ywin_pix_stride, channels);
+  if (e) return e;
+  return bn_relu_pool_impl(y, y_pix_stride, scale, shift, a, a_pix_stride, pooled, pooled_pix_stride, ywin,
+                           ywin_pix_stride, batch, height, width, channels, stream_);
+}
+
+static int bn_relu_pool_impl(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
+                             int a_pix_stride, void* pooled, int pooled_pix_stride, void* ywin, int ywin_pix_stride,
+                             int batch, int height, int width, int channels, sunet_stream_t stream_) {
   if (!y || !scale || !shift || !a || batch <= 0 || height <= 0 || width <= 0)
     return set_error(SUNET_ERR_INVALID, "bn_relu_pool: bad arguments");
   int e;
@@ -1046,9 +1121,9 @@ extern "C" int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* 
     if ((e = check_act("bn_relu_pool(pooled)", pooled_pix_stride, channels))) return e;
     const long long total = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
     if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool: tensor too large (%lld items)", total);
-    launch_k(bn_relu_pool_kernel<true>, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, 
+    launch_k(bn_relu_pool_kernel<true>, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM,
         yp, y_pix_stride, scale, shift, ap, a_pix_stride, reinterpret_cast<__nv_bfloat16*>(pooled), pooled_pix_stride,
-        batch, height, width, channels);
+        reinterpret_cast<__nv_bfloat16*>(ywin), ywin_pix_stride, batch, height, width, channels);
   } else {
     const long long total = (long long)batch * height * width * (channels / 8);
     if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_relu_pool: tensor too large (%lld items)", total);
@@ -1057,8 +1132,7 @@ extern "C" int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* 
                                                                 channels / 8);
     else
       launch_k(bn_relu_pool_kernel<false>, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, yp, y_pix_stride, scale, shift, ap,
-                                                                           a_pix_stride, nullptr, 0, batch, height,
-                                                                           width, channels);
+               a_pix_stride, nullptr, 0, nullptr, 0, batch, height, width, channels);
   }
   return check_launch("bn_relu_pool");
 }
@@ -1144,4 +1218,39 @@ extern "C" int sunet_bn_bwd_apply(const void* dA, int dA_pix_stride, const void*
       reinterpret_cast<const __nv_bfloat16*>(dA), dA_pix_stride, reinterpret_cast<const __nv_bfloat16*>(y),
       y_pix_stride, scale, shift, coef, reinterpret_cast<__nv_bfloat16*>(dy), dy_pix_stride, total, channels);
   return check_launch("bn_bwd_apply");
+}
+
+extern "C" int sunet_bn_pool_bwd_apply(const void* dA, int dA_pix_stride, const void* dPool, int dPool_pix_stride,
+                                       const void* y, int y_pix_stride, const float* scale, const float* shift,
+                                       const float* mean, const float* invstd, const float* partials0, int rows0,
+                                       int stride0, int col0, const float* partials1, int rows1, int stride1,
+                                       int col1, float* dgamma, float* dbeta, void* dy, int dy_pix_stride, int batch,
+                                       int height, int width, int channels, void* workspace, size_t workspace_bytes,
+                                       sunet_stream_t stream_) {
+  if (!dA || !dPool || !y || !scale || !shift || !mean || !invstd || !partials0 || !partials1 || rows0 <= 0 ||
+      rows1 <= 0 || !dy || !workspace || stride0 < col0 + channels || stride1 < col1 + channels || col0 < 0 || col1 < 0)
+    return set_error(SUNET_ERR_INVALID, "bn_pool_bwd_apply: bad arguments");
+  int e;
+  if ((e = check_act("bn_pool_bwd_apply(y)", y_pix_stride, channels))) return e;
+  if ((e = check_act("bn_pool_bwd_apply(dy)", dy_pix_stride, channels))) return e;
+  if ((e = check_act("bn_pool_bwd_apply(dA)", dA_pix_stride, channels))) return e;
+  if ((e = check_act("bn_pool_bwd_apply(dPool)", dPool_pix_stride, channels))) return e;
+  const int G = channels / 8;
+  if (256 % G) return set_error(SUNET_ERR_INVALID, "bn_pool_bwd_apply: channels %d unsupported", channels);
+  if ((height | width) & 1) return set_error(SUNET_ERR_INVALID, "bn_pool_bwd_apply: odd size");
+  const long long total = (long long)batch * (height / 2) * (width / 2) * G;
+  if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "bn_pool_bwd_apply: tensor too large");
+  if (workspace_bytes < 3 * (size_t)channels * sizeof(float))
+    return set_error(SUNET_ERR_WORKSPACE, "bn_pool_bwd_apply: workspace too small");
+  float* coef = reinterpret_cast<float*>(workspace);
+  const double count = (double)batch * height * width;
+  PartialSrc s0 = {partials0, rows0, stride0, col0}, s1 = {partials1, rows1, stride1, col1};
+  launch_k(bn_bwd_finalize2_kernel, dim3((channels + 7) / 8), dim3(256), 0, STREAM, s0, s1, channels, count, scale,
+           mean, invstd, dgamma, dbeta, coef);
+  if ((e = check_launch("bn_bwd_finalize2"))) return e;
+  launch_k(bn_bwd_pool_apply_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM,
+           reinterpret_cast<const __nv_bfloat16*>(dA), dA_pix_stride, reinterpret_cast<const __nv_bfloat16*>(dPool),
+           dPool_pix_stride, reinterpret_cast<const __nv_bfloat16*>(y), y_pix_stride, scale, shift, coef,
+           reinterpret_cast<__nv_bfloat16*>(dy), dy_pix_stride, batch, height, width, channels);
+  return check_launch("bn_pool_bwd_apply");
 }

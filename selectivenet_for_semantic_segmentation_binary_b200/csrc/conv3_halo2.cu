@@ -31,6 +31,7 @@ struct Halo2Params {
   const float* bnb_shift;
   const float* bnb_mean;
   const float* bnb_invstd;
+  int bnb_col0;              // BNB covers output columns [bnb_col0, n_total); lower columns get (sum, sum sq)
 };
 
 // TILES = M=128 tiles per CTA and block: 2 (16x16 block) for BN <= 128, 1 (8 wide x 16 tall) for BN = 256
@@ -217,35 +218,45 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
 #pragma unroll
     for (int q = 0; q < NCHUNK; ++q) ssum[q][0] = ssum[q][1] = ssq[q][0] = ssq[q][1] = 0.f;
 
-    // BNB: this thread's two columns of every chunk (channel = n_tile*BN + q*64 + 2*lane + {0,1})
+    // BNB covers the channel chunks q >= q0 of this CTA's N tile (q0 = 0 unless the launch also produces columns
+    // that only need plain statistics, e.g. the [d_up | d_skip] gradient of a decoder block's concat input)
+    int q0 = NCHUNK;
+    if (BNB) {
+      q0 = (p.bnb_col0 - n_tile * BN) / 64;
+      q0 = q0 < 0 ? 0 : (q0 > NCHUNK ? NCHUNK : q0);
+    }
+    const int nqb = NCHUNK - q0;                 // BNB chunks per tile
+    // this thread's two columns of every BNB chunk (channel of the BN = output column - bnb_col0)
     float csc[NCHUNK][2], csh[NCHUNK][2], cmu[NCHUNK][2];
     if (BNB) {
 #pragma unroll
       for (int q = 0; q < NCHUNK; ++q) {
-        const int c = n_tile * BN + q * 64 + lane * 2;
-        csc[q][0] = __ldg(p.bnb_scale + c);
-        csc[q][1] = __ldg(p.bnb_scale + c + 1);
-        csh[q][0] = __ldg(p.bnb_shift + c);
-        csh[q][1] = __ldg(p.bnb_shift + c + 1);
-        cmu[q][0] = __ldg(p.bnb_mean + c);
-        cmu[q][1] = __ldg(p.bnb_mean + c + 1);
+        const int c = n_tile * BN + q * 64 + lane * 2 - p.bnb_col0;
+        const bool on = q >= q0;
+        csc[q][0] = on ? __ldg(p.bnb_scale + c) : 0.f;
+        csc[q][1] = on ? __ldg(p.bnb_scale + c + 1) : 0.f;
+        csh[q][0] = on ? __ldg(p.bnb_shift + c) : 0.f;
+        csh[q][1] = on ? __ldg(p.bnb_shift + c + 1) : 0.f;
+        cmu[q][0] = on ? __ldg(p.bnb_mean + c) : 0.f;
+        cmu[q][1] = on ? __ldg(p.bnb_mean + c + 1) : 0.f;
       }
     }
-    // BNB y-tile pipeline (issuer thread): chunk number k of this CTA = (block k / CPB of its sequence, tile
-    // (k % CPB) / NCHUNK, channel chunk k % NCHUNK); slot k % YS.  Loads run YS-1 chunks ahead of the consumer
-    // (the slot of chunk k-1 is free once every thread has passed the staging barrier of chunk k); L2
+    // BNB y-tile pipeline (issuer thread): BNB chunk number k of this CTA = (block k / CPBY of its sequence, tile
+    // (k % CPBY) / nqb, channel chunk q0 + k % nqb); slot k % YS.  Loads run YS-1 chunks ahead of the consumer
+    // (the slot of chunk k-1 is free once every thread has passed a staging barrier after its stats loop); L2
     // prefetches run kPfAhead chunks further ahead so the smem fill is an L2 hit.
     constexpr uint32_t YS = C::Y_SLOTS > 0 ? C::Y_SLOTS : 1;
     constexpr uint32_t YS_LOG = (YS == 4) ? 2 : ((YS == 2) ? 1 : 0);
     constexpr int kPfAhead = 4;
     uint32_t y_issued = 0, y_prefetched = 0;
     const uint32_t my_blocks = (m_first < m_pairs) ? (uint32_t)((m_pairs - 1 - m_first) / m_step + 1) : 0u;
-    const uint32_t y_total = my_blocks * CPB;
+    const uint32_t cpby = (uint32_t)(C::TILES * nqb);
+    const uint32_t y_total = my_blocks * cpby;
     auto y_coords = [&](uint32_t k, int& c0, int& x0, int& y0, int& nn) {
-      const int blk = (int)(k / CPB), rem = (int)(k % CPB);
+      const int blk = (int)(k / cpby), rem = (int)(k % cpby);
       const int mb_ = 2 * (m_first + blk * m_step) + (int)rank;
-      c0 = n_tile * BN + (rem % NCHUNK) * 64;
-      x0 = (mb_ % p.blocks_x) * (8 * C::TILES) + 8 * (rem / NCHUNK);
+      c0 = n_tile * BN + (q0 + rem % nqb) * 64 - p.bnb_col0;
+      x0 = (mb_ % p.blocks_x) * (8 * C::TILES) + 8 * (rem / nqb);
       y0 = ((mb_ / p.blocks_x) % p.blocks_y) * 16;
       nn = mb_ / (p.blocks_x * p.blocks_y);
     };
@@ -267,6 +278,7 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       }
     };
     if (BNB && issuer) y_pump(YS);
+    uint32_t yctr = 0;                           // BNB chunks whose statistics loop this thread has finished
 
     int it = 0;
     uint32_t chunk_ctr = 0;
@@ -307,14 +319,14 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           if (issuer) {
             tma_store_5d(&mapD, stg, ncol0, bx * (8 * C::TILES) + 8 * t, by * 16, n, 0);   // out-of-range n: clipped
             tma_store_commit();
-            if (BNB) y_pump(chunk_ctr + YS);     // everyone is past the stats loop of chunk_ctr-1: its slot is free
+            if (BNB) y_pump(yctr + YS);          // everyone is past the stats loop of BNB chunk yctr-1: slot free
           }
-          if (BNB) {
+          if (BNB && q >= q0) {
             // (sum g, sum g*(y-mean)) over this quad's 32 rows for this thread's two columns; g = dA where
             // relu(bn(y)) > 0.  dA itself is stored unmasked: the apply kernel masks with the same expression.
-            mbar_wait(&yfull[chunk_ctr & (YS - 1)], (chunk_ctr >> YS_LOG) & 1);
+            mbar_wait(&yfull[yctr & (YS - 1)], (yctr >> YS_LOG) & 1);
             const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
-            const uint32_t* ywords = reinterpret_cast<const uint32_t*>(sY + (chunk_ctr & (YS - 1)) * C::STG_BYTES);
+            const uint32_t* ywords = reinterpret_cast<const uint32_t*>(sY + (yctr & (YS - 1)) * C::STG_BYTES);
             const float sc0 = csc[q][0], sc1 = csc[q][1], sh0 = csh[q][0], sh1 = csh[q][1];
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;     // sum g, sum g*y (mean folded in after the loop)
 #pragma unroll 16
@@ -334,6 +346,7 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
             ssum[q][1] += s1;
             ssq[q][0] += fmaf(-cmu[q][0], s0, q0);             // 32-row partial of sum g*(y-mean)
             ssq[q][1] += fmaf(-cmu[q][1], s1, q1);
+            ++yctr;
           } else if (p.stats != nullptr) {
             const uint32_t* words = reinterpret_cast<const uint32_t*>(stg);
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -379,7 +392,8 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       float* dst = p.stats + (static_cast<size_t>(srow) * p.n_total + n_tile * BN) * 2;
       for (int i = t; i < BN * 2; i += 128) {
         float v = red[i] + red[BN * 2 + i] + red[2 * BN * 2 + i] + red[3 * BN * 2 + i];
-        if (BNB && (i & 1)) v *= __ldg(p.bnb_invstd + n_tile * BN + (i >> 1));     // sum g*(y-mean) -> sum g*xhat
+        const int col = n_tile * BN + (i >> 1);
+        if (BNB && (i & 1) && col >= p.bnb_col0) v *= __ldg(p.bnb_invstd + col - p.bnb_col0);   // -> sum g*xhat
         dst[i] = v;
       }
     }
@@ -465,9 +479,12 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
     return e;
   if ((e = halo2_map(&mD, a->dst, a->n_total, a->dst_pix_stride, B, H, W, 8, 16))) return e;
   if (bnb) {
-    if (a->bnb_y_pix_stride < a->n_total || (a->bnb_y_pix_stride % 8))
+    const int yc = a->n_total - a->bnb_col0;
+    if (a->bnb_col0 < 0 || a->bnb_col0 % 64 || yc <= 0)
+      return set_error(SUNET_ERR_INVALID, "conv_gemm: bnb_col0 %d must be a multiple of 64 below n_total", a->bnb_col0);
+    if (a->bnb_y_pix_stride < yc || (a->bnb_y_pix_stride % 8))
       return set_error(SUNET_ERR_INVALID, "conv_gemm: bad bnb_y_pix_stride %d", a->bnb_y_pix_stride);
-    if ((e = halo2_map(&mY, a->bnb_y, a->n_total, a->bnb_y_pix_stride, B, H, W, 8, 16))) return e;
+    if ((e = halo2_map(&mY, a->bnb_y, yc, a->bnb_y_pix_stride, B, H, W, 8, 16))) return e;
   } else {
     mY = mD;
   }
@@ -484,6 +501,7 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   p.bnb_shift = a->bnb_shift;
   p.bnb_mean = a->bnb_mean;
   p.bnb_invstd = a->bnb_invstd;
+  p.bnb_col0 = bnb ? a->bnb_col0 : 0;
   const int grid = halo2_slots(B, H, W, p.n_tiles, bw) * p.n_tiles * 2;
   if (bnb) {
     if (bn == 256) return halo2_launch_t<256, true>(mA0, mA1, mB, mD, mY, p, grid, stream);

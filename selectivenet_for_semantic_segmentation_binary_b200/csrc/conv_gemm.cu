@@ -547,6 +547,8 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
                                         "shape/mode; check sunet_conv_gemm_bnb_supported()");
   if (bnb && (!a->stats || !a->bnb_scale || !a->bnb_shift || !a->bnb_mean || !a->bnb_invstd))
     return set_error(SUNET_ERR_INVALID, "conv_gemm: bnb_y needs stats and the four bnb_* vectors");
+  if (bnb && a->bnb_col0 != 0)
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: bnb_col0 != 0 is implemented by the CTA-pair halo kernel only");
   if (conv3_halo_eligible(a)) return conv3_halo_launch(a, stream);
 
   TileGeom g = tile_geom(B, H, W, 128);

@@ -185,6 +185,28 @@ class SUNetPlan:
                     cl.bnb_rows = K.conv_gemm_stat_rows(B, hh, ww, cl.cout, K.A_GATHER2X2)
                     cl.bnb_stats = torch.zeros(cl.bnb_rows, cl.cout, 2, device=dev)
                     self.bnb_convT[L] = cl
+        # Pooled encoder blocks (level L output feeds a skip AND a max-pool): their reduction is split between the
+        # two producers of their gradient — the decoder dgrad writing [d_up | d_skip] reduces the skip half
+        # (bnb_col0 = C), the deeper dgrad writing d_pool reduces the pool-routed half against ywin (the conv output
+        # of each window's winner, stored by the forward pool kernel).  pool_fuse[L] = (skip producer, pool producer)
+        self.pool_fuse: Dict[int, tuple] = {}
+        self.ywin: Dict[int, torch.Tensor] = {}
+        self.pool_stats: Dict[int, tuple] = {}
+        if os.environ.get("SUNET_FUSE_BNB", "1") != "0" and os.environ.get("SUNET_FUSE_BNB_POOL", "1") != "0":
+            for L in (1, 2, 3):
+                c = _CH[L]
+                skip_p = self.layers[f"decoder_layer_{L}_2"]
+                pool_p = self.layers["decoder_layer_4_2" if L == 3 else f"encoder_layer_{L + 1}_1"]
+                h, w = self.hw[L]
+                h2, w2 = self.hw[L + 1]
+                ok1 = K.conv_gemm_bnb_supported(K.A_CONV3X3, (B, h, w), self.gB[L][0], skip_p.wd, self.dcat[L]) and \
+                    h % 16 == 0 and w % 16 == 0          # the column-offset form lives in the halo kernel only
+                ok2 = K.conv_gemm_bnb_supported(K.A_CONV3X3, (B, h2, w2), self.gB[L + 1][0], pool_p.wd, self.dpool[L])
+                if ok1 and ok2:
+                    rows = K.conv_gemm_stat_rows(B, h2, w2, c)
+                    self.pool_stats[L] = (torch.zeros(rows, c, 2, device=dev), rows)
+                    self.ywin[L] = act(L + 1, c)
+                    self.pool_fuse[L] = (skip_p.name, pool_p.name)
         # the last block: heads_bwd recomputes relu(bn(y)) from y and emits the BN-backward reduction rows, so the
         # activation of decoder_layer_1_1 is never stored (SUNET_FUSE_HEADS_BN=0 restores the two-pass form)
         self.fuse_heads_bn = os.environ.get("SUNET_FUSE_HEADS_BN", "1") != "0"
@@ -313,7 +335,8 @@ class SUNetPlan:
             K.bn_relu_heads(ly.y, ly.scale, ly.shift, ly.a, [params[f"{h}.weight"] for h in heads],
                             [params[f"{h}.bias"] for h in heads], self.logits)
         else:
-            K.bn_relu_pool(ly.y, ly.scale, ly.shift, ly.a, self.pool[ly.level] if ly.pool else None)
+            K.bn_relu_pool(ly.y, ly.scale, ly.shift, ly.a, self.pool[ly.level] if ly.pool else None,
+                           ywin=self.ywin.get(ly.level) if (ly.pool and training) else None)
 
     def forward(self, x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor],
                 training: bool) -> torch.Tensor:
@@ -375,8 +398,14 @@ class SUNetPlan:
         busy = self._gB_busy[lvl][idx]
         if busy is not None:                       # the wgrad that last read this buffer must be finished
             torch.cuda.current_stream().wait_event(busy)
-        if fused_reduce:
-            assert dPool is None and ly.bnb_stats is not None
+        if fused_reduce and dPool is not None:
+            c = ly.cout
+            st0, rows0 = self.dcat_stats[lvl]
+            st1, rows1 = self.pool_stats[lvl]
+            K.bn_pool_bwd_apply(dA, dPool, ly.y, ly.scale, ly.shift, ly.mean, ly.invstd, (st0, rows0, 2 * c, c),
+                                (st1, rows1, c, 0), grads[f"{n}.1.weight"], grads[f"{n}.1.bias"], dy, self.ws)
+        elif fused_reduce:
+            assert ly.bnb_stats is not None
             K.bn_bwd_apply(dA, ly.y, ly.scale, ly.shift, ly.mean, ly.invstd, ly.bnb_stats, ly.bnb_rows,
                            grads[f"{n}.1.weight"], grads[f"{n}.1.bias"], dy, self.ws)
         else:
@@ -402,6 +431,13 @@ class SUNetPlan:
         bnb = None if nxt is None else (nxt.y, nxt.scale, nxt.shift, nxt.mean, nxt.invstd)
         if nxt is not None:
             dgrad_stats = nxt.bnb_stats
+        for Lp, (skip_name, pool_name) in self.pool_fuse.items():
+            pl = self.layers[f"encoder_layer_{Lp}_2"]
+            if n == skip_name:           # [d_up | d_skip]: plain column sums for d_up, the reduction for d_skip
+                bnb = (pl.y, pl.scale, pl.shift, pl.mean, pl.invstd, _CH[Lp])
+            elif n == pool_name:         # d_pool against the winners' conv outputs
+                bnb = (self.ywin[Lp], pl.scale, pl.shift, pl.mean, pl.invstd)
+                dgrad_stats = self.pool_stats[Lp][0]
 
         def dgrad():
             if dgrad_out is not None:
@@ -480,7 +516,8 @@ class SUNetPlan:
         for lvl in (3, 2, 1):
             c = _CH[lvl]
             n2, n1 = f"encoder_layer_{lvl}_2", f"encoder_layer_{lvl}_1"
-            f = self._cbr_bwd(L[n2], self.dcat[lvl][..., c:], self.dpool[lvl], params, grads, self.gA[lvl])
+            f = self._cbr_bwd(L[n2], self.dcat[lvl][..., c:], self.dpool[lvl], params, grads, self.gA[lvl],
+                              fused_reduce=lvl in self.pool_fuse)
             self._cbr_bwd(L[n1], self.gA[lvl], None, params, grads, self.dpool[lvl - 1] if lvl > 1 else None,
                           fused_reduce=f)
             done(f"enc{lvl}")

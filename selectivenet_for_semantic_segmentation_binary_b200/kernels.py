@@ -95,8 +95,10 @@ def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst:
         assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() >= rows * a.n_total * 2
         a.stats = stats.data_ptr()
     if bnb is not None:
-        y, scale, shift, mean, invstd = bnb
-        assert stats is not None and y.shape == dst.shape
+        y, scale, shift, mean, invstd = bnb[:5]
+        col0 = bnb[5] if len(bnb) > 5 else 0       # the reduction covers output columns [col0, n_total)
+        assert stats is not None and y.shape[:3] == dst.shape[:3] and y.shape[3] == dst.shape[3] - col0
+        a.bnb_col0 = col0
         a.bnb_y, _, a.bnb_y_pix_stride = _act(y)
         a.bnb_scale, a.bnb_shift, a.bnb_mean, a.bnb_invstd = _f32(scale), _f32(shift), _f32(mean), _f32(invstd)
     _lib.check(lib.sunet_conv_gemm(C.byref(a), _stream()), "sunet_conv_gemm")
@@ -203,15 +205,41 @@ def bn_eval_affine(gamma, beta, conv_bias, running_mean, running_var, eps, scale
                                                 _stream()), "sunet_bn_eval_affine")
 
 
-def bn_relu_pool(y, scale, shift, a, pooled=None) -> None:
+def bn_relu_pool(y, scale, shift, a, pooled=None, ywin=None) -> None:
+    """ywin (with pooled): also store the conv output y of each window's first maximum (the element the pool
+    gradient is routed to), which lets the producer of the pooled gradient reduce it for BatchNorm backward."""
     B, H, W, Cc = y.shape
     yp, _, ys = _act(y)
     ap, _, as_ = _act(a)
     pp, ps = (None, 0)
     if pooled is not None:
         pp, _, ps = _act(pooled)
+    if ywin is not None:
+        assert pooled is not None and ywin.shape == pooled.shape
+        wp, _, wps = _act(ywin)
+        _lib.check(_lib.load().sunet_bn_relu_pool_ywin(yp, ys, _f32(scale), _f32(shift), ap, as_, pp, ps, wp, wps, B, H,
+                                                       W, Cc, _stream()), "sunet_bn_relu_pool_ywin")
+        return
     _lib.check(_lib.load().sunet_bn_relu_pool(yp, ys, _f32(scale), _f32(shift), ap, as_, pp, ps, B, H, W, Cc,
                                               _stream()), "sunet_bn_relu_pool")
+
+
+def bn_pool_bwd_apply(dA, dPool, y, scale, shift, mean, invstd, src0, src1, dgamma, dbeta, dy, workspace) -> None:
+    """Pooled block, reduction rows already written by the two producers of its gradient.
+    src = (partials fp32 tensor, rows, row stride in channels, first column)."""
+    B, H, W, Cc = y.shape
+    yp, _, ys = _act(y)
+    dyp, _, dys = _act(dy)
+    dAp, _, das = _act(dA)
+    dPp, _, dps = _act(dPool)
+    (p0, r0, s0, c0), (p1, r1, s1, c1) = src0, src1
+    for pt, r, st in ((p0, r0, s0), (p1, r1, s1)):
+        assert pt.dtype == torch.float32 and pt.is_contiguous() and pt.numel() >= r * st * 2
+    _lib.check(_lib.load().sunet_bn_pool_bwd_apply(dAp, das, dPp, dps, yp, ys, _f32(scale), _f32(shift), _f32(mean),
+                                                   _f32(invstd), p0.data_ptr(), r0, s0, c0, p1.data_ptr(), r1, s1, c1,
+                                                   _f32(dgamma), _f32(dbeta), dyp, dys, B, H, W, Cc,
+                                                   workspace.data_ptr(), workspace.numel(), _stream()),
+               "sunet_bn_pool_bwd_apply")
 
 
 def bn_relu_pool_bwd(dA, dPool, y, scale, shift, mean, invstd, gamma, dgamma, dbeta, dy, workspace) -> None:

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 B, S = 16, 256
 
-FUSED_OFF = {"SUNET_FUSE_BNB": "0", "SUNET_FUSE_HEADS_BN": "0", "SUNET_FIRST_PAIR": "0", "SUNET_OVERLAP_WGRAD": "0"}
+FUSED_OFF = {"SUNET_FUSE_BNB": "0", "SUNET_FUSE_BNB_POOL": "0", "SUNET_FUSE_HEADS_BN": "0", "SUNET_FIRST_PAIR": "0", "SUNET_OVERLAP_WGRAD": "0"}
 
 
 def _step(monkeypatch, env):
