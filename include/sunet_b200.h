@@ -131,6 +131,15 @@ int sunet_pack_input_im2col(const float* x, void* out, int batch, int cin, int h
 int sunet_pack_input_im2col32(const float* x, void* out, int batch, int cin, int height, int width,
                               sunet_stream_t stream);
 int sunet_pack_conv1_pair_weights(const float* w, void* wf, int cout, int cin, sunet_stream_t stream);
+/* Device-side input pipeline (utils/data_utils.py:94-126 Normalization + RandomFlip, :159-168 ToTensor, :216-219 the
+ * /255 of PatchDataset): img uint8 [B][H][W][3] as decoded, lut[256] = float32((b/255) - mean)/std computed by the
+ * caller in numpy (bit-identical values), flip[B] (bit 0 left-right, bit 1 up-down; NULL = none) -> the same
+ * [B][H][W][32] bf16 tensor sunet_pack_input_im2col32 would produce from the transformed float32 NCHW tensor.
+ * sunet_pack_label_u8: label uint8 [B][H][W] -> float32 {0,1} = (label/255).astype(uint8), same flips. */
+int sunet_pack_input_u8_im2col32(const void* img, const float* lut, const void* flip, void* out, int batch, int height,
+                                 int width, sunet_stream_t stream);
+int sunet_pack_label_u8(const void* label, const void* flip, float* out, int batch, int height, int width,
+                        sunet_stream_t stream);
 /* Conv2d weight [co][ci][3][3] -> wf [co][9*ci] (k = tap*ci_total + ci) and, if wd != NULL,
  * the dgrad operand wd [ci][9*co] (k = flipped_tap*co_total + co) */
 int sunet_pack_conv3x3_weights(const float* w, void* wf, void* wd, int cout, int cin, sunet_stream_t stream);

@@ -291,3 +291,25 @@ def synthetic_batch(batch: int, size: int, seed: int = 0, in_ch: int = 3, p_labe
     g2 = torch.Generator().manual_seed(seed + 1)
     label = (torch.rand(batch, size, size, generator=g2) < p_label).float()
     return x, label
+
+
+# ------------------------------------------------------------------ input transforms (SURVEY.md §8(f) "next" #2)
+def input_lut(mean: float = 0.5, std: float = 0.5) -> np.ndarray:
+    """float32 value of every input byte after PatchDataset.__getitem__'s ``input/255.0`` -> float32
+    (utils/data_utils.py:216-217) and Normalization (:100), with numpy's own arithmetic."""
+    x = (np.arange(256, dtype=np.uint8) / 255.0).astype(np.float32)
+    return ((x - mean) / std).astype(np.float32)
+
+
+def input_transform(img_u8: np.ndarray, label_u8: np.ndarray, flip: int = 0, mean: float = 0.5, std: float = 0.5):
+    """One sample through PatchDataset.__getitem__ (:216-219), Normalization (:94-105), RandomFlip (:107-126, with the
+    two coin flips decided by the caller: bit 0 = left-right, bit 1 = up-down) and ToTensor (:159-168).
+    img_u8 [H,W,3], label_u8 [H,W] -> (float32 [3,H,W], int64 [H,W])."""
+    x, lab = img_u8 / 255.0, label_u8 / 255.0
+    x, lab = x.astype(np.float32), lab.astype(np.uint8)
+    x = (x - mean) / std
+    if flip & 1:
+        lab, x = np.fliplr(lab).copy(), np.fliplr(x)
+    if flip & 2:
+        lab, x = np.flipud(lab).copy(), np.flipud(x)
+    return np.ascontiguousarray(x.transpose((2, 0, 1)).astype(np.float32)), lab.astype(np.int64)

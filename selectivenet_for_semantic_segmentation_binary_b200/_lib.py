@@ -78,6 +78,8 @@ SIGNATURES = {
     "sunet_pack_input_im2col": [_vp, _vp, _i, _i, _i, _i, _vp],
     "sunet_pack_input_im2col32": [_vp, _vp, _i, _i, _i, _i, _vp],
     "sunet_pack_conv1_pair_weights": [_vp, _vp, _i, _i, _vp],
+    "sunet_pack_input_u8_im2col32": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "sunet_pack_label_u8": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "sunet_pack_conv3x3_weights": [_vp, _vp, _vp, _i, _i, _vp],
     "sunet_pack_conv1_weights": [_vp, _vp, _i, _i, _vp],
     "sunet_pack_convT_weights": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],

@@ -134,6 +134,62 @@ pack_input_im2col32_kernel(const float* __restrict__ x, bf16x8* __restrict__ out
   }
 }
 
+// Device-side input pipeline (SURVEY.md §8(f) "next" #2; /root/reference/utils/data_utils.py:94-126,159-168,216-219):
+// uint8 HWC patch -> /255 -> Normalization(mean, std) -> RandomFlip -> CHW float32, fused with the first layer's
+// im2col.  The byte -> float32 map is a 256-entry table built on the host with numpy's own arithmetic, so the values
+// are bit-identical to the reference's; flips are index arithmetic (bit 0: left-right, bit 1: up-down, per image).
+__global__ void __launch_bounds__(256)
+pack_input_u8_im2col32_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut,
+                              const uint8_t* __restrict__ flip, bf16x8* __restrict__ out, int B, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float s_lut[256];
+  s_lut[threadIdx.x] = __ldg(lut + threadIdx.x);
+  __syncthreads();
+  const uint32_t total = (uint32_t)B * H * W;
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+    const uint32_t rowi = pix / (uint32_t)W;
+    const int xx = (int)(pix - rowi * (uint32_t)W);
+    const int n = (int)(rowi / (uint32_t)H);
+    const int yy = (int)(rowi - (uint32_t)n * (uint32_t)H);
+    const int f = flip ? flip[n] : 0;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+        const int iy = (f & 2) ? H - 1 - sy : sy, ix = (f & 1) ? W - 1 - sx : sx;
+        const uint8_t* src = img + (((size_t)n * H + iy) * W + ix) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) v[tap * 3 + ci] = s_lut[src[ci]];
+      }
+    }
+    bf16x8* o = out + (size_t)pix * 4;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) o[g] = pack8(v + g * 8);
+  }
+}
+
+// label bytes -> {0,1} float32 with the same flips: (label / 255.0).astype(uint8) is 1 only for 255
+__global__ void __launch_bounds__(256)
+pack_label_u8_kernel(const uint8_t* __restrict__ label, const uint8_t* __restrict__ flip, float* __restrict__ out,
+                     int B, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t total = (uint32_t)B * H * W;
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+    const uint32_t rowi = pix / (uint32_t)W;
+    const int xx = (int)(pix - rowi * (uint32_t)W);
+    const int n = (int)(rowi / (uint32_t)H);
+    const int yy = (int)(rowi - (uint32_t)n * (uint32_t)H);
+    const int f = flip ? flip[n] : 0;
+    const int iy = (f & 2) ? H - 1 - yy : yy, ix = (f & 1) ? W - 1 - xx : xx;
+    out[pix] = label[((size_t)n * H + iy) * W + ix] == 255 ? 1.f : 0.f;
+  }
+}
+
 // weights of the paired-pixel first layer: wf[128][64]; row n < 64: [w_n (k = tap*cin+ci, 32 wide) | 0],
 // row 64 + n: [0 | w_n] — a plain GEMM over pixel PAIRS then yields both pixels' 64 outputs side by side.
 __device__ __forceinline__ float conv1_pair_weight(const float* __restrict__ w, int cin, int i) {
@@ -1003,6 +1059,29 @@ extern "C" int sunet_pack_input_im2col32(const float* x, void* out, int batch, i
     launch_k(pack_input_im2col32_kernel<2>, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM, x,
              reinterpret_cast<bf16x8*>(out), batch, height, width);
   return check_launch("pack_input_im2col32");
+}
+
+extern "C" int sunet_pack_input_u8_im2col32(const void* img, const float* lut, const void* flip, void* out, int batch,
+                                            int height, int width, sunet_stream_t stream_) {
+  if (!img || !lut || !out || batch <= 0 || height <= 0 || width <= 0 || (width & 1))
+    return set_error(SUNET_ERR_INVALID, "pack_input_u8_im2col32: bad arguments (width=%d)", width);
+  const long long total = (long long)batch * height * width;
+  if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "pack_input_u8_im2col32: tensor too large");
+  launch_k(pack_input_u8_im2col32_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM,
+           reinterpret_cast<const uint8_t*>(img), lut, reinterpret_cast<const uint8_t*>(flip),
+           reinterpret_cast<bf16x8*>(out), batch, height, width);
+  return check_launch("pack_input_u8_im2col32");
+}
+
+extern "C" int sunet_pack_label_u8(const void* label, const void* flip, float* out, int batch, int height, int width,
+                                   sunet_stream_t stream_) {
+  if (!label || !out || batch <= 0 || height <= 0 || width <= 0)
+    return set_error(SUNET_ERR_INVALID, "pack_label_u8: bad arguments");
+  const long long total = (long long)batch * height * width;
+  if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "pack_label_u8: tensor too large");
+  launch_k(pack_label_u8_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM,
+           reinterpret_cast<const uint8_t*>(label), reinterpret_cast<const uint8_t*>(flip), out, batch, height, width);
+  return check_launch("pack_label_u8");
 }
 
 extern "C" int sunet_pack_conv1_pair_weights(const float* w, void* wf, int cout, int cin, sunet_stream_t stream_) {

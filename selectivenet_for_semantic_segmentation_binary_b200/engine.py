@@ -340,13 +340,18 @@ class SUNetPlan:
 
     def forward(self, x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor],
                 training: bool) -> torch.Tensor:
-        """x: fp32 NCHW on this plan's device.  Returns the plan-owned logits buffer [nheads, P]."""
-        assert x.shape == (self.B, self.in_ch, self.H, self.W), (x.shape, (self.B, self.in_ch, self.H, self.W))
+        """x: fp32 NCHW on this plan's device, or None when the caller has already filled ``self.col`` (the uint8
+        input pipeline, kernels.pack_input_u8_im2col32).  Returns the plan-owned logits buffer [nheads, P]."""
         self.pack_weights(params)
-        if self.first_pair:
-            K.pack_input_im2col32(x, self.col)
+        if x is None:
+            if not self.first_pair:
+                raise RuntimeError("the uint8 input pipeline needs the paired-pixel first layer (SUNET_FIRST_PAIR=1)")
         else:
-            K.pack_input_im2col(x, self.col)
+            assert x.shape == (self.B, self.in_ch, self.H, self.W), (x.shape, (self.B, self.in_ch, self.H, self.W))
+            if self.first_pair:
+                K.pack_input_im2col32(x, self.col)
+            else:
+                K.pack_input_im2col(x, self.col)
         L = self.layers
         for name in ("encoder_layer_1_1", "encoder_layer_1_2", "encoder_layer_2_1", "encoder_layer_2_2",
                      "encoder_layer_3_1", "encoder_layer_3_2", "decoder_layer_4_2", "decoder_layer_4_1"):

@@ -166,6 +166,27 @@ def pack_input_im2col32(x: torch.Tensor, out: torch.Tensor) -> None:
                "sunet_pack_input_im2col32")
 
 
+def pack_input_u8_im2col32(img: torch.Tensor, lut: torch.Tensor, flip: Optional[torch.Tensor],
+                           out: torch.Tensor) -> None:
+    """uint8 [B,H,W,3] patches (+ per-image flip bits) -> the first layer's [B,H,W,32] bf16 operand."""
+    B, H, W, Cc = img.shape
+    assert img.dtype == torch.uint8 and img.is_contiguous() and img.is_cuda and Cc == 3
+    assert lut.dtype == torch.float32 and lut.numel() == 256 and lut.is_cuda and lut.is_contiguous()
+    assert flip is None or (flip.dtype == torch.uint8 and flip.numel() == B and flip.is_cuda)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and tuple(out.shape) == (B, H, W, 32)
+    _lib.check(_lib.load().sunet_pack_input_u8_im2col32(img.data_ptr(), lut.data_ptr(), _ptr(flip), out.data_ptr(), B, H,
+                                                        W, _stream()), "sunet_pack_input_u8_im2col32")
+
+
+def pack_label_u8(label: torch.Tensor, flip: Optional[torch.Tensor], out: torch.Tensor) -> None:
+    B, H, W = label.shape
+    assert label.dtype == torch.uint8 and label.is_contiguous() and label.is_cuda
+    assert flip is None or (flip.dtype == torch.uint8 and flip.numel() == B and flip.is_cuda)
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, H, W)
+    _lib.check(_lib.load().sunet_pack_label_u8(label.data_ptr(), _ptr(flip), out.data_ptr(), B, H, W, _stream()),
+               "sunet_pack_label_u8")
+
+
 def pack_conv1_pair_weights(w, wf) -> None:
     co, ci = w.shape[0], w.shape[1]
     assert wf.dtype == torch.bfloat16 and wf.is_contiguous() and tuple(wf.shape) == (128, 64)

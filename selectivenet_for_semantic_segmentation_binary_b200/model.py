@@ -116,6 +116,18 @@ class UNet_B(nn.Module):
     def _buffer_dict(self) -> Dict[str, torch.Tensor]:
         return dict(self.named_buffers())
 
+    def _plan_for_shape(self, batch: int, height: int, width: int, device) -> SUNetPlan:
+        """Plan lookup by shape (the uint8 input pipeline has no float32 NCHW tensor to derive it from)."""
+        device = torch.device(device)
+        key = (batch, height, width, device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 4:
+                self._plans.pop(next(iter(self._plans)))
+            plan = SUNetPlan(batch, height, width, self.input_ch, self.selective, device)
+            self._plans[key] = plan
+        return plan
+
     def _plan_for(self, x: torch.Tensor) -> SUNetPlan:
         if not x.is_cuda:
             raise RuntimeError("UNet_B (B200-native) has no CPU path: move the input and the model to a CUDA device")

@@ -67,15 +67,27 @@ class SUNetTrainer:
         import os
         self._buckets = bucket_plan(self._ranges, self.fg.total, os.environ.get("SUNET_DP_BUCKETS", DEFAULT_BUCKETS))
         self.launches_per_step = 0
+        self.input_lut = None          # set_input_normalization(): byte -> float32 table of the uint8 pipeline
+        self._u8 = None                # static (img, label_u8, flip, label_f32, dlogits) buffers + graph of step_u8
+        self._u8_graph = None
+        self._u8_warm = 0
         self.global_pixels_override = 0
 
     def set_lr(self, lr: float) -> None:
         self.lr_dev.fill_(lr)
 
     # ------------------------------------------------------------------ one step, eager
-    def _step_impl(self, x: torch.Tensor, label: torch.Tensor, dl: torch.Tensor) -> None:
+    def _step_impl(self, x: torch.Tensor, label: torch.Tensor, dl: torch.Tensor, u8=None) -> None:
+        """u8 = (img uint8 [B,H,W,3], label uint8 [B,H,W], flip uint8 [B] or None): the device-side input pipeline;
+        x is then None and `label` is the float32 buffer the label kernel fills."""
         net = self.net
-        plan = net._plan_for(x)
+        if u8 is not None:
+            img, lab_u8, flip = u8
+            plan = net._plan_for_shape(img.shape[0], img.shape[1], img.shape[2], img.device)
+            K.pack_input_u8_im2col32(img, self.input_lut, flip, plan.col)
+            K.pack_label_u8(lab_u8, flip, label)
+        else:
+            plan = net._plan_for(x)
         logits = plan.forward(x, self.params, self.buffers, True)
         lab = label.reshape(-1)
         P = plan.P
@@ -119,6 +131,48 @@ class SUNetTrainer:
             B, H, W = plan.B, plan.H, plan.W
             self.evaluator.add_batch_from_logits(label.reshape(B, H, W), logits[0].view(B, H, W),
                                                  logits[1].view(B, H, W) if self.selective else None, path='train')
+
+    # ------------------------------------------------------------------ uint8 input pipeline
+    def set_input_normalization(self, mean: float = 0.5, std: float = 0.5) -> None:
+        """Byte -> float32 table of ``(b/255 - mean)/std`` built with numpy's arithmetic, i.e. the values the
+        reference's PatchDataset + Normalization produce (utils/data_utils.py:100,216-217)."""
+        import numpy as np
+        x = (np.arange(256, dtype=np.uint8) / 255.0).astype(np.float32)
+        self.input_lut = torch.from_numpy(((x - mean) / std).astype(np.float32)).to(self.device)
+
+    def step_u8(self, img: torch.Tensor, label: torch.Tensor, flip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One training step straight from decoded patches: img uint8 [N,H,W,3], label uint8 [N,H,W] (PNG values,
+        255 = tumour), flip uint8 [N] (bit 0 left-right, bit 1 up-down — RandomFlip's two coin flips, drawn by the
+        caller).  Normalisation, flips, NHWC/bf16 conversion and the first layer's im2col are one kernel; 4x less
+        host->device traffic than float32 tensors.  Same return value as step()."""
+        if not img.is_cuda or not label.is_cuda or img.dtype != torch.uint8 or label.dtype != torch.uint8:
+            raise RuntimeError("SUNetTrainer.step_u8: uint8 CUDA tensors expected")
+        if self.input_lut is None:
+            self.set_input_normalization()
+        N, H, W, _ = img.shape
+        if flip is None:
+            flip = torch.zeros(N, dtype=torch.uint8, device=self.device)
+        plan = self.net._plan_for_shape(N, H, W, self.device)
+        if self._u8 is None or tuple(self._u8[0].shape) != tuple(img.shape):
+            self._u8 = (torch.empty_like(img), torch.empty_like(label), torch.empty_like(flip),
+                        torch.empty(N, H, W, device=self.device), torch.empty(plan.nheads, plan.P, device=self.device))
+            self._u8_graph, self._u8_warm = None, 0
+        si, sl, sf, lab32, dl = self._u8
+        si.copy_(img, non_blocking=True)
+        sl.copy_(label, non_blocking=True)
+        sf.copy_(flip, non_blocking=True)
+        if not self.use_graph or self._u8_warm < 2:
+            self._step_impl(None, lab32, dl, u8=(si, sl, sf))
+            self._u8_warm += 1
+            return self.results
+        if self._u8_graph is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g):
+                self._step_impl(None, lab32, dl, u8=(si, sl, sf))
+            self._u8_graph = g
+        self._u8_graph.replay()
+        return self.results
 
     # ------------------------------------------------------------------ public
     def step(self, x: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
@@ -189,6 +243,8 @@ def bucket_plan(ranges, total: int, spec: str):
             hi = lo
     assert hi == 0
     return out
+
+
 
 
 def chunk_bounds(total: int, world: int, rank: int):

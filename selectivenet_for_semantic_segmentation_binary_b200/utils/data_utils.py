@@ -51,3 +51,45 @@ class PatchArrays:
         for i in range(0, len(order) - batch_size + 1, batch_size):
             xs, ys = zip(*(self._load(self.ids[j]) for j in order[i:i + batch_size]))
             yield torch.from_numpy(np.stack(xs)), torch.from_numpy(np.stack(ys))
+
+
+# ------------------------------------------------------------------ the reference's transform objects
+# Same names / call convention as /root/reference/utils/data_utils.py:94-126,159-168 (dict in, dict out) for scripts
+# that build ``transforms.Compose([Normalization(0.5, 0.5), RandomFlip(), ToTensor()])``.  The fast path does not use
+# them: ``SUNetTrainer.step_u8`` takes the decoded uint8 patches plus the two coin flips per image and performs
+# normalisation, flips, layout and the first layer's im2col in one kernel (kernels.pack_input_u8_im2col32).
+class Normalization:
+    def __init__(self, mean=0.5, std=0.5):
+        self.mean, self.std = mean, std
+
+    def __call__(self, data):
+        data['input'] = (data['input'] - self.mean) / self.std
+        return data
+
+
+class RandomFlip:
+    """Left-right, then up-down, each with probability 1/2 (two ``np.random.rand()`` draws per sample)."""
+
+    @staticmethod
+    def draw() -> int:
+        """The two coin flips as the bit mask step_u8 expects (bit 0 left-right, bit 1 up-down)."""
+        lr = np.random.rand() > 0.5
+        ud = np.random.rand() > 0.5
+        return int(lr) | (int(ud) << 1)
+
+    def __call__(self, data):
+        bits = self.draw()
+        label, image = data['label'], data['input']
+        if bits & 1:
+            label, image = np.fliplr(label).copy(), np.fliplr(image)
+        if bits & 2:
+            label, image = np.flipud(label).copy(), np.flipud(image)
+        data['input'], data['label'] = image, label
+        return data
+
+
+class ToTensor:
+    def __call__(self, data):
+        data['input'] = torch.from_numpy(np.ascontiguousarray(data['input'].transpose((2, 0, 1)).astype(np.float32)))
+        data['label'] = torch.from_numpy(np.ascontiguousarray(data['label'])).type(torch.LongTensor)
+        return data
