@@ -236,13 +236,15 @@ int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float* scale, con
                         sunet_stream_t stream);
 /* sunet_heads_bwd with the activation recomputed from y = the last block's conv output (nothing but y is read),
  * plus that block's BatchNorm-backward reduction: bn_partials[sunet_heads_bwd_bn_rows(pixels)][64][2] receives
- * per-block (sum g, sum g*xhat), g = dA where relu(bn(y)) > 0 — the rows sunet_bn_bwd_apply() folds. */
+ * per-block (sum g, sum g*xhat), g = dA where relu(bn(y)) > 0 — the rows sunet_bn_bwd_apply() folds.
+ * addend (optional, NHWC bf16, may alias dA): gradient of the same activation from heads handled by an earlier call
+ * (model.py:106-191 `UNet` has 2 x 3 head channels); it is added before rounding and enters the reduction rows. */
 int sunet_heads_bwd_bn_rows(long long pixels);
 int sunet_heads_bwd_bn(const float* dlogits, const void* y, int y_pix_stride, const float* scale, const float* shift,
                        const float* mean, const float* invstd, const float* w0, const float* w1, const float* w2,
                        int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0, float* dw1, float* db1,
-                       float* dw2, float* db2, float* bn_partials, long long pixels, void* workspace,
-                       size_t workspace_bytes, sunet_stream_t stream);
+                       float* dw2, float* db2, float* bn_partials, const void* addend, int addend_pix_stride,
+                       long long pixels, void* workspace, size_t workspace_bytes, sunet_stream_t stream);
 /* dA[p][c] = sum_h dl[h][p]*w_h[c] (bf16);  dw_h[c] = sum_p dl[h][p]*a[p][c];  db_h = sum_p dl[h][p] */
 int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,
                     const float* w2, int nheads, void* dA, int dA_pix_stride, float* dw0, float* db0, float* dw1,

@@ -51,7 +51,8 @@ def input_channels(input_type: str) -> int:
     raise ValueError(input_type)
 
 
-def init_state_dict(seed: int, input_type: str = "RGB", selective: bool = True) -> "OrderedDict[str, torch.Tensor]":
+def init_state_dict(seed: int, input_type: str = "RGB", selective: bool = True,
+                    n_cls: int = 1) -> "OrderedDict[str, torch.Tensor]":
     """Default-initialised parameters/buffers in the reference's key order (Appendix B of SURVEY.md).
 
     Restates the constructor model.py:19-66: layers are created in the same order with the same
@@ -78,7 +79,8 @@ def init_state_dict(seed: int, input_type: str = "RGB", selective: bool = True) 
             sd[f"{name}.1.num_batches_tracked"] = bn.num_batches_tracked.detach().clone()
     heads = ["conv1x1"] + (["conv_select", "conv_aux"] if selective else [])
     for h in heads:
-        m = torch.nn.Conv2d(64, 1, kernel_size=1)
+        # n_cls = 1: UNet_B (model.py:62-66); n_cls = 2: UNet (model.py:151-155, conv_select always has 2 channels)
+        m = torch.nn.Conv2d(64, n_cls if h != "conv_select" else (1 if n_cls == 1 else 2), kernel_size=1)
         sd[f"{h}.weight"] = m.weight.detach().clone()
         sd[f"{h}.bias"] = m.bias.detach().clone()
     return sd
@@ -131,7 +133,11 @@ def unet_b_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, selective: bool
     if selective:
         select = F.conv2d(dec1_1, sd["conv_select.weight"], sd["conv_select.bias"])  # :99
         aux = F.conv2d(dec1_1, sd["conv_aux.weight"], sd["conv_aux.bias"])           # :100
+        if output.shape[1] != 1:            # UNet (CE variant), model.py:185-191: (N, C, H, W) outputs, no squeeze
+            return output, select, aux
         return torch.squeeze(output, 1), torch.squeeze(select, 1), torch.squeeze(aux, 1)  # :101
+    if output.shape[1] != 1:
+        return output
     return torch.squeeze(output, 1)                                                # :103
 
 
@@ -313,3 +319,32 @@ def input_transform(img_u8: np.ndarray, label_u8: np.ndarray, flip: int = 0, mea
     if flip & 2:
         lab, x = np.flipud(lab).copy(), np.flipud(x)
     return np.ascontiguousarray(x.transpose((2, 0, 1)).astype(np.float32)), lab.astype(np.int64)
+
+
+# ------------------------------------------------------------------ cross-entropy variant (SURVEY.md §8(f) "next" #3)
+def selective_risk_ce(output, selection, target, target_coverage=0.8, lamb=8) -> Tuple[torch.Tensor, torch.Tensor]:
+    """calc_selective_risk_image, selective_loss.py:24-56 (hard_selection=False): output/selection (N,C,H,W),
+    target (N,H,W) int64 class indices."""
+    onehot = torch.zeros(target.size(0), output.size(1), target.size(1), target.size(2)).scatter_(
+        1, target.view(target.size(0), 1, target.size(1), target.size(2)), 1)               # :40-41
+    sel = F.softmax(selection, dim=1)[:, 1, :, :]                                           # :43
+    coverage = torch.mean(sel)                                                              # :44
+    risk = -torch.mean(torch.sum(F.log_softmax(output, dim=1) * onehot, dim=1) * sel) / coverage   # :52
+    diff = torch.clamp(target_coverage - coverage, min=0)                                   # :53
+    return risk + lamb * diff * diff, coverage                                              # :54-56
+
+
+def train_losses_ce(sd, x, label, s_lamb=2, update_running=True):
+    """train.py:193-201 with --model_arch UNet --loss CE --selective 1: label is int64 (N,H,W)."""
+    out, sel, aux = unet_b_forward(sd, x, True, True, update_running)
+    aux_loss = F.cross_entropy(aux, label)                                                  # train.py:80,195
+    s_loss, cov = selective_risk_ce(out, sel, label, lamb=s_lamb)
+    return aux_loss + s_loss, dict(output=out, selection=sel, aux=aux, aux_loss=aux_loss, select_loss=s_loss,
+                                   coverage=cov)
+
+
+def postprocess_ce(output: np.ndarray, selection: Optional[np.ndarray]):
+    """train.py:216-226 for (N,C,H,W) outputs: argmax over the class axis (first maximum wins ties)."""
+    pred = np.argmax(output.transpose(0, 2, 3, 1), axis=-1).astype("uint8")
+    sel = None if selection is None else np.argmax(selection.transpose(0, 2, 3, 1), -1).astype("uint8")
+    return pred, sel

@@ -100,7 +100,7 @@ SIGNATURES = {
     "sunet_heads_bwd": [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _sz, _vp],
     "sunet_heads_bwd_bn_rows": [_ll],
     "sunet_heads_bwd_bn": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
-                           _vp, _ll, _vp, _sz, _vp],
+                           _vp, _vp, _i, _ll, _vp, _sz, _vp],
     "sunet_loss_sums": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _sz, _vp],
     "sunet_loss_finalize": [_vp, _ll, _f, _f, _vp, _vp],
     "sunet_loss_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _ll, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp],

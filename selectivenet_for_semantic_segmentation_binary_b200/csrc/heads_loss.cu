@@ -164,6 +164,8 @@ struct HeadBN {
   const float* mean;
   const float* invstd;
   float* partials;     // [gridDim.x][64][2]
+  const __nv_bfloat16* addend;   // optional: gradient of the same activation from heads handled by an earlier call
+  int adds;                      // its pixel stride (may alias dA: each element is read and then written by one thread)
 };
 
 // shared-memory load the compiler may not hoist out of the pixel loop (it would turn back into 48 registers)
@@ -238,8 +240,13 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
             a0 = bf16lo(r);
             a1 = bf16hi(r);
           }
-          const float o0 = g[u][0] * w0.x + g[u][1] * w1.x + g[u][2] * w2.x;
-          const float o1 = g[u][0] * w0.y + g[u][1] * w1.y + g[u][2] * w2.y;
+          float o0 = g[u][0] * w0.x + g[u][1] * w1.x + g[u][2] * w2.x;
+          float o1 = g[u][0] * w0.y + g[u][1] * w1.y + g[u][2] * w2.y;
+          if (BN && bn.addend != nullptr) {     // more than three heads (UNet, n_cls = 2): second call adds the first
+            const uint32_t aw = *reinterpret_cast<const uint32_t*>(bn.addend + p * bn.adds + c);
+            o0 += bf16lo(aw);
+            o1 += bf16hi(aw);
+          }
 #pragma unroll
           for (int h = 0; h < 3; ++h) {
             dw[h][2 * i] = fmaf(g[u][h], a0, dw[h][2 * i]);
@@ -536,7 +543,7 @@ extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_st
   const size_t need = (size_t)blocks * 195 * sizeof(float);
   if (workspace_bytes < need) return set_error(SUNET_ERR_WORKSPACE, "heads_bwd: workspace %zu < %zu", workspace_bytes, need);
   float* partials = reinterpret_cast<float*>(workspace);
-  HeadBN nobn = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  HeadBN nobn = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   launch_k(heads_bwd_kernel<false>, dim3(blocks), dim3(256), 0, STREAM, dlogits,
            reinterpret_cast<const __nv_bfloat16*>(a), a_pix_stride, hw, nheads, reinterpret_cast<__nv_bfloat16*>(dA),
            dA_pix_stride, partials, pixels, nobn);
@@ -555,8 +562,8 @@ extern "C" int sunet_heads_bwd_bn(const float* dlogits, const void* y, int y_pix
                                   const float* shift, const float* mean, const float* invstd, const float* w0,
                                   const float* w1, const float* w2, int nheads, void* dA, int dA_pix_stride,
                                   float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2,
-                                  float* bn_partials, long long pixels, void* workspace, size_t workspace_bytes,
-                                  sunet_stream_t stream_) {
+                                  float* bn_partials, const void* addend, int addend_pix_stride, long long pixels,
+                                  void* workspace, size_t workspace_bytes, sunet_stream_t stream_) {
   if (!dlogits || !y || !dA || !workspace || !scale || !shift || !mean || !invstd || !bn_partials || pixels <= 0 ||
       (nheads != 1 && nheads != 3) || y_pix_stride < 64 || y_pix_stride % 8 || dA_pix_stride < 64 ||
       dA_pix_stride % 8)
@@ -569,7 +576,10 @@ extern "C" int sunet_heads_bwd_bn(const float* dlogits, const void* y, int y_pix
   if (workspace_bytes < need)
     return set_error(SUNET_ERR_WORKSPACE, "heads_bwd_bn: workspace %zu < %zu", workspace_bytes, need);
   float* partials = reinterpret_cast<float*>(workspace);
-  HeadBN bn = {scale, shift, mean, invstd, bn_partials};
+  if (addend && (addend_pix_stride < 64 || addend_pix_stride % 8))
+    return set_error(SUNET_ERR_INVALID, "heads_bwd_bn: bad addend stride");
+  HeadBN bn = {scale, shift, mean, invstd, bn_partials, reinterpret_cast<const __nv_bfloat16*>(addend),
+               addend_pix_stride};
   launch_k(heads_bwd_kernel<true>, dim3(blocks), dim3(256), 0, STREAM, dlogits,
            reinterpret_cast<const __nv_bfloat16*>(y), y_pix_stride, hw, nheads, reinterpret_cast<__nv_bfloat16*>(dA),
            dA_pix_stride, partials, pixels, bn);

@@ -60,11 +60,16 @@ class _Layer:
 
 
 class SUNetPlan:
-    def __init__(self, batch: int, height: int, width: int, in_ch: int, selective: bool, device):
+    def __init__(self, batch: int, height: int, width: int, in_ch: int, selective: bool, device, n_cls: int = 1):
         if height % 8 or width % 8:
             raise ValueError("UNet_B needs H and W divisible by 8 (three 2x2 pools)")
         self.B, self.H, self.W, self.in_ch, self.selective = batch, height, width, in_ch, selective
         self.device = torch.device(device)
+        # n_cls = 1: UNet_B (one logit per head); n_cls = 2: the reference's `UNet` (model.py:106-191), whose heads
+        # have two output channels each.  Logit row c * nheads + h = channel c of head h.
+        if n_cls not in (1, 2):
+            raise NotImplementedError("n_cls must be 1 (UNet_B) or 2 (UNet): the metrics are binary (SURVEY.md §2)")
+        self.n_cls = n_cls
         self.nheads = 3 if selective else 1
         dev = self.device
         bf = torch.bfloat16
@@ -136,7 +141,7 @@ class SUNetPlan:
                                b4=torch.empty(4 * co, device=dev))
         P = B * height * width
         self.P = P
-        self.logits = torch.empty(self.nheads, P, device=dev)
+        self.logits = torch.empty(self.n_cls * self.nheads, P, device=dev)
 
         # ---- backward scratch
         self.gA = {L: act(L, _CH[L]) for L in (1, 2, 3, 4)}
@@ -332,8 +337,10 @@ class SUNetPlan:
         if n == "decoder_layer_1_1":
             # last block: BN + ReLU fused with the three 1x1 heads
             heads = ["conv1x1"] + (["conv_select", "conv_aux"] if self.selective else [])
-            K.bn_relu_heads(ly.y, ly.scale, ly.shift, ly.a, [params[f"{h}.weight"] for h in heads],
-                            [params[f"{h}.bias"] for h in heads], self.logits)
+            for c in range(self.n_cls):          # one pass over y per output channel of the heads
+                K.bn_relu_heads(ly.y, ly.scale, ly.shift, ly.a if c == 0 else None,
+                                [params[f"{h}.weight"][c] for h in heads], [params[f"{h}.bias"][c:c + 1] for h in heads],
+                                self.logits[c * self.nheads:(c + 1) * self.nheads])
         else:
             K.bn_relu_pool(ly.y, ly.scale, ly.shift, ly.a, self.pool[ly.level] if ly.pool else None,
                            ywin=self.ywin.get(ly.level) if (ly.pool and training) else None)
@@ -477,11 +484,18 @@ class SUNetPlan:
         B = self.B
         heads = ["conv1x1"] + (["conv_select", "conv_aux"] if self.selective else [])
         last = L["decoder_layer_1_1"]
+        nh = self.nheads
         if self.fuse_heads_bn:
-            K.heads_bwd_bn(dlogits, last.y, last.scale, last.shift, last.mean, last.invstd,
-                           [params[f"{h}.weight"] for h in heads], self.gA[1], [grads[f"{h}.weight"] for h in heads],
-                           [grads[f"{h}.bias"] for h in heads], last.bnb_stats, self.ws)
+            # channel c of every head per call; the second call (UNet, n_cls = 2) adds the first call's gradient
+            # and writes the reduction rows of the total
+            for c in range(self.n_cls):
+                K.heads_bwd_bn(dlogits[c * nh:(c + 1) * nh], last.y, last.scale, last.shift, last.mean, last.invstd,
+                               [params[f"{h}.weight"][c] for h in heads], self.gA[1],
+                               [grads[f"{h}.weight"][c] for h in heads], [grads[f"{h}.bias"][c:c + 1] for h in heads],
+                               last.bnb_stats, self.ws, addend=self.gA[1] if c > 0 else None)
         else:
+            if self.n_cls != 1:
+                raise RuntimeError("UNet (n_cls = 2) needs SUNET_FUSE_HEADS_BN=1")
             K.heads_bwd(dlogits, last.a, [params[f"{h}.weight"] for h in heads], self.gA[1],
                         [grads[f"{h}.weight"] for h in heads], [grads[f"{h}.bias"] for h in heads], self.ws)
         dA = self.gA[1]

@@ -337,8 +337,10 @@ def heads_bwd_bn_rows(pixels: int) -> int:
     return int(_lib.load().sunet_heads_bwd_bn_rows(pixels))
 
 
-def heads_bwd_bn(dlogits, y, scale, shift, mean, invstd, weights, dA, dws, dbs, bn_partials, workspace) -> None:
-    """heads_bwd on y (activation recomputed) + the last block's BN-backward reduction rows into bn_partials."""
+def heads_bwd_bn(dlogits, y, scale, shift, mean, invstd, weights, dA, dws, dbs, bn_partials, workspace,
+                 addend=None) -> None:
+    """heads_bwd on y (activation recomputed) + the last block's BN-backward reduction rows into bn_partials.
+    addend: gradient of the same activation from heads handled by an earlier call (may be dA itself)."""
     yp, _, ys = _act(y)
     dp, _, ds = _act(dA)
     n = len(weights)
@@ -351,7 +353,9 @@ def heads_bwd_bn(dlogits, y, scale, shift, mean, invstd, weights, dA, dws, dbs, 
     assert bn_partials.numel() >= heads_bwd_bn_rows(P) * 64 * 2
     _lib.check(_lib.load().sunet_heads_bwd_bn(dlogits.data_ptr(), yp, ys, _f32(scale), _f32(shift), _f32(mean),
                                               _f32(invstd), w[0], w[1], w[2], n, dp, ds, dw[0], db[0], dw[1], db[1],
-                                              dw[2], db[2], bn_partials.data_ptr(), P, workspace.data_ptr(),
+                                              dw[2], db[2], bn_partials.data_ptr(),
+                                              None if addend is None else _act(addend)[0],
+                                              0 if addend is None else _act(addend)[2], P, workspace.data_ptr(),
                                               workspace.numel(), _stream()), "sunet_heads_bwd_bn")
 
 

@@ -41,7 +41,7 @@ class _UNetBFunction(torch.autograd.Function):
         logits = plan.forward(x.contiguous(), params, buffers, training)
         ctx.net, ctx.plan, ctx.generation = net, plan, plan.generation
         B, H, W = plan.B, plan.H, plan.W
-        outs = tuple(logits[h].view(B, H, W).clone() for h in range(plan.nheads))
+        outs = tuple(logits[h].view(B, H, W).clone() for h in range(plan.n_cls * plan.nheads))
         return outs
 
     @staticmethod
@@ -51,7 +51,7 @@ class _UNetBFunction(torch.autograd.Function):
             raise RuntimeError("UNet_B.backward: the activation buffers of this forward pass were overwritten by a "
                                "later forward pass (one in-flight training step per model/shape)")
         P = plan.P
-        dl = torch.empty(plan.nheads, P, device=plan.device)
+        dl = torch.empty(plan.n_cls * plan.nheads, P, device=plan.device)
         for h, d in enumerate(douts):
             if d is None:
                 dl[h].zero_()
@@ -67,6 +67,8 @@ class _UNetBFunction(torch.autograd.Function):
 
 
 class UNet_B(nn.Module):
+    _N_CLS = 1          # output channels per head; the `UNet` subclass (CE variant) has 2
+
     def __init__(self, input_type='RGB', selective=False):
         super(UNet_B, self).__init__()
         self.selective = selective
@@ -101,13 +103,16 @@ class UNet_B(nn.Module):
                                           bias=True)
         self.decoder_layer_1_2 = CBR_2D(in_ch=128, out_ch=64)
         self.decoder_layer_1_1 = CBR_2D(in_ch=64, out_ch=64)
+        self._build_heads()
+
+        self._plans: Dict[Tuple, SUNetPlan] = {}
+        self._fg = None
+
+    def _build_heads(self):
         self.conv1x1 = nn.Conv2d(in_channels=64, out_channels=1, kernel_size=1)
         if self.selective:
             self.conv_select = nn.Conv2d(64, 1, 1)
             self.conv_aux = nn.Conv2d(64, 1, 1)
-
-        self._plans: Dict[Tuple, SUNetPlan] = {}
-        self._fg = None
 
     # ------------------------------------------------------------------ plumbing
     def _param_dict(self) -> Dict[str, torch.Tensor]:
@@ -124,7 +129,7 @@ class UNet_B(nn.Module):
         if plan is None:
             if len(self._plans) >= 4:
                 self._plans.pop(next(iter(self._plans)))
-            plan = SUNetPlan(batch, height, width, self.input_ch, self.selective, device)
+            plan = SUNetPlan(batch, height, width, self.input_ch, self.selective, device, n_cls=self._N_CLS)
             self._plans[key] = plan
         return plan
 
@@ -143,7 +148,8 @@ class UNet_B(nn.Module):
         if plan is None:
             if len(self._plans) >= 4:        # plans own GBs of activations: keep a few shapes only
                 self._plans.pop(next(iter(self._plans)))
-            plan = SUNetPlan(x.shape[0], x.shape[2], x.shape[3], self.input_ch, self.selective, x.device)
+            plan = SUNetPlan(x.shape[0], x.shape[2], x.shape[3], self.input_ch, self.selective, x.device,
+                             n_cls=self._N_CLS)
             self._plans[key] = plan
         return plan
 
@@ -169,3 +175,34 @@ class UNet_B(nn.Module):
         if self.selective:
             return outs[0], outs[1], outs[2]
         return outs[0]
+
+
+class UNet(UNet_B):
+    """The reference's cross-entropy variant (/root/reference/model.py:106-191): same trunk, heads with ``n_cls``
+    output channels — ``conv1x1`` 64 -> n_cls, ``conv_select`` 64 -> 2, ``conv_aux`` 64 -> n_cls — and outputs of shape
+    ``(N, C, H, W)``.  Only ``n_cls == 2`` is built (the task and the Evaluator are binary).  Same
+    kernels as UNet_B: the fused BN+ReLU+heads pass and the heads backward run once per output channel, the second
+    backward call adding the first call's activation gradient before the BatchNorm reduction."""
+    _N_CLS = 2
+
+    def __init__(self, input_type='RGB', n_cls=2, selective=False):
+        if n_cls != 2:
+            raise NotImplementedError("UNet: only n_cls = 2 is implemented (binary segmentation)")
+        self.n_cls = n_cls
+        super(UNet, self).__init__(input_type, selective)
+
+    def _build_heads(self):
+        self.conv1x1 = nn.Conv2d(in_channels=64, out_channels=self.n_cls, kernel_size=1, stride=1)
+        if self.selective:
+            self.conv_select = nn.Conv2d(64, 2, 1, 1)
+            self.conv_aux = nn.Conv2d(64, self.n_cls, 1, 1)
+
+    def forward(self, x):
+        params = self._param_dict()
+        order = param_order(self.selective)
+        rows = _UNetBFunction.apply(self, x, self.training, *[params[n] for n in order])
+        nh = 3 if self.selective else 1
+        heads = [torch.stack([rows[c * nh + h] for c in range(2)], dim=1) for h in range(nh)]    # (N, 2, H, W)
+        if self.selective:
+            return heads[0], heads[1], heads[2]
+        return heads[0]

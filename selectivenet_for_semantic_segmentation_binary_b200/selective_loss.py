@@ -138,3 +138,40 @@ class BCEWithLogitsLoss(torch.nn.Module):
 
     def forward(self, input, target):
         return _BCEMean.apply(input, target)
+
+
+# ------------------------------------------------------------------ cross-entropy variant (`UNet`, n_cls = 2)
+# For two classes, log_softmax(z)[t] = -bce_with_logits(z1 - z0, t) and softmax(s)[1] = sigmoid(s1 - s0), so the
+# reference's CE losses are the binary losses above applied to the channel differences; autograd carries the
+# gradient back through the subtraction (d/dz1 = g, d/dz0 = -g).
+def _logit_difference(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() != 4 or x.shape[1] != 2:
+        raise NotImplementedError("only two-class (N, 2, H, W) logits are implemented")
+    return x[:, 1] - x[:, 0]
+
+
+def calc_selective_risk_image(output, selection, target, target_coverage=0.8, lamb=8, hard_selection=False):
+    """
+    the modificated selective risk for image segmentation with Cross Entropy Loss (2 classes)
+
+    Args
+        output: (N, 2, H, W)
+        selection: (N, 2, H, W)
+        target: (N, H, W) class indices, or (N, 2, H, W) one-hot
+    Return
+        selective loss, coverage          (selective_loss.py:24-56)
+    """
+    if hard_selection:
+        raise NotImplementedError("hard_selection=True is dead code in the reference and is not implemented")
+    if target.dim() == 4:
+        target = target[:, 1]
+    return _SelectiveRisk.apply(_logit_difference(output), _logit_difference(selection), target.to(torch.float32),
+                                float(target_coverage), float(lamb))
+
+
+class CrossEntropyLoss(torch.nn.Module):
+    """Drop-in for the ``torch.nn.CrossEntropyLoss()`` of train.py:80 on (N, 2, H, W) logits and (N, H, W) class
+    indices (mean reduction, no weights)."""
+
+    def forward(self, input, target):
+        return _BCEMean.apply(_logit_difference(input), target.to(torch.float32))

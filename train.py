@@ -176,7 +176,9 @@ def train_worker(rank, world, args, ckpt_dir):
 
 def train(args, ckpt_dir):
     if args.model_arch != 'UNet_B' or 'BCE' not in args.loss:
-        raise SystemExit('the B200-native path covers --model_arch UNet_B --loss BCElogit (see DESIGN.md §6)')
+        raise SystemExit('this CLI drives the fused UNet_B/BCElogit step; the UNet/CE variant is available through the '
+                         'module API (model.UNet, selective_loss.CrossEntropyLoss / calc_selective_risk_image; '
+                         'DESIGN.md §5c)')
     if args.optim != 'Adam':
         raise SystemExit('only --optim Adam is built (the reference default)')
     world = len(args.local_rank)
