@@ -87,6 +87,9 @@ def eval_worker(rank, world, args, ret=None):
     lo, hi = chunk_bounds(n_total, world, rank)
     in_ch, size, bs = net.input_ch, args.patch_size, args.batch_size
     print("Model Prediction...") if rank == 0 else None
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    t0.record()
     with torch.no_grad():
         for start in range(lo, hi, bs):
             n = min(bs, hi - start)
@@ -100,6 +103,12 @@ def eval_worker(rank, world, args, ret=None):
             evaluator.add_batch_from_logits(label, output, selection if args.select_eval else None,
                                             cut_off=args.cut_off, s_cut_off=args.s_cut_off, path='eval',
                                             scale=args.single_scale)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    secs = t0.elapsed_time(t1) / 1e3
+    if rank == 0:       # forward + thresholding + masked confusion-matrix counting, synthetic batches made on the device
+        print(f'    throughput: {round((hi - lo) / secs, 1)} patches/s per GPU ({hi - lo} patches of {size}x{size} in '
+              f'{round(secs, 3)} s, x{world} GPUs)')
     counts = evaluator.counts_tensor().clone()
     if world > 1:
         dist.all_reduce(counts)
