@@ -55,7 +55,7 @@ constexpr int MAX_STAGES = 12;
 
 // MMA issue for one pipeline stage, taps unrolled at compile time.  The generic (runtime T) loop spent ~25 SASS
 // instructions of the single issuing thread per UTCHMMA — more than the 64 tensor-core cycles an N=128 MMA takes,
-// which capped these kernels at ~67 % tensor-pipe utilisation (profiles/r01/ncu_full_r01e.md).
+// which capped these kernels at ~67 % tensor-pipe utilisation (profiles/r01/ncu_full_r01g.md).
 template <int T, bool PAIR>
 __device__ __forceinline__ void wg_issue_stage(uint32_t tmem_base, uint32_t bnw, uint64_t adesc, uint64_t bdesc,
                                                uint32_t tstep16, uint32_t idesc, int nkk, uint32_t acc_first) {
