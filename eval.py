@@ -28,6 +28,7 @@ def parse_arguments(argv=None):
     parser.add_argument('--patch_mag', type=int, default=200)
     parser.add_argument('--patch_size', type=int, default=256)
     parser.add_argument('--n_cls', type=int, default=2)
+    parser.add_argument('--no_graph', action='store_true', help='issue every batch eagerly (no CUDA graph)')
     parser.add_argument('--batch_size', type=int, default=16)
     parser.add_argument('--num_workers', type=int, default=16, help='Dataloader num_workers')
     parser.add_argument('--model_dir', type=str, default='*/model', help='network ckpt (.pth) directory')
@@ -88,21 +89,52 @@ def eval_worker(rank, world, args, ret=None):
     in_ch, size, bs = net.input_ch, args.patch_size, args.batch_size
     print("Model Prediction...") if rank == 0 else None
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run_batch(x, label):
+        if args.selective:
+            output, selection, _ = net(x)
+        else:
+            output, selection = net(x), None
+        evaluator.add_batch_from_logits(label, output, selection if args.select_eval else None,
+                                        cut_off=args.cut_off, s_cut_off=args.s_cut_off, path='eval',
+                                        scale=args.single_scale)
+
+    def make_batch(start, n):
+        g = torch.Generator(device=dev).manual_seed(1000 + start)           # batch content depends only on its position
+        x = torch.rand(n, in_ch, size, size, generator=g, device=dev) * 2 - 1
+        label = (torch.rand(n, size, size, generator=g, device=dev) < 0.4).to(torch.uint8)
+        return x, label
+
+    # Full batches replay one CUDA graph (forward + thresholding + masked counting: ~65 launches that would
+    # otherwise be issued from Python per batch); the ragged tail, if any, runs eagerly.
+    graph, sx, sl = None, None, None
+    n_full = (hi - lo) // bs
+    with torch.no_grad():
+        if n_full >= 2 and not args.no_graph:
+            sx = torch.zeros(bs, in_ch, size, size, device=dev)
+            sl = torch.zeros(bs, size, size, dtype=torch.uint8, device=dev)
+            net(sx)                                                          # plan allocation, not timed / not counted
+            saved = evaluator._ensure(dev).clone()
+            run_batch(sx, sl)                                                # lazy one-time work outside capture
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run_batch(sx, sl)
+            evaluator.counts_tensor().copy_(saved)                           # the warm-up batch was not data
+        else:
+            net(torch.zeros(min(bs, hi - lo), in_ch, size, size, device=dev))
     torch.cuda.synchronize(dev)
     t0.record()
     with torch.no_grad():
         for start in range(lo, hi, bs):
             n = min(bs, hi - start)
-            g = torch.Generator(device=dev).manual_seed(1000 + start)       # batch content depends only on its position
-            x = torch.rand(n, in_ch, size, size, generator=g, device=dev) * 2 - 1
-            label = (torch.rand(n, size, size, generator=g, device=dev) < 0.4).to(torch.uint8)
-            if args.selective:
-                output, selection, _ = net(x)
+            x, label = make_batch(start, n)
+            if graph is not None and n == bs:
+                sx.copy_(x)
+                sl.copy_(label)
+                graph.replay()
             else:
-                output, selection = net(x), None
-            evaluator.add_batch_from_logits(label, output, selection if args.select_eval else None,
-                                            cut_off=args.cut_off, s_cut_off=args.s_cut_off, path='eval',
-                                            scale=args.single_scale)
+                run_batch(x, label)
     t1.record()
     torch.cuda.synchronize(dev)
     secs = t0.elapsed_time(t1) / 1e3

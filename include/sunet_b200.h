@@ -75,6 +75,10 @@ typedef struct sunet_conv_gemm_args {
   const float* bnb_shift;
   const float* bnb_mean;
   const float* bnb_invstd;
+  /* Optional inference epilogue: dst = relu(acc * ep_scale[n] + ep_shift[n]) (BatchNorm in eval mode folded into
+   * the conv: model.py:11-13 under net.eval(), eval.py:191-206).  fp32 [n_total]; no statistics, no bias. */
+  const float* ep_scale;
+  const float* ep_shift;
   int bnb_col0;                /* the reduction covers output columns [bnb_col0, n_total) (multiple of 64; y and the  */
                                /* bnb_* vectors then have n_total - bnb_col0 channels); lower columns keep (sum, sq)   */
 } sunet_conv_gemm_args;
@@ -190,6 +194,9 @@ int sunet_bn_relu_pool(const void* y, int y_pix_stride, const float* scale, cons
 int sunet_bn_relu_pool_ywin(const void* y, int y_pix_stride, const float* scale, const float* shift, void* a,
                             int a_pix_stride, void* pooled, int pooled_pix_stride, void* ywin, int ywin_pix_stride,
                             int batch, int height, int width, int channels, sunet_stream_t stream);
+/* pooled = 2x2 / stride-2 max of a (model.py:31,35,39 when the activation was produced by the ep_* epilogue) */
+int sunet_maxpool2x2(const void* a, int a_pix_stride, void* pooled, int pooled_pix_stride, int batch, int height,
+                     int width, int channels, sunet_stream_t stream);
 /* backward of [BN(train) -> ReLU -> (skip + MaxPool)]:
  *   g = (dA [+ dPool routed to the first maximum of each 2x2 window]) * (a > 0)
  *   dgamma = sum g*xhat, dbeta = sum g, dy = scale*(g - dbeta/n - xhat*dgamma/n)  -> bf16

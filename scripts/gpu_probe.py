@@ -266,6 +266,40 @@ def g1_conv(K):
     return ok
 
 
+def g1_eval_epilogue(K):
+    """Inference epilogue: dst = relu(acc * scale + shift) (BatchNorm in eval mode folded into the conv), and the
+    plain 2x2 max-pool that follows it for the encoder outputs."""
+    dev = "cuda"
+    ok = True
+    for (B, H, W, Cin, Cout, dual) in [(2, 32, 32, 64, 64, False), (1, 16, 16, 128, 128, False), (2, 16, 16, 256, 256, True),
+                                       (2, 16, 16, 256, 512, False), (3, 8, 8, 64, 128, False)]:
+        g = torch.Generator().manual_seed(B + Cin + Cout)
+        x = torch.randn(B, Cin, H, W, generator=g).to(dev)
+        w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(dev)
+        scale = ((torch.rand(Cout, generator=g) + 0.5) * torch.where(torch.rand(Cout, generator=g) < 0.1, -1.0, 1.0)).to(dev)
+        shift = (torch.randn(Cout, generator=g) * 0.3).to(dev)
+        xb = nhwc(x)
+        wf = torch.empty(Cout, 9 * Cin, dtype=torch.bfloat16, device=dev)
+        K.pack_conv3x3_weights(w, wf, None)
+        a = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
+        if dual:
+            c0 = Cin // 2
+            K.conv_gemm(K.A_CONV3X3, (B, H, W), xb[..., :c0].contiguous(), wf, a, src1=xb[..., c0:].contiguous(),
+                        ep=(scale, shift))
+        else:
+            K.conv_gemm(K.A_CONV3X3, (B, H, W), xb, wf, a, ep=(scale, shift))
+        pooled = torch.full((B, H // 2, W // 2, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
+        K.maxpool2x2(a, pooled)
+        torch.cuda.synchronize()
+        ref = F.relu(F.conv2d(nchw(xb), w.to(torch.bfloat16).float(), padding=1) * scale.view(1, -1, 1, 1) +
+                     shift.view(1, -1, 1, 1))
+        ok &= report(f"conv+bn(eval)+relu epilogue B{B} {H}x{W} {Cin}->{Cout}{' dual' if dual else ''}", nchw(a), ref)
+        same = bool(torch.equal(nchw(pooled), F.max_pool2d(nchw(a), 2)))
+        print(f"  [{'OK ' if same else 'BAD'}]    maxpool2x2 exact")
+        ok &= same
+    return ok
+
+
 def g1_big(K):
     # many tiles per CTA: exercises the persistent schedule, phase wrap-around, TMEM double buffering
     ok = conv3x3_case(K, 8, 128, 128, 64, 64)
@@ -638,7 +672,7 @@ def swizzle_exp(K):
     return True
 
 
-GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g1_bnb": g1_bnb, "g1_bnb_convT": g1_bnb_convT, "g1_bnb_pool": g1_bnb_pool, "g2_wgrad": g2_wgrad,
+GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g1_eval_epilogue": g1_eval_epilogue, "g1_bnb": g1_bnb, "g1_bnb_convT": g1_bnb_convT, "g1_bnb_pool": g1_bnb_pool, "g2_wgrad": g2_wgrad,
           "ew_bn": ew_bn, "ew_heads_loss": ew_heads_loss}
 
 

@@ -32,6 +32,7 @@ class ConvGemmArgs(C.Structure):
         ("stats", C.c_void_p),
         ("bnb_y", C.c_void_p), ("bnb_y_pix_stride", C.c_int),
         ("bnb_scale", C.c_void_p), ("bnb_shift", C.c_void_p), ("bnb_mean", C.c_void_p), ("bnb_invstd", C.c_void_p),
+        ("ep_scale", C.c_void_p), ("ep_shift", C.c_void_p),
         ("bnb_col0", C.c_int),
     ]
 
@@ -90,6 +91,7 @@ SIGNATURES = {
     "sunet_bn_relu_pool_ywin": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "sunet_bn_pool_bwd_apply": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp,
                                 _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp],
+    "sunet_maxpool2x2": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "sunet_bn_relu_pool_bwd": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
                                _vp, _sz, _vp],
     "sunet_bn_bwd_apply": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz,

@@ -463,6 +463,37 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __
   }
 }
 
+// plain 2x2 / stride-2 max-pool of an activation (inference path: the conv epilogue already applied BN + ReLU)
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const __nv_bfloat16* __restrict__ a, int as, __nv_bfloat16* __restrict__ pooled, int ps, int B, int H,
+                  int W, int C) {
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t G = (uint32_t)C >> 3, HW = (uint32_t)H >> 1, WW = (uint32_t)W >> 1;
+  const uint32_t total = (uint32_t)B * HW * WW * G;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t win = i / G, g = i - win * G;
+    const uint32_t rowi = win / WW, wx = win - rowi * WW;
+    const uint32_t n = rowi / HW, wy = rowi - n * HW;
+    const size_t p00 = ((size_t)n * H + wy * 2) * W + wx * 2;
+    bf16x8 v[4];
+    v[0] = *reinterpret_cast<const bf16x8*>(a + p00 * as + g * 8);
+    v[1] = *reinterpret_cast<const bf16x8*>(a + (p00 + 1) * as + g * 8);
+    v[2] = *reinterpret_cast<const bf16x8*>(a + (p00 + W) * as + g * 8);
+    v[3] = *reinterpret_cast<const bf16x8*>(a + (p00 + W + 1) * as + g * 8);
+    float m[8];
+    unpack8(v[0], m);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      float f[8];
+      unpack8(v[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    }
+    *reinterpret_cast<bf16x8*>(pooled + (size_t)win * ps + g * 8) = pack8(m);
+  }
+}
+
 // ------------------------------------------------------------------ BN + ReLU (+ pool) backward
 // Shared gradient gather: g[k][j] for the 4 (POOL) or 1 pixels of this item, ReLU mask applied,
 // pooled gradient routed to the first maximum (row-major window order, computed on the same
@@ -1332,4 +1363,19 @@ extern "C" int sunet_bn_pool_bwd_apply(const void* dA, int dA_pix_stride, const 
            dPool_pix_stride, reinterpret_cast<const __nv_bfloat16*>(y), y_pix_stride, scale, shift, coef,
            reinterpret_cast<__nv_bfloat16*>(dy), dy_pix_stride, batch, height, width, channels);
   return check_launch("bn_pool_bwd_apply");
+}
+
+extern "C" int sunet_maxpool2x2(const void* a, int a_pix_stride, void* pooled, int pooled_pix_stride, int batch,
+                                int height, int width, int channels, sunet_stream_t stream_) {
+  if (!a || !pooled || batch <= 0 || height <= 0 || width <= 0 || ((height | width) & 1))
+    return set_error(SUNET_ERR_INVALID, "maxpool2x2: bad arguments");
+  int e;
+  if ((e = check_act("maxpool2x2(a)", a_pix_stride, channels))) return e;
+  if ((e = check_act("maxpool2x2(pooled)", pooled_pix_stride, channels))) return e;
+  const long long total = (long long)batch * (height / 2) * (width / 2) * (channels / 8);
+  if (total >= (1ll << 31)) return set_error(SUNET_ERR_INVALID, "maxpool2x2: tensor too large");
+  launch_k(maxpool2x2_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM,
+           reinterpret_cast<const __nv_bfloat16*>(a), a_pix_stride, reinterpret_cast<__nv_bfloat16*>(pooled),
+           pooled_pix_stride, batch, height, width, channels);
+  return check_launch("maxpool2x2");
 }

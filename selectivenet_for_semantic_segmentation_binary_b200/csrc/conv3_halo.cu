@@ -26,6 +26,8 @@ struct HaloParams {
   int m_blocks, n_tiles;
   float* stats;              // [gridDim.x / n_tiles][n_total][2] or nullptr
   int n_total;
+  const float* ep_scale;     // inference epilogue: dst = relu(acc * ep_scale[n] + ep_shift[n]) (nullptr = off)
+  const float* ep_shift;
 };
 
 // TILES = M=128 tiles per block: 2 (16x16 block, BN <= 128) or 1 (8 wide x 16 tall block, BN = 256 —
@@ -218,6 +220,12 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           tmem_ld_32x32b_x32(taddr + 32, v + 32);
           tmem_ld_wait();
           const int ncol0 = n_tile * BN + q * 64;
+          if (p.ep_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              v[j] = __float_as_uint(fmaxf(
+                  fmaf(__uint_as_float(v[j]), __ldg(p.ep_scale + ncol0 + j), __ldg(p.ep_shift + ncol0 + j)), 0.f));
+          }
           uint8_t* stg = sStg + (chunk_ctr & 1) * C::STG_BYTES;
           uint4* rowp = reinterpret_cast<uint4*>(stg + row * 128);
 #pragma unroll
@@ -357,6 +365,8 @@ int conv3_halo_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   p.n_tiles = a->n_total / bn;
   p.stats = a->stats;
   p.n_total = a->n_total;
+  p.ep_scale = a->ep_scale;
+  p.ep_shift = a->ep_shift;
   const int slots = conv3_halo_stat_rows(B, H, W, a->n_total);
   const int grid = slots * p.n_tiles;
   if (bn == 256) return halo_launch_t<256>(mA0, mA1, mB, mD, p, grid, stream);

@@ -31,6 +31,8 @@ struct Halo2Params {
   const float* bnb_shift;
   const float* bnb_mean;
   const float* bnb_invstd;
+  const float* ep_scale;     // inference epilogue: dst = relu(acc * ep_scale[n] + ep_shift[n]) (nullptr = off)
+  const float* ep_shift;
   int bnb_col0;              // BNB covers output columns [bnb_col0, n_total); lower columns get (sum, sum sq)
 };
 
@@ -48,7 +50,9 @@ struct H2Cfg {
   static constexpr int B_STAGES = (BN == 256) ? (BNB ? 7 : 8) : ((BNB && BN == 128) ? 9 : 10);
   static constexpr int STG_BYTES = 128 * 128;
   static constexpr int Y_SLOTS = BNB ? ((BN == 64) ? 4 : 2) : 0;      // power of two
-  static constexpr int SMEM = A_STAGES * A_SLOT + B_STAGES * B_HALF + (2 + Y_SLOTS) * STG_BYTES + 1024 + 512;
+  static constexpr int EP_BYTES = BNB ? 0 : 2 * BN * 4;   // inference epilogue: this CTA's scale / shift columns
+  static constexpr int SMEM =
+      A_STAGES * A_SLOT + B_STAGES * B_HALF + (2 + Y_SLOTS) * STG_BYTES + 1024 + 512 + EP_BYTES;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr int TMEM_COLS = 2 * TILES * BN;   // TILES x BN columns x 2 accumulator stages
 };
@@ -78,6 +82,7 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   uint64_t* tempty = tfull + 2;
   uint64_t* yfull = tempty + 2;                           // [4], BNB only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 4);
+  float* sEp = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);      // [2][BN], !BNB only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,6 +107,13 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     tma_prefetch_desc(&mapB);
     tma_prefetch_desc(&mapD);
     if (BNB) tma_prefetch_desc(&mapY);
+  }
+  if (!BNB && p.ep_scale != nullptr) {
+    const int c0 = ((blockIdx.x >> 1) % p.n_tiles) * BN;
+    for (int i = threadIdx.x; i < BN; i += kH2Threads) {
+      sEp[i] = __ldg(p.ep_scale + c0 + i);
+      sEp[BN + i] = __ldg(p.ep_shift + c0 + i);
+    }
   }
   __syncthreads();
   cluster_sync_all();               // both CTAs' barriers exist before anything signals across the pair
@@ -302,6 +314,18 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           tmem_ld_32x32b_x32(taddr + 32, v + 32);
           tmem_ld_wait();
           const int ncol0 = n_tile * BN + q * 64;
+          if (!BNB && p.ep_scale != nullptr) {      // eval-mode BatchNorm + ReLU folded into the store
+            const float4* es = reinterpret_cast<const float4*>(sEp + q * 64);
+            const float4* eh = reinterpret_cast<const float4*>(sEp + BN + q * 64);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {         // broadcast 16-byte reads: every thread needs all 64 columns
+              const float4 s4 = es[j], h4 = eh[j];
+              v[4 * j + 0] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * j + 0]), s4.x, h4.x), 0.f));
+              v[4 * j + 1] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * j + 1]), s4.y, h4.y), 0.f));
+              v[4 * j + 2] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * j + 2]), s4.z, h4.z), 0.f));
+              v[4 * j + 3] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * j + 3]), s4.w, h4.w), 0.f));
+            }
+          }
           uint8_t* stg = sStg + (chunk_ctr & 1) * C::STG_BYTES;
           uint4* rowp = reinterpret_cast<uint4*>(stg + row * 128);
 #pragma unroll
@@ -502,6 +526,8 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   p.bnb_mean = a->bnb_mean;
   p.bnb_invstd = a->bnb_invstd;
   p.bnb_col0 = bnb ? a->bnb_col0 : 0;
+  p.ep_scale = a->ep_scale;
+  p.ep_shift = a->ep_shift;
   const int grid = halo2_slots(B, H, W, p.n_tiles, bw) * p.n_tiles * 2;
   if (bnb) {
     if (bn == 256) return halo2_launch_t<256, true>(mA0, mA1, mB, mD, mY, p, grid, stream);

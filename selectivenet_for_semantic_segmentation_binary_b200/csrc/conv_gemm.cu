@@ -43,6 +43,8 @@ struct ConvGemmParams {
   const float* bnb_shift;
   const float* bnb_mean;
   const float* bnb_invstd;
+  const float* ep_scale;     // inference epilogue: dst = relu(acc * ep_scale[n] + ep_shift[n]) (nullptr = off)
+  const float* ep_shift;
   int dbg_shift, dbg_boff;  // SUNET_DBG_SHIFT / SUNET_DBG_BOFF: descriptor-swizzle experiment (scripts/gpu_probe.py)
 };
 
@@ -288,6 +290,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + ncol0 + j));
+        }
+        if (!BNB && p.ep_scale != nullptr) {      // eval-mode BatchNorm + ReLU folded into the store
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            v[j] = __float_as_uint(fmaxf(
+                fmaf(__uint_as_float(v[j]), __ldg(p.ep_scale + ncol0 + j), __ldg(p.ep_shift + ncol0 + j)), 0.f));
         }
         uint8_t* stg = sStg + (chunk_ctr & 1) * C::STG_BYTES;
         // 128B-swizzled staging row (matches the TMA store map): 16B chunk j lands at j ^ (row & 7)
@@ -540,6 +548,10 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
   if (a->d_mode == SUNET_D_SCATTER2X2 && (a->n_total % 4 || (a->n_total / 4) % 64))
     return set_error(SUNET_ERR_INVALID, "conv_gemm: scatter store needs n_total = 4 x (multiple of 64)");
 
+  if ((a->ep_scale == nullptr) != (a->ep_shift == nullptr))
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: ep_scale and ep_shift go together");
+  if (a->ep_scale && (a->stats || a->bias || a->bnb_y || a->d_mode != SUNET_D_NHWC))
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: the inference epilogue excludes stats / bias / bnb / scatter store");
   if (conv3_halo2_eligible(a)) return conv3_halo2_launch(a, stream);
   const bool bnb = a->bnb_y != nullptr;
   if (bnb && !sunet_conv_gemm_bnb_supported(a))
@@ -600,6 +612,8 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
   p.bnb_shift = a->bnb_shift;
   p.bnb_mean = a->bnb_mean;
   p.bnb_invstd = a->bnb_invstd;
+  p.ep_scale = a->ep_scale;
+  p.ep_shift = a->ep_shift;
   {
     const char* s = getenv("SUNET_DBG_SHIFT");
     const char* b = getenv("SUNET_DBG_BOFF");

@@ -220,6 +220,7 @@ class SUNetPlan:
             last.bnb_rows = K.heads_bwd_bn_rows(B * height * width)
             last.bnb_stats = torch.zeros(last.bnb_rows, last.cout, 2, device=dev)
             last.a = None
+        self.eval_fused = os.environ.get("SUNET_EVAL_FUSED", "1") != "0"
         self.ws = K.new_workspace(dev)
         self.partials = None      # sized lazily from the wgrad split plan
         self._partials_bytes = 0
@@ -311,7 +312,29 @@ class SUNetPlan:
             K.pack_convT_weights(params[f"unpool{L}.weight"], params[f"unpool{L}.bias"], u["wf"], u["wd"], u["b4"])
 
     # ------------------------------------------------------------------ forward
+    def _cbr_fwd_eval_fused(self, ly: _Layer, params, buffers) -> bool:
+        """Inference: BatchNorm (running statistics) + ReLU folded into the conv's epilogue, so y is never written
+        and there is no BN/ReLU pass (model.py:11-13 under net.eval()).  All blocks except the first (pixel-pair
+        GEMM) and the last (its BN+ReLU is fused with the heads)."""
+        n = ly.name
+        if ly.kind == "first" or n == "decoder_layer_1_1" or not self.eval_fused:
+            return False
+        B = self.B
+        h, w = self.hw[ly.level]
+        K.bn_eval_affine(params[f"{n}.1.weight"], params[f"{n}.1.bias"], params[f"{n}.0.bias"],
+                         buffers[f"{n}.1.running_mean"], buffers[f"{n}.1.running_var"], BN_EPS, ly.scale, ly.shift)
+        ep = (ly.scale, ly.shift)
+        if ly.kind == "cat":
+            K.conv_gemm(K.A_CONV3X3, (B, h, w), self.up[ly.level], ly.wf, ly.a, src1=self._skip(ly.level), ep=ep)
+        else:
+            K.conv_gemm(K.A_CONV3X3, (B, h, w), self._conv_src(ly), ly.wf, ly.a, ep=ep)
+        if ly.pool:
+            K.maxpool2x2(ly.a, self.pool[ly.level])
+        return True
+
     def _cbr_fwd(self, ly: _Layer, params, buffers, training: bool):
+        if not training and self._cbr_fwd_eval_fused(ly, params, buffers):
+            return
         B = self.B
         h, w = self.hw[ly.level]
         grid = (B, h, w)

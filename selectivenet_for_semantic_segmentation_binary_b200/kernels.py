@@ -84,7 +84,7 @@ def conv_gemm_bnb_supported(a_mode: int, grid, src0, weights, dst, *, src1=None,
 
 def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst: torch.Tensor, *,
               src1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-              stats: Optional[torch.Tensor] = None, d_mode: int = D_NHWC, bnb=None) -> None:
+              stats: Optional[torch.Tensor] = None, d_mode: int = D_NHWC, bnb=None, ep=None) -> None:
     """grid = (batch, height, width) of the GEMM-M pixel grid.
     bnb = (y, scale, shift, mean, invstd): fuse the BatchNorm-backward reduction of the block whose input
     gradient this launch produces into the epilogue; `stats` then receives (sum g, sum g*xhat) rows."""
@@ -101,6 +101,8 @@ def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst:
         a.bnb_col0 = col0
         a.bnb_y, _, a.bnb_y_pix_stride = _act(y)
         a.bnb_scale, a.bnb_shift, a.bnb_mean, a.bnb_invstd = _f32(scale), _f32(shift), _f32(mean), _f32(invstd)
+    if ep is not None:               # inference: dst = relu(acc * scale + shift), BatchNorm(eval) + ReLU folded in
+        a.ep_scale, a.ep_shift = _f32(ep[0]), _f32(ep[1])
     _lib.check(lib.sunet_conv_gemm(C.byref(a), _stream()), "sunet_conv_gemm")
 
 
@@ -243,6 +245,13 @@ def bn_relu_pool(y, scale, shift, a, pooled=None, ywin=None) -> None:
         return
     _lib.check(_lib.load().sunet_bn_relu_pool(yp, ys, _f32(scale), _f32(shift), ap, as_, pp, ps, B, H, W, Cc,
                                               _stream()), "sunet_bn_relu_pool")
+
+
+def maxpool2x2(a, pooled) -> None:
+    B, H, W, Cc = a.shape
+    ap, _, as_ = _act(a)
+    pp, _, ps = _act(pooled)
+    _lib.check(_lib.load().sunet_maxpool2x2(ap, as_, pp, ps, B, H, W, Cc, _stream()), "sunet_maxpool2x2")
 
 
 def bn_pool_bwd_apply(dA, dPool, y, scale, shift, mean, invstd, src0, src1, dgamma, dbeta, dy, workspace) -> None:
