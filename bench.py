@@ -245,7 +245,7 @@ def run_ours(args):
     # ---- the same loop fed with the DECODED patches (uint8 HWC + label bytes + flip bits): normalisation, flips,
     # layout and the first layer's im2col run on the device (SUNetTrainer.step_u8), 4x less H2D traffic
     e2e_u8 = None
-    if not args.no_u8:
+    if not args.no_u8 and world == 1:          # informational extra pass: single-GPU runs only
         g8 = torch.Generator().manual_seed(4321)
         img_host = torch.randint(0, 256, (b, args.size, args.size, 3), dtype=torch.uint8, generator=g8).pin_memory()
         lab_host = ((torch.rand(b, args.size, args.size, generator=g8) < 0.4).to(torch.uint8) * 255).pin_memory()
