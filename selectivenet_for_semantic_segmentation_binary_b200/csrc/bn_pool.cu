@@ -495,187 +495,11 @@ maxpool2x2_kernel(const __nv_bfloat16* __restrict__ a, int as, __nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------ BN + ReLU (+ pool) backward
-// Shared gradient gather: g[k][j] for the 4 (POOL) or 1 pixels of this item, ReLU mask applied,
-// pooled gradient routed to the first maximum (row-major window order, computed on the same
-// bf16-rounded activations the forward pass pooled).
-template <bool POOL>
-struct BwdItem {
-  static constexpr int NP = POOL ? 4 : 1;
-  float g[NP][8];
-  float yv[NP][8];
-  long long pix[NP];
-};
-
-template <bool POOL>
-__device__ __forceinline__ void bwd_gather(BwdItem<POOL>& it, long long i, int G, const __nv_bfloat16* __restrict__ dA,
-                                           int das, const __nv_bfloat16* __restrict__ dP, int dps,
-                                           const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
-                                           const float* __restrict__ shift, int H, int W, int& g_out) {
-  constexpr int NP = BwdItem<POOL>::NP;
-  const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
-  const int g = (int)(i % G);
-  g_out = g;
-  const long long wpix = i / G;
-  const int wx = (int)(wpix % WW);
-  const int wy = (int)((wpix / WW) % HW);
-  const int n = (int)(wpix / ((long long)WW * HW));
-  float sc[8], sh[8];
-  *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
-  *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
-  *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
-  *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
-  float act[NP][8];
-#pragma unroll
-  for (int k = 0; k < NP; ++k) {
-    it.pix[k] = POOL ? (((long long)n * H + (wy * 2 + (k >> 1))) * W + (wx * 2 + (k & 1))) : wpix;
-    unpack8(*reinterpret_cast<const bf16x8*>(y + it.pix[k] * ys + g * 8), it.yv[k]);
-    if (dA) {
-      unpack8(*reinterpret_cast<const bf16x8*>(dA + it.pix[k] * das + g * 8), it.g[k]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) it.g[k][j] = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) act[k][j] = round_bf16(fmaxf(fmaf(it.yv[k][j], sc[j], sh[j]), 0.f));
-  }
-  if (POOL) {
-    float dp[8];
-    const long long ppix = ((long long)n * HW + wy) * WW + wx;
-    unpack8(*reinterpret_cast<const bf16x8*>(dP + ppix * dps + g * 8), dp);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int best = 0;
-      float bv = act[0][j];
-#pragma unroll
-      for (int k = 1; k < NP; ++k)
-        if (act[k][j] > bv) {
-          bv = act[k][j];
-          best = k;
-        }
-#pragma unroll
-      for (int k = 0; k < NP; ++k)
-        if (k == best) it.g[k][j] += dp[j];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < NP; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (!(act[k][j] > 0.f)) it.g[k][j] = 0.f;
-}
-
-// stage 1: per-block partial (sum g, sum g*xhat) per channel -> partials[block][C][2]
-template <bool POOL>
-__global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ dP, int dps,
-                     const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
-                     const float* __restrict__ shift, const float* __restrict__ mean,
-                     const float* __restrict__ invstd, float* __restrict__ partials, int B, int H, int W, int C) {
-  pdl_wait();
-  pdl_trigger();
-  __shared__ float red[256][17];
-  const int G = C >> 3;
-  const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
-  const long long total = (long long)B * HW * WW * G;
-  float acc[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-  // blockDim (256) is a multiple of G (8..64), and the grid stride too, so a thread keeps its
-  // channel group for the whole loop.
-  const int g = threadIdx.x % G;
-  float mu[8], is[8];
-  *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + g * 8));
-  *reinterpret_cast<float4*>(mu + 4) = __ldg(reinterpret_cast<const float4*>(mean + g * 8 + 4));
-  *reinterpret_cast<float4*>(is) = __ldg(reinterpret_cast<const float4*>(invstd + g * 8));
-  *reinterpret_cast<float4*>(is + 4) = __ldg(reinterpret_cast<const float4*>(invstd + g * 8 + 4));
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    BwdItem<POOL> it;
-    int gg;
-    bwd_gather<POOL>(it, i, G, dA, das, dP, dps, y, ys, scale, shift, H, W, gg);
-#pragma unroll
-    for (int k = 0; k < BwdItem<POOL>::NP; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] += it.g[k][j];
-        acc[8 + j] = fmaf(it.g[k][j], (it.yv[k][j] - mu[j]) * is[j], acc[8 + j]);
-      }
-  }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = acc[j];
-  __syncthreads();
-  const int reps = 256 / G;
-  for (int o = threadIdx.x; o < G * 16; o += 256) {
-    const int og = o >> 4, oj = o & 15;
-    float s = 0.f;
-    for (int r = 0; r < reps; ++r) s += red[r * G + og][oj];
-    const int c = og * 8 + (oj & 7);
-    partials[((size_t)blockIdx.x * C + c) * 2 + (oj >> 3)] = s;
-  }
-}
-
-// stage 2: dgamma, dbeta and the three coefficients of dy = kg*g + k1*y + k0
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int C, double count,
-                                       const float* __restrict__ scale, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, float* dgamma, float* dbeta, float* coef) {
-  pdl_wait();
-  pdl_trigger();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double sg = 0.0, sgx = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    sg += (double)partials[((size_t)b * C + c) * 2];
-    sgx += (double)partials[((size_t)b * C + c) * 2 + 1];
-  }
-  if (dbeta) dbeta[c] = (float)sg;
-  if (dgamma) dgamma[c] = (float)sgx;
-  const double sc = scale[c];
-  const double k1 = -sc * (double)invstd[c] * sgx / count;
-  const double k0 = -sc * sg / count - k1 * (double)mean[c];
-  coef[c] = (float)sc;
-  coef[C + c] = (float)k1;
-  coef[2 * C + c] = (float)k0;
-}
-
-// stage 3: dy
-template <bool POOL>
-__global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ dP, int dps,
-                    const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
-                    const float* __restrict__ shift, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
-                    int dys, int B, int H, int W, int C) {
-  pdl_wait();
-  pdl_trigger();
-  const int G = C >> 3;
-  const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
-  const long long total = (long long)B * HW * WW * G;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    BwdItem<POOL> it;
-    int g;
-    bwd_gather<POOL>(it, i, G, dA, das, dP, dps, y, ys, scale, shift, H, W, g);
-    float kg[8], k1[8], k0[8];
-    *reinterpret_cast<float4*>(kg) = __ldg(reinterpret_cast<const float4*>(coef + g * 8));
-    *reinterpret_cast<float4*>(kg + 4) = __ldg(reinterpret_cast<const float4*>(coef + g * 8 + 4));
-    *reinterpret_cast<float4*>(k1) = __ldg(reinterpret_cast<const float4*>(coef + C + g * 8));
-    *reinterpret_cast<float4*>(k1 + 4) = __ldg(reinterpret_cast<const float4*>(coef + C + g * 8 + 4));
-    *reinterpret_cast<float4*>(k0) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + g * 8));
-    *reinterpret_cast<float4*>(k0 + 4) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + g * 8 + 4));
-#pragma unroll
-    for (int k = 0; k < BwdItem<POOL>::NP; ++k) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(kg[j], it.g[k][j], fmaf(k1[j], it.yv[k][j], k0[j]));
-      *reinterpret_cast<bf16x8*>(dy + it.pix[k] * dys + g * 8) = pack8(o);
-    }
-  }
-}
-
-
-// ------------------------------------------------------------------ non-pooled fast paths
-// Same math as the templates above for the layers that are not followed by a max-pool (11 of 14), with
-// the per-channel vectors hoisted out of the loop and FOUR independent 16-byte loads per operand in
-// flight per thread: these kernels are pure HBM streams and latency, not arithmetic, limits them.
+//   g = (dA [+ dPool routed to the first maximum of each 2x2 window]) * [relu(bn(y)) > 0]
+//   dgamma = sum g*xhat, dbeta = sum g, dy = kg*g + k1*y + k0  (the three per-channel coefficients fold scale,
+//   invstd, mean and the two sums; bn_bwd_finalize_par_kernel)
+// Non-pooled blocks (11 of 14): per-channel vectors hoisted out of the loop and FOUR independent 16-byte loads per
+// operand in flight per thread — these kernels are pure HBM streams and latency, not arithmetic, limits them.
 constexpr int EW_U = 4;
 
 struct ChanVec {

@@ -300,16 +300,6 @@ class SUNetPlan:
             self._pack_n = len(self.order) + 3
             self._pack_key = key
         K.pack_weights_table(self._pack_jobs, self._pack_n)
-        return
-        for ly in self.order:
-            w = params[f"{ly.name}.0.weight"]
-            if ly.kind == "first":
-                K.pack_conv1_weights(w, ly.wf)
-            else:
-                K.pack_conv3x3_weights(w, ly.wf, ly.wd)
-        for L in (1, 2, 3):
-            u = self.upw[L]
-            K.pack_convT_weights(params[f"unpool{L}.weight"], params[f"unpool{L}.bias"], u["wf"], u["wd"], u["b4"])
 
     # ------------------------------------------------------------------ forward
     def _cbr_fwd_eval_fused(self, ly: _Layer, params, buffers) -> bool:
