@@ -253,43 +253,59 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         cmu[q][1] = on ? __ldg(p.bnb_mean + c + 1) : 0.f;
       }
     }
-    // BNB y-tile pipeline (issuer thread): BNB chunk number k of this CTA = (block k / CPBY of its sequence, tile
-    // (k % CPBY) / nqb, channel chunk q0 + k % nqb); slot k % YS.  Loads run YS-1 chunks ahead of the consumer
-    // (the slot of chunk k-1 is free once every thread has passed a staging barrier after its stats loop); L2
-    // prefetches run kPfAhead chunks further ahead so the smem fill is an L2 hit.
+    // BNB y-tile pipeline, driven by lane 0 of the second epilogue warp (`y_issuer`; the first warp's lane 0 issues
+    // the output stores).  BNB chunks are visited in the consumer's order (block, tile, channel chunk q0..NCHUNK-1);
+    // chunk k uses slot k % YS.  Loads run YS-1 chunks ahead of the consumer (the slot of chunk k-1 is free once
+    // every thread has passed a staging barrier after its stats loop), L2 prefetches kPfAhead chunks further.
+    // Coordinates advance incrementally: the first version recomputed them with integer divisions per chunk, which
+    // made this one thread the slowest of the epilogue (0.18 ms of a 0.55 ms launch, gpurun_out/bnb_timing*).
     constexpr uint32_t YS = C::Y_SLOTS > 0 ? C::Y_SLOTS : 1;
     constexpr uint32_t YS_LOG = (YS == 4) ? 2 : ((YS == 2) ? 1 : 0);
-    constexpr int kPfAhead = 4;
-    uint32_t y_issued = 0, y_prefetched = 0;
-    const uint32_t my_blocks = (m_first < m_pairs) ? (uint32_t)((m_pairs - 1 - m_first) / m_step + 1) : 0u;
-    const uint32_t cpby = (uint32_t)(C::TILES * nqb);
-    const uint32_t y_total = my_blocks * cpby;
-    auto y_coords = [&](uint32_t k, int& c0, int& x0, int& y0, int& nn) {
-      const int blk = (int)(k / cpby), rem = (int)(k % cpby);
-      const int mb_ = 2 * (m_first + blk * m_step) + (int)rank;
-      c0 = n_tile * BN + (q0 + rem % nqb) * 64 - p.bnb_col0;
-      x0 = (mb_ % p.blocks_x) * (8 * C::TILES) + 8 * (rem / nqb);
-      y0 = ((mb_ / p.blocks_x) % p.blocks_y) * 16;
-      nn = mb_ / (p.blocks_x * p.blocks_y);
+    constexpr int kPfAhead = 2;
+    const bool y_issuer = (threadIdx.x == 96);
+    struct YIter {
+      int mp, t, q, x0, y0, n;
+      bool valid;
     };
-    auto y_pump = [&](uint32_t upto) {      // issuer only: smem loads up to chunk `upto` (exclusive), prefetch beyond
-      while (y_issued < upto && y_issued < y_total) {
-        int c0, x0, y0, nn;
-        y_coords(y_issued, c0, x0, y0, nn);
-        uint64_t* bar = &yfull[y_issued & (YS - 1)];
-        mbar_arrive_expect_tx(bar, C::STG_BYTES);
-        tma_load_5d(sY + (y_issued & (YS - 1)) * C::STG_BYTES, &mapY, bar, c0, x0, y0, nn, 0);
-        ++y_issued;
-      }
-      if (y_prefetched < y_issued) y_prefetched = y_issued;
-      while (y_prefetched < y_issued + kPfAhead && y_prefetched < y_total) {
-        int c0, x0, y0, nn;
-        y_coords(y_prefetched, c0, x0, y0, nn);
-        tma_prefetch_5d(&mapY, c0, x0, y0, nn, 0);
-        ++y_prefetched;
+    auto y_block = [&](YIter& it) {              // block coordinates of pair item it.mp (this CTA's half)
+      const int mb_ = 2 * it.mp + (int)rank;
+      it.x0 = (mb_ % p.blocks_x) * (8 * C::TILES);
+      it.y0 = ((mb_ / p.blocks_x) % p.blocks_y) * 16;
+      it.n = mb_ / (p.blocks_x * p.blocks_y);
+    };
+    auto y_next = [&](YIter& it) {
+      if (++it.q == NCHUNK) {
+        it.q = q0;
+        if (++it.t == C::TILES) {
+          it.t = 0;
+          it.mp += m_step;
+          it.valid = it.mp < m_pairs;
+          if (it.valid) y_block(it);
+        }
       }
     };
-    if (BNB && issuer) y_pump(YS);
+    YIter yld = {m_first, 0, q0, 0, 0, 0, BNB && nqb > 0 && m_first < m_pairs}, ypf = yld;
+    uint32_t y_issued = 0;
+    auto y_load_one = [&]() {
+      if (!yld.valid) return;
+      uint64_t* bar = &yfull[y_issued & (YS - 1)];
+      mbar_arrive_expect_tx(bar, C::STG_BYTES);
+      tma_load_5d(sY + (y_issued & (YS - 1)) * C::STG_BYTES, &mapY, bar, n_tile * BN + yld.q * 64 - p.bnb_col0,
+                  yld.x0 + 8 * yld.t, yld.y0, yld.n, 0);
+      ++y_issued;
+      y_next(yld);
+    };
+    auto y_prefetch_one = [&]() {
+      if (!ypf.valid) return;
+      tma_prefetch_5d(&mapY, n_tile * BN + ypf.q * 64 - p.bnb_col0, ypf.x0 + 8 * ypf.t, ypf.y0, ypf.n, 0);
+      y_next(ypf);
+    };
+    if (BNB && y_issuer && yld.valid) {
+      y_block(yld);
+      for (uint32_t i = 0; i < YS; ++i) y_load_one();
+      ypf = yld;
+      for (int i = 0; i < kPfAhead; ++i) y_prefetch_one();
+    }
     uint32_t yctr = 0;                           // BNB chunks whose statistics loop this thread has finished
 
     int it = 0;
@@ -343,7 +359,13 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           if (issuer) {
             tma_store_5d(&mapD, stg, ncol0, bx * (8 * C::TILES) + 8 * t, by * 16, n, 0);   // out-of-range n: clipped
             tma_store_commit();
-            if (BNB) y_pump(yctr + YS);          // everyone is past the stats loop of BNB chunk yctr-1: slot free
+          }
+          if (BNB && y_issuer) {
+            // everyone is past the stats loop of BNB chunk yctr-1: its slot is free for chunk yctr-1+YS
+            while (y_issued < yctr + YS && yld.valid) {
+              y_load_one();
+              y_prefetch_one();
+            }
           }
           if (BNB && q >= q0) {
             // (sum g, sum g*(y-mean)) over this quad's 32 rows for this thread's two columns; g = dA where
