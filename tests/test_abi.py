@@ -46,3 +46,20 @@ def test_missing_library_fails_loudly(monkeypatch):
     import pytest
     with pytest.raises(_lib.SunetError):
         _lib.load()
+
+
+def _header_struct_fields(name):
+    src = open(os.path.join(ROOT, "include", "sunet_b200.h")).read()
+    body = src[src.index(f"typedef struct {name} {{"):src.index(f"}} {name};")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    body = body[body.index("{") + 1:]
+    return re.findall(r"(\w+)\s*(?:,|;)", body)
+
+
+def test_ctypes_structs_mirror_the_header_field_for_field():
+    """A field added to a C struct without its ctypes twin would shift every later argument silently."""
+    from selectivenet_for_semantic_segmentation_binary_b200 import _lib
+    pairs = [("sunet_conv_gemm_args", _lib.ConvGemmArgs), ("sunet_wgrad_gemm_args", _lib.WgradGemmArgs),
+             ("sunet_pack_job", _lib.PackJob), ("sunet_adam_tensor", _lib.AdamTensor)]
+    for cname, cls in pairs:
+        assert _header_struct_fields(cname) == [f[0] for f in cls._fields_], cname
