@@ -254,3 +254,47 @@ def test_no_cpu_fallback():
     net = UNet_B("RGB", selective=True)
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 32, 32))
+
+
+def test_untileable_shape_fails_loudly():
+    """The GEMM kernels tile the pixel grid into power-of-two blocks (>= 32 pixels at the deepest level): a patch
+    like 48 x 80 (6 x 10 at level 4) is rejected with an error that says so — never computed wrongly."""
+    from selectivenet_for_semantic_segmentation_binary_b200 import _lib
+    net, _ = _make(True, seed=0)
+    with pytest.raises((_lib.SunetError, ValueError)) as e:
+        net(torch.zeros(3, 3, 48, 80, device="cuda"))
+    assert "tile" in str(e.value) or "shape" in str(e.value)
+
+
+@pytest.mark.parametrize("batch,h,w", [(3, 64, 128), (1, 64, 32), (2, 128, 192)])
+def test_forward_backward_parity_non_square(batch, h, w):
+    """Ragged shapes: odd batch, batch of one, non-square patches, a side with an odd factor (192 = 64 x 3)."""
+    from selectivenet_for_semantic_segmentation_binary_b200.selective_loss import (BCEWithLogitsLoss,
+                                                                                   calc_selective_risk_image_b)
+    net, sd = _make(True, seed=0)
+    names = [n for n, _ in net.named_parameters()]
+    for n in names:
+        sd[n].requires_grad_(True)
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand(batch, 3, h, w, generator=g) * 2 - 1
+    label = (torch.rand(batch, h, w, generator=g) < 0.4).float()
+    ref_loss, ref = O.train_losses(sd, x, label, s_lamb=2, selective=True)
+    ref_loss.backward()
+    net.train()
+    out, sel, aux = net(x.cuda())
+    lab = label.cuda()
+    loss = BCEWithLogitsLoss()(aux, lab)
+    s_loss, cov = calc_selective_risk_image_b(out, sel, target=lab, lamb=2)
+    (loss + s_loss).backward()
+    torch.cuda.synchronize()
+    for got, want in ((out, ref["output"]), (sel, ref["selection"]), (aux, ref["aux"])):
+        assert got.shape == want.shape
+        assert _rel_l2(got.detach().cpu().numpy(), want.detach().numpy()) < REL_TOL_BF16
+    assert abs(float((loss + s_loss).detach()) - float(ref_loss.detach())) < REL_TOL_BF16 * abs(float(ref_loss.detach()))
+    params = dict(net.named_parameters())
+    for n in names:
+        gr = params[n].grad.cpu()
+        if n.endswith(".0.bias") and "layer" in n:
+            assert float(gr.abs().max()) <= 1e-6
+        else:
+            assert _cos(gr, sd[n].grad) >= 0.85, (n, _cos(gr, sd[n].grad))     # tiny batches: bf16 noise is larger
