@@ -65,6 +65,267 @@ class ClockSampler(threading.Thread):
                     reasons=reasons, samples=len(sm))
 
 
+def kernel_source_sha() -> str:
+    """sha256 over the CUDA sources + headers the shipped .so was built from: ncu-derived numbers committed under
+    profiles/ are stamped with it, and bench.py refuses a stale stamp (traffic was a static number)."""
+    import hashlib
+    h = hashlib.sha256()
+    cs = os.path.join(ROOT, "selectivenet_for_semantic_segmentation_binary_b200", "csrc")
+    files = sorted(os.path.join(cs, f) for f in os.listdir(cs) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(ROOT, "include", "sunet_b200.h"))
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic():
+    """DRAM bytes per G1 launch from the newest committed ncu launch list whose kernel-source stamp matches."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for rnd in sorted(os.listdir(pdir), reverse=True):
+        tj = os.path.join(pdir, rnd, "roofline_traffic.json")
+        if os.path.exists(tj):
+            with open(tj) as f:
+                t = json.load(f)
+            t["file"] = os.path.relpath(tj, ROOT)
+            best = t
+            break
+    if best is None:
+        return None, "no roofline_traffic.json under profiles/"
+    if best.get("kernel_sha") != kernel_source_sha():
+        return None, (f"stale: {best['file']} was captured on kernel sources {best.get('kernel_sha', 'unstamped')}, "
+                      f"this build is {kernel_source_sha()}")
+    return best["dram_bytes_per_launch"], best["source"] + f" [{best['file']}, kernel_sha {best['kernel_sha']}]"
+
+
+# --------------------------------------------------------------------------------------- stock-PyTorch GPU baseline
+def stock_gpu_baseline(batch: int, size: int, steps: int = 3):
+    """BASELINE.md §4 / SURVEY §8(d) "GPU timing": the reference's layer graph (model.py:18-103, losses
+    selective_loss.py:58-85 + BCEWithLogits, Adam) executed by STOCK PyTorch layers (cuDNN / cuBLAS / ATen) on the
+    same GPU, same batch — fp32 as the reference is written (TF32 off) and under torch.autocast(bfloat16) with
+    channels_last.  The practical "kernel to beat"; nothing of this repo's engine is on this path."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    def cbr(i, o):
+        return nn.Sequential(nn.Conv2d(i, o, 3, 1, 1, bias=True), nn.BatchNorm2d(o), nn.ReLU())
+
+    class StockSUNetB(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.e11, self.e12 = cbr(3, 64), cbr(64, 64)
+            self.e21, self.e22 = cbr(64, 128), cbr(128, 128)
+            self.e31, self.e32 = cbr(128, 256), cbr(256, 256)
+            self.d42, self.d41 = cbr(256, 512), cbr(512, 512)
+            self.u3 = nn.ConvTranspose2d(512, 256, 2, 2)
+            self.d32, self.d31 = cbr(512, 256), cbr(256, 256)
+            self.u2 = nn.ConvTranspose2d(256, 128, 2, 2)
+            self.d22, self.d21 = cbr(256, 128), cbr(128, 128)
+            self.u1 = nn.ConvTranspose2d(128, 64, 2, 2)
+            self.d12, self.d11 = cbr(128, 64), cbr(64, 64)
+            self.h = nn.ModuleList([nn.Conv2d(64, 1, 1) for _ in range(3)])
+
+        def forward(self, x):
+            e1 = self.e12(self.e11(x))
+            e2 = self.e22(self.e21(F.max_pool2d(e1, 2)))
+            e3 = self.e32(self.e31(F.max_pool2d(e2, 2)))
+            d4 = self.d41(self.d42(F.max_pool2d(e3, 2)))
+            d3 = self.d31(self.d32(torch.cat((self.u3(d4), e3), 1)))
+            d2 = self.d21(self.d22(torch.cat((self.u2(d3), e2), 1)))
+            d1 = self.d11(self.d12(torch.cat((self.u1(d2), e1), 1)))
+            return tuple(h(d1).squeeze(1) for h in self.h)
+
+    def step(net, opt, x, label, autocast):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            o, s_, a = net(x)
+        o, s_, a = o.float(), s_.float(), a.float()
+        sg = torch.sigmoid(s_)
+        cov = sg.mean()
+        loss = (F.binary_cross_entropy_with_logits(o, label, reduction="none") * sg).mean() / cov
+        loss = loss + 2 * torch.clamp(0.8 - cov, min=0) ** 2 + F.binary_cross_entropy_with_logits(a, label)
+        loss.backward()
+        opt.step()
+        return loss
+
+    out = {}
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(1234)
+    x = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).cuda()
+    label = (torch.rand(batch, size, size, generator=g) < 0.4).float().cuda()
+    try:
+        for name, autocast in (("bf16_autocast_channels_last", True), ("fp32", False)):
+            try:
+                torch.manual_seed(0)
+                net = StockSUNetB().cuda()
+                xx = x.contiguous(memory_format=torch.channels_last) if autocast else x
+                if autocast:
+                    net = net.to(memory_format=torch.channels_last)
+                opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+                for _ in range(2):
+                    step(net, opt, xx, label, autocast)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(steps):
+                    loss = step(net, opt, xx, label, autocast)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                out[name] = {"value": batch / (ms / 1e3), "unit": "patches/s", "ms_per_step": ms, "batch": batch,
+                             "steps": steps, "loss": float(loss)}
+                del net, opt
+            except Exception as e:  # noqa: BLE001
+                out[name] = {"unavailable": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["what"] = ("reference layer graph on stock torch.nn layers (cuDNN/cuBLAS/ATen), same GPU, same batch, CUDA-event "
+                   "timed, eager; selective loss + aux BCE + Adam; 2 warm-up steps")
+    return out
+
+
+# --------------------------------------------------------------------------------------- BASELINE configs[3]: evaluation
+def eval_block(net, world, rank, dev, n_total, size, batch, K, torch, dist):
+    """SUNet_B eval with --select_eval 1 over n_total synthetic patches sharded across the ranks (eval.py path:
+    eval-mode forward, float32-sigmoid thresholding, coverage-masked confusion matrix), one CUDA graph per batch;
+    plus the counting kernel alone (HBM roofline: 9 B per pixel)."""
+    from selectivenet_for_semantic_segmentation_binary_b200.trainer import chunk_bounds
+    from selectivenet_for_semantic_segmentation_binary_b200.utils.compute_metric import Evaluator, logit_threshold
+    lo, hi = chunk_bounds(n_total, world, rank)
+    n_full = (hi - lo) // batch
+    was_training = net.training
+    net.train(False)
+    ev = Evaluator(2, True, device=dev)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    sx = torch.rand(batch, 3, size, size, generator=g, device=dev) * 2 - 1
+    sl = (torch.rand(batch, size, size, generator=g, device=dev) < 0.4).to(torch.uint8)
+
+    def run(x, lab):
+        out, sel, _ = net(x)
+        ev.add_batch_from_logits(lab, out, sel, cut_off=0.5, s_cut_off=0.5, path="eval")
+
+    with torch.no_grad():
+        run(sx, sl)
+        run(sx, sl)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run(sx, sl)
+        ev.reset()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_full):
+            graph.replay()
+        tail = (hi - lo) - n_full * batch
+        if tail:
+            run(sx[:tail].contiguous(), sl[:tail].contiguous())
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    counts = ev.counts_tensor().clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts)
+    # the histogram kernel alone: fp32 out + fp32 sel + uint8 labels of 512 patches = 302 MB per launch (> 126 MB L2)
+    P = 512 * size * size
+    lg = torch.randn(2, P, device=dev)
+    hl = (torch.rand(P, device=dev) < 0.4).to(torch.uint8)
+    cnt = torch.zeros(6, dtype=torch.int64, device=dev)
+    thr = logit_threshold(0.5, "eval")
+    for _ in range(3):
+        K.metric_hist(lg[0], lg[1], hl, thr, thr, True, cnt)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    h0.record()
+    for _ in range(reps):
+        K.metric_hist(lg[0], lg[1], hl, thr, thr, True, cnt)
+    h1.record()
+    torch.cuda.synchronize(dev)
+    hist_gbps = 9.0 * P * reps / (h0.elapsed_time(h1) * 1e-3) / 1e9
+    del lg, hl
+    net.train(was_training)
+    c = counts.cpu().tolist()
+    return {"workload": f"SUNet_B eval --select_eval 1, {n_total} synthetic {size}x{size} patches sharded over {world} "
+                        f"GPU(s), batch {batch} per GPU (BASELINE configs[3])",
+            "value": n_total / (float(t.item()) / 1e3), "unit": "patches/s", "ms_total": float(t.item()),
+            "per_gpu_patches": hi - lo, "pixels_counted": c[5], "pixels_selected": c[4], "confusion_matrix": c[:4],
+            "pixels_expected": n_total * size * size,
+            "metric_hist": {"achieved": hist_gbps, "unit": "GB/s", "algorithmic_bytes_per_pixel": 9,
+                            "pixels_per_launch": P, "l2": "inputs_exceed_l2 (302 MB per launch)"}}
+
+
+# --------------------------------------------------------------------------------------- data-parallel parity (N > 1)
+def dp_parity_block(world, rank, dev, group, torch, dist):
+    """One small SUNetTrainer step on real NCCL ranks (uneven shards on purpose) against the CPU oracle emulating
+    nn.DataParallel (train.py:132-134,194-201): per-replica BatchNorm statistics, loss on the gathered
+    global batch, gradients summed over replicas.  The oracle is the checker here, nothing of it is timed."""
+    from selectivenet_for_semantic_segmentation_binary_b200.model import UNet_B
+    from selectivenet_for_semantic_segmentation_binary_b200.trainer import SUNetTrainer, shard_bounds
+    total, size = 2 * world + 1, 64
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(total, 3, size, size, generator=g) * 2 - 1
+    label = (torch.rand(total, size, size, generator=g) < 0.4).float()
+    torch.manual_seed(0)
+    net = UNet_B("RGB", selective=True).to(dev)
+    net.train()
+    tr = SUNetTrainer(net, lr=0.0, s_lamb=2, process_group=group, world_size=world, use_cuda_graph=False)
+    lo, hi = shard_bounds(total, world, rank)
+    res = tr.step(x[lo:hi].to(dev), label[lo:hi].to(dev)).clone()
+    torch.cuda.synchronize(dev)
+    flat = tr.fg.flat.clone()
+    chk = torch.stack([flat.double().sum(), flat.double().abs().sum()])
+    lst = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(lst, chk)
+    out = None
+    if rank == 0:
+        from oracle import sunet_oracle as O
+        sd = O.init_state_dict(0, "RGB", True)
+        names = [n for n, _ in net.named_parameters()]
+        for n in names:
+            sd[n].requires_grad_(True)
+        outs = []
+        for r in range(world):                            # one replica per shard, own BN statistics
+            a, b = shard_bounds(total, world, r)
+            outs.append(O.unet_b_forward(sd, x[a:b], True, True, update_running=(r == 0)))
+        o, s_, a_ = (torch.cat([t[i] for t in outs]) for i in range(3))
+        l_sel, cov = O.selective_risk_b(o, s_, label, lamb=2)
+        loss = l_sel + O.bce_with_logits_mean(a_, label)
+        loss.backward()
+        got = res.cpu().tolist()
+        worst, worst_name = 1.0, ""
+        for n in names:
+            if n.endswith(".0.bias") and "layer" in n:
+                continue
+            off, k = tr.fg.offsets[n]
+            gg = flat[off:off + k].cpu().double()
+            rr = sd[n].grad.flatten().double()
+            c = (gg @ rr / (gg.norm() * rr.norm()).clamp_min(1e-30)).item()
+            if c < worst:
+                worst, worst_name = c, n
+        out = {"ranks": world, "global_batch": total, "shards": [shard_bounds(total, world, r) for r in range(world)],
+               "patch": size, "loss_ours": got[3], "loss_oracle": float(loss), "loss_vs_oracle": abs(got[3] - float(loss)) / abs(float(loss)),
+               "coverage_ours": got[1], "coverage_oracle": float(cov),
+               "coverage_vs_oracle": abs(got[1] - float(cov)) / abs(float(cov)),
+               "worst_grad_cos": worst, "worst_grad_tensor": worst_name,
+               "grads_identical_on_all_ranks": all(torch.equal(lst[0], t) for t in lst),
+               "pass": bool(abs(got[3] - float(loss)) / abs(float(loss)) < 2e-2 and worst > 0.90 and
+                            all(torch.equal(lst[0], t) for t in lst)),
+               "oracle": "CPU oracle with one BatchNorm replica per shard, loss on the gathered batch, summed gradients"}
+    del tr, net
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------- reference arm
 def cpu_reference_step_rate(steps: int, warmup: int, batch: int = 4):
     """The reference's CPU path (PyTorch fp32 on the host cores), restated by oracle/sunet_oracle.py:
@@ -99,7 +360,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    # every step is a bounded 4-patch sample of the 128-patch batch (~1 s of CPU work), so the requested
+    # --steps / --warmup are honoured as given (capped at 60 + 10 to keep the run within a few minutes)
+    steps, warmup = max(1, min(args.steps, 60)), max(0, min(args.warmup, 10))
     pps, sec, cores = cpu_reference_step_rate(steps, warmup, batch=4)
     line = {
         "impl": "reference", "metric": "SUNet_B train patches/sec (256^2, bf16)", "value": pps, "unit": "patches/s",
@@ -143,6 +406,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         group = dist.group.WORLD
     lib = _lib.load()
+
+    dp_parity = None
+    if world > 1 and not args.no_dp_parity:
+        dp_parity = dp_parity_block(world, rank, dev, group, torch, dist)
 
     gb = args.batch
     lo, hi = chunk_bounds(gb, world, rank)
@@ -306,6 +573,19 @@ def run_ours(args):
     if rank != 0:
         roof = None
 
+    evalb = None
+    if not args.no_eval:
+        evalb = eval_block(net, world, rank, dev, args.eval_patches, args.size, min(128, max(1, args.eval_patches // world)),
+                           K, torch, dist)
+    graph_on = tr.graph_active("train")
+    stock = None
+    if rank == 0 and world == 1 and not args.no_stock:
+        # free this repo's plan buffers first: the stock fp32 graph keeps ~0.8 GB of activations per patch
+        tr._graphs.clear()
+        net._plans.clear()
+        torch.cuda.empty_cache()
+        stock = stock_gpu_baseline(gb, args.size)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pps, sec, cores = cpu_reference_step_rate(3, 1, batch=4)
@@ -323,7 +603,7 @@ def run_ours(args):
                                    "selective risk + bwd + Adam + confusion matrix, 256x256 RGB patches, random init",
                        "global_batch": gb, "per_gpu_batch": b, "patch": args.size, "parallelism": f"dp{world}",
                        "l2": "inputs_exceed_l2 (activations ~120 MB/patch >> 126 MB L2)",
-                       "cuda_graph": bool(tr.use_graph)},
+                       "cuda_graph": bool(graph_on)},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbps_measured": h2d_gbps,
                     "pipeline": "pinned host -> device copy of step i+1 overlaps step i; the 4 loss scalars of every "
@@ -337,18 +617,21 @@ def run_ours(args):
             "last_losses": [float(v) for v in res_host.tolist()] if res_host is not None else None,
         }
         if roof is not None:
-            tj = os.path.join(ROOT, "profiles", "r01", "roofline_traffic.json")
-            if os.path.exists(tj):               # DRAM bytes per launch from the committed ncu launch list
-                with open(tj) as f:
-                    t = json.load(f)
-                roof["traffic"] = t["dram_bytes_per_launch"]
-                roof["traffic_source"] = t["source"]
+            # DRAM bytes per launch from the committed ncu launch list of THIS build (null when the stamp is stale)
+            roof["traffic"], roof["traffic_source"] = measured_traffic()
             roof["peak"] = pk["bf16"]
             roof["frac"] = roof["achieved"] / pk["bf16"]
             roof["peak_source"] = pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)"
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if stock is not None:
+            line["stock_gpu_baseline"] = stock
+        if evalb is not None:
+            line["eval"] = evalb
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
+        line["kernel_sha"] = kernel_source_sha()
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL collectives keep the communicator busy: destroy_process_group()
@@ -457,6 +740,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-u8", action="store_true", help="skip the extra end-to-end pass fed with uint8 patches")
     ap.add_argument("--launch-table", default=None, help="write per-launch tensor-core timings of one step here")
+    ap.add_argument("--no-stock", action="store_true", help="skip the stock-PyTorch (cuDNN) GPU baseline leg")
+    ap.add_argument("--no-eval", action="store_true", help="skip the evaluation block (BASELINE configs[3])")
+    ap.add_argument("--no-dp-parity", action="store_true", help="skip the data-parallel parity step (N > 1)")
+    ap.add_argument("--eval-patches", type=int, default=10000)
     args = ap.parse_args()
     LAUNCH_TABLE[0] = args.launch_table
     if args.impl == "reference":

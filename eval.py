@@ -2,11 +2,18 @@
 
     python3 eval.py --model_dir ./model --selective 1 --select_eval 1 --local_rank 0 1 2 3 4 5 6 7 --synthetic 10000
 
-Forward in eval mode (BatchNorm folded from running statistics), thresholding with the float32 numpy
-semantics of eval.py:175-179 (`--cut_off`, `--s_cut_off`, `--single_scale`) and the coverage-masked
-confusion matrix, all on the GPU; patches are sharded across the ids of ``--local_rank`` (one process per
-GPU) and the six integer counters are all-reduced once at the end.  Single checkpoint only (the
-reference's ensemble branch does not support selection and is out of scope).
+Forward in eval mode (BatchNorm folded from running statistics into the conv epilogues), thresholding with the
+float32 numpy semantics of eval.py:175-179 (``--cut_off``, ``--s_cut_off``, ``--single_scale``) and the
+coverage-masked confusion matrix, all on the GPU; patches are sharded across the ids of ``--local_rank`` (one process
+per GPU) and the six integer counters are all-reduced once at the end.
+
+Every ``*.pth`` in ``--model_dir`` is loaded (eval.py:116-123).  One checkpoint: the single-model branch
+(eval.py:198-206).  Several: the ensemble branch (eval.py:208-222) — each net's output map is re-scaled with
+``--ens_scale`` (None / clip / minmax over the batch tensor / sigmoid), the maps are averaged in numpy's float32 order
+by one kernel (``sunet_ensemble_mean``) and the mean is thresholded like a single output.  As in the reference the
+ensemble branch has no selection ("selective 불가", eval.py:208).  ``--single_scale``: only ``sigmoid`` changes the
+decision (eval.py:232-233); ``None`` / ``clip`` / ``minmax`` compare the raw value with the cut-off, exactly like the
+reference, whose main loop never applies the clip / minmax lambdas.
 """
 import argparse
 import os
@@ -45,7 +52,8 @@ def parse_arguments(argv=None):
     parser.add_argument('--save_dir', type=str, default='./output', help='saving results')
     # additions
     parser.add_argument('--synthetic', type=int, default=0, help='evaluate this many synthetic patches')
-    parser.add_argument('--random_init', type=bool, default=False, help='no checkpoint: seeded random weights')
+    parser.add_argument('--random_init', type=int, default=0,
+                        help='no checkpoint: this many seeded random-weight models (1 = single model, >1 = ensemble)')
     parser.add_argument('--master_port', type=int, default=29534)
     args = parser.parse_args(argv)
     print('')
@@ -53,12 +61,37 @@ def parse_arguments(argv=None):
     return args
 
 
+def load_nets(args, dev):
+    """eval.py:116-157: one net per checkpoint in --model_dir (sorted), eval mode."""
+    from selectivenet_for_semantic_segmentation_binary_b200.model import UNet_B
+    from selectivenet_for_semantic_segmentation_binary_b200.utils.net_utils import net_test_load
+    nets = []
+    if args.random_init:
+        for i in range(int(args.random_init)):
+            torch.manual_seed(i)
+            nets.append(UNet_B(args.input_type, selective=args.selective))
+    else:
+        model_list = sorted([c for c in os.listdir(args.model_dir) if 'pth' in c])
+        if not model_list:
+            raise SystemExit(f'no checkpoint (*.pth) in {args.model_dir}')
+        for name in model_list:
+            model_path = os.path.join(args.model_dir, name)
+            if args.info_print:
+                print(f'    {model_path} - UNet_B / SelectiveNet: {args.selective}')
+            net = UNet_B(args.input_type, selective=args.selective)
+            nets.append(net_test_load(model_path, net, device='cpu'))
+    nets = [n.to(dev) for n in nets]
+    for n in nets:
+        n.train(False)
+        n._plans = nets[0]._plans        # same shapes: one set of activation buffers serves every member
+    return nets
+
+
 def eval_worker(rank, world, args, ret=None):
     import torch.distributed as dist
-    from selectivenet_for_semantic_segmentation_binary_b200.model import UNet_B
+    from selectivenet_for_semantic_segmentation_binary_b200 import kernels as K
     from selectivenet_for_semantic_segmentation_binary_b200.trainer import chunk_bounds
     from selectivenet_for_semantic_segmentation_binary_b200.utils.compute_metric import Evaluator
-    from selectivenet_for_semantic_segmentation_binary_b200.utils.net_utils import net_test_load
 
     gpu = args.local_rank[rank]
     torch.cuda.set_device(gpu)
@@ -67,34 +100,53 @@ def eval_worker(rank, world, args, ret=None):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', str(args.master_port))
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
-    torch.manual_seed(0)
-    net = UNet_B(args.input_type, selective=args.selective)
-    if not args.random_init:
-        model_list = sorted([c for c in os.listdir(args.model_dir) if 'pth' in c])
-        if len(model_list) != 1:
-            raise SystemExit(f'expected exactly one checkpoint in {args.model_dir} (ensembles are out of scope)')
-        net = net_test_load(os.path.join(args.model_dir, model_list[0]), net, device='cpu')
-    net = net.to(dev)
-    net.train(False)
     if args.select_eval and not args.selective:
         raise SystemExit('--select_eval needs --selective')
+    nets = load_nets(args, dev)
+    ensemble = len(nets) > 1
+    if ensemble and args.selective:
+        raise SystemExit('the ensemble branch has no selection (eval.py:208 "ensemble, selective 불가"): '
+                         'use one checkpoint with --selective, or non-selective checkpoints for an ensemble')
     evaluator = Evaluator(num_class=args.n_cls, selective=args.select_eval, device=dev)
-    if args.single_scale not in ('sigmoid', 'None'):
-        raise SystemExit("--single_scale clip/minmax are not built (DESIGN.md §6)")
+    ws = K.new_workspace(dev)
 
-    n_total = args.synthetic
-    if n_total <= 0:
-        raise SystemExit('no dataset ships with the reference: pass --synthetic N (DESIGN.md §6)')
+    in_ch, size, bs = nets[0].input_ch, args.patch_size, args.batch_size
+    data = None
+    if args.synthetic > 0:
+        n_total = args.synthetic
+    else:
+        from selectivenet_for_semantic_segmentation_binary_b200.utils.data_utils import PatchArrays, construct_test
+        if not os.path.exists(f'{args.data_dir}/{args.test_fold}-fold_tumorable_data.npy'):
+            raise SystemExit(f'no fold lists under {args.data_dir}: pass --synthetic N to evaluate synthetic patches')
+        test_list = construct_test(args.data_dir, test_fold=args.test_fold)
+        data = PatchArrays(args.data_dir, test_list, args.patch_mag, args.patch_size, args.input_type, train=False)
+        n_total = len(data)
+        if args.info_print:
+            print(f'    # of test dataset {n_total}')
     lo, hi = chunk_bounds(n_total, world, rank)
-    in_ch, size, bs = net.input_ch, args.patch_size, args.batch_size
     print("Model Prediction...") if rank == 0 else None
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ens_buf = {}
 
     def run_batch(x, label):
-        if args.selective:
-            output, selection, _ = net(x)
+        if not ensemble:
+            if args.selective:
+                output, selection, _ = nets[0](x)
+            else:
+                output, selection = nets[0](x), None
         else:
-            output, selection = net(x), None
+            # eval.py:209-222: re-scale every member's map, mean over members in float32 (one kernel)
+            n = x.shape[0]
+            if n not in ens_buf:
+                ens_buf[n] = ([torch.empty(n, size, size, device=dev) for _ in nets],
+                              [torch.empty(2, device=dev) for _ in nets], torch.empty(n, size, size, device=dev))
+            maps, mm, mean = ens_buf[n]
+            for net, m, e in zip(nets, maps, mm):
+                m.copy_(net(x))
+                if args.ens_scale == 'minmax':
+                    K.minmax_f32(m, e, ws)
+            K.ensemble_mean(maps, args.ens_scale, mean, minmax=mm if args.ens_scale == 'minmax' else None)
+            output, selection = mean, None
         evaluator.add_batch_from_logits(label, output, selection if args.select_eval else None,
                                         cut_off=args.cut_off, s_cut_off=args.s_cut_off, path='eval',
                                         scale=args.single_scale)
@@ -105,15 +157,21 @@ def eval_worker(rank, world, args, ret=None):
         label = (torch.rand(n, size, size, generator=g, device=dev) < 0.4).to(torch.uint8)
         return x, label
 
-    # Full batches replay one CUDA graph (forward + thresholding + masked counting: ~65 launches that would
-    # otherwise be issued from Python per batch); the ragged tail, if any, runs eagerly.
+    def real_batches():
+        idx = list(range(lo, hi))
+        for i in range(0, len(idx), bs):
+            xs, ys = zip(*(data._load(j) for j in idx[i:i + bs]))
+            yield (torch.from_numpy(np.stack(xs)).to(dev), torch.from_numpy(np.stack(ys)).to(dev))
+
+    # Full batches replay one CUDA graph (forward + thresholding + masked counting: ~65 launches per member that
+    # would otherwise be issued from Python per batch); the ragged tail, if any, runs eagerly.
     graph, sx, sl = None, None, None
     n_full = (hi - lo) // bs
     with torch.no_grad():
         if n_full >= 2 and not args.no_graph:
             sx = torch.zeros(bs, in_ch, size, size, device=dev)
             sl = torch.zeros(bs, size, size, dtype=torch.uint8, device=dev)
-            net(sx)                                                          # plan allocation, not timed / not counted
+            nets[0](sx)                                                      # plan allocation, not timed / not counted
             saved = evaluator._ensure(dev).clone()
             run_batch(sx, sl)                                                # lazy one-time work outside capture
             torch.cuda.synchronize(dev)
@@ -121,15 +179,17 @@ def eval_worker(rank, world, args, ret=None):
             with torch.cuda.graph(graph):
                 run_batch(sx, sl)
             evaluator.counts_tensor().copy_(saved)                           # the warm-up batch was not data
-        else:
-            net(torch.zeros(min(bs, hi - lo), in_ch, size, size, device=dev))
+        elif hi > lo:
+            nets[0](torch.zeros(min(bs, hi - lo), in_ch, size, size, device=dev))
     torch.cuda.synchronize(dev)
     t0.record()
     with torch.no_grad():
-        for start in range(lo, hi, bs):
-            n = min(bs, hi - start)
-            x, label = make_batch(start, n)
-            if graph is not None and n == bs:
+        if data is None:
+            batches = (make_batch(start, min(bs, hi - start)) for start in range(lo, hi, bs))
+        else:
+            batches = real_batches()
+        for x, label in batches:
+            if graph is not None and x.shape[0] == bs:
                 sx.copy_(x)
                 sl.copy_(label)
                 graph.replay()
@@ -139,9 +199,9 @@ def eval_worker(rank, world, args, ret=None):
     torch.cuda.synchronize(dev)
     secs = t0.elapsed_time(t1) / 1e3
     if rank == 0:       # forward + thresholding + masked confusion-matrix counting, synthetic batches made on the device
-        print(f'    throughput: {round((hi - lo) / secs, 1)} patches/s per GPU ({hi - lo} patches of {size}x{size} in '
-              f'{round(secs, 3)} s, x{world} GPUs)')
-    counts = evaluator.counts_tensor().clone()
+        print(f'    throughput: {round((hi - lo) / max(secs, 1e-9), 1)} patches/s per GPU ({hi - lo} patches of '
+              f'{size}x{size} in {round(secs, 3)} s, x{world} GPUs, {len(nets)} model(s))')
+    counts = evaluator._ensure(dev).clone()
     if world > 1:
         dist.all_reduce(counts)
         dist.destroy_process_group()
@@ -166,14 +226,15 @@ def eval_worker(rank, world, args, ret=None):
         print(f'    IoU_class:{IoU_class}')
         if ret is not None:
             ret['counts'] = c.tolist()
+            ret['patches_per_s_per_gpu'] = (hi - lo) / max(secs, 1e-9)
         return CM
 
 
-def main(argv=None):
+def main(argv=None, ret=None):
     args = parse_arguments(argv)
     world = len(args.local_rank)
     if world == 1:
-        return eval_worker(0, 1, args)
+        return eval_worker(0, 1, args, ret)
     import torch.multiprocessing as mp
     mp.spawn(eval_worker, args=(world, args), nprocs=world, join=True)
 

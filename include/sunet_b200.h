@@ -30,7 +30,7 @@ extern "C" {
 
 typedef struct CUstream_st* sunet_stream_t;
 
-#define SUNET_ABI_VERSION 1
+#define SUNET_ABI_VERSION 2
 /* workspace every reduce-type call may use (bytes); callers pass one buffer of at least this size */
 #define SUNET_WORKSPACE_BYTES (8u << 20)
 
@@ -264,19 +264,21 @@ int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const
  * three sums in between (the reference computes the loss on the gathered global batch).
  * ---------------------------------------------------------------------------------------- */
 /* sums[0] = sum sigmoid(sel), sums[1] = sum bce(out,t)*sigmoid(sel), sums[2] = sum bce(aux,t)   (fp64)
- * any of out/sel/aux may be NULL (its sums stay 0) */
+ * any of out/sel/aux may be NULL (its sums stay 0).  pixels_out (optional, device) receives (double)pixels, so a
+ * data-parallel caller can all-reduce [S, R, A, pixels] as one buffer and uneven shards need no host bookkeeping. */
 int sunet_loss_sums(const float* out, const float* sel, const float* aux, const float* target, long long pixels,
-                    double* sums, void* workspace, size_t workspace_bytes, sunet_stream_t stream);
+                    double* sums, double* pixels_out, void* workspace, size_t workspace_bytes, sunet_stream_t stream);
 /* results[0] = selective loss (risk + lamb*max(0, cov_target - c)^2), [1] = coverage c,
- * [2] = aux BCE mean, [3] = total;  P = global pixel count */
-int sunet_loss_finalize(const double* sums, long long global_pixels, float lamb, float target_coverage,
-                        float* results, sunet_stream_t stream);
+ * [2] = aux BCE mean, [3] = total;  P = global pixel count: global_pixels, or *global_pixels_dev when that device
+ * pointer is not NULL (the all-reduced count; keeps a captured CUDA graph valid for any shard split) */
+int sunet_loss_finalize(const double* sums, long long global_pixels, const double* global_pixels_dev, float lamb,
+                        float target_coverage, float* results, sunet_stream_t stream);
 /* per-pixel gradients given the (global) sums; g_sel / g_aux = upstream grads of the two losses
- * (device scalars, NULL = 1.0).  Outputs may be NULL. */
+ * (device scalars, NULL = 1.0).  Outputs may be NULL.  global_pixels_dev as above. */
 int sunet_loss_bwd(const float* out, const float* sel, const float* aux, const float* target, long long pixels,
-                   const double* sums, long long global_pixels, float lamb, float target_coverage,
-                   const float* g_sel, const float* g_aux, float* d_out, float* d_sel, float* d_aux,
-                   sunet_stream_t stream);
+                   const double* sums, long long global_pixels, const double* global_pixels_dev, float lamb,
+                   float target_coverage, const float* g_sel, const float* g_aux, float* d_out, float* d_sel,
+                   float* d_aux, sunet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Metrics: thresholding + Evaluator confusion matrix (train.py:211-239, eval.py:228-251,
@@ -289,6 +291,19 @@ int sunet_loss_bwd(const float* out, const float* sel, const float* aux, const f
  * counts are ACCUMULATED (caller zeroes them at reset()). */
 int sunet_metric_hist(const float* out, const float* sel, const void* label, int label_dtype, long long pixels,
                       float thr_out, float thr_sel, int masked, unsigned long long* counts, sunet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation ensemble (eval.py:116-123 model list, :209-222 mean of re-scaled outputs; scaling lambdas
+ * eval.py:162-179).  mean[p] = (((s(map_0[p]) + s(map_1[p])) + ...) / n_models in float32, the order and rounding of
+ * numpy's np.mean(np.asarray(outputs), axis=0) — bit-identical for scale NONE / CLIP / MINMAX (SIGMOID uses CUDA's
+ * expf).  `maps` and `minmax` are HOST arrays of n_models DEVICE pointers (each map fp32 [pixels], 16-byte aligned;
+ * minmax[m] -> device (min, max) of map m over the whole batch tensor as written by sunet_minmax_f32, MINMAX only).
+ * ---------------------------------------------------------------------------------------- */
+enum { SUNET_SCALE_NONE = 0, SUNET_SCALE_CLIP = 1, SUNET_SCALE_MINMAX = 2, SUNET_SCALE_SIGMOID = 3 };
+int sunet_minmax_f32(const float* x, long long n, float* out_min_max, void* workspace, size_t workspace_bytes,
+                     sunet_stream_t stream);
+int sunet_ensemble_mean(const float* const* maps, const float* const* minmax, int n_models, long long pixels,
+                        int scale, float* mean, sunet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer: Adam over a table of tensors in one launch (train.py:88-92,209)

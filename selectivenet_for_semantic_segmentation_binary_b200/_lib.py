@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("SUNET_LIB") or os.path.join(_HERE, "libsunet_b200.so"
 A_CONV3X3, A_PLAIN, A_GATHER2X2 = 0, 1, 2
 D_NHWC, D_SCATTER2X2 = 0, 1
 WORKSPACE_BYTES = 8 << 20
+SCALE_MODES = {"None": 0, "clip": 1, "minmax": 2, "sigmoid": 3}
 
 
 class SunetError(RuntimeError):
@@ -103,10 +104,12 @@ SIGNATURES = {
     "sunet_heads_bwd_bn_rows": [_ll],
     "sunet_heads_bwd_bn": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                            _vp, _vp, _i, _ll, _vp, _sz, _vp],
-    "sunet_loss_sums": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _sz, _vp],
-    "sunet_loss_finalize": [_vp, _ll, _f, _f, _vp, _vp],
-    "sunet_loss_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _ll, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "sunet_loss_sums": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _sz, _vp],
+    "sunet_loss_finalize": [_vp, _ll, _vp, _f, _f, _vp, _vp],
+    "sunet_loss_bwd": [_vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "sunet_metric_hist": [_vp, _vp, _vp, _i, _ll, _f, _f, _i, _vp, _vp],
+    "sunet_minmax_f32": [_vp, _ll, _vp, _vp, _sz, _vp],
+    "sunet_ensemble_mean": [_vp, _vp, _i, _ll, _i, _vp, _vp],
     "sunet_adam_step": [_vp, _i, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp],
 }
 _RESTYPES = {"sunet_last_error": C.c_char_p, "sunet_launch_count": C.c_longlong}

@@ -21,6 +21,11 @@ static inline int grid_for(long long items, int threads, int per_sm) {
   return (int)b;
 }
 
+static inline bool aligned16(const void* a, const void* b, const void* c, const void* d) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+}
+
 struct alignas(16) bf16x8 {
   uint32_t w[4];
 };
@@ -313,19 +318,30 @@ struct HeadG {
   float* dw[3];
   float* db[3];
 };
-__global__ void heads_bwd_reduce_kernel(const float* __restrict__ partials, int blocks, int nheads, HeadG hg) {
+// one block per output (3 heads x (64 weight grads + 1 bias grad)); the per-block partial rows are summed in a
+// fixed order (strided per thread, then a shared-memory tree), so the result does not depend on scheduling
+__global__ void __launch_bounds__(128)
+heads_bwd_reduce_kernel(const float* __restrict__ partials, int blocks, int nheads, HeadG hg) {
   pdl_wait();
   pdl_trigger();
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= 3 * 65) return;
+  __shared__ double red[128];
+  const int o = blockIdx.x;
   const int h = o / 65, c = o % 65;
   if (h >= nheads) return;
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)partials[(size_t)b * 195 + o];
-  if (c < 64) {
-    if (hg.dw[h]) hg.dw[h][c] = (float)s;
-  } else {
-    if (hg.db[h]) hg.db[h][0] = (float)s;
+  for (int b = threadIdx.x; b < blocks; b += 128) s += (double)partials[(size_t)b * 195 + o];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 64; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (c < 64) {
+      if (hg.dw[h]) hg.dw[h][c] = (float)red[0];
+    } else {
+      if (hg.db[h]) hg.db[h][0] = (float)red[0];
+    }
   }
 }
 
@@ -336,6 +352,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Streaming kernels below read 16 bytes per array per thread per trip (float4 / uchar4 / 2 x longlong2) when every
+// pointer is 16-byte aligned (VEC = 4; the launcher falls back to VEC = 1 otherwise); the last pixels % 4 are taken
+// by the first threads of block 0 as scalars.
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <int VEC>
 __global__ void __launch_bounds__(256)
 loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ sel, const float* __restrict__ aux,
                  const float* __restrict__ tgt, long long P, double* __restrict__ partials) {
@@ -343,14 +365,34 @@ loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ sel, c
   pdl_trigger();
   __shared__ float red[8][3];
   float S = 0.f, R = 0.f, A = 0.f;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
-    const float t = __ldg(tgt + p);
+  auto pixel = [&](float t, float xs, float xo, float xa) {
     if (sel) {
-      const float s = sigmoid_acc(__ldg(sel + p));
+      const float s = sigmoid_acc(xs);
       S += s;
-      if (out) R = fmaf(bce_logits(__ldg(out + p), t), s, R);
+      if (out) R = fmaf(bce_logits(xo, t), s, R);
     }
-    if (aux) A += bce_logits(__ldg(aux + p), t);
+    if (aux) A += bce_logits(xa, t);
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (VEC == 4) {
+    const long long nq = P >> 2;
+    for (long long q = tid; q < nq; q += stride) {
+      const float4 t = ldg4(tgt + 4 * q);
+      float4 xs = make_float4(0.f, 0.f, 0.f, 0.f), xo = xs, xa = xs;
+      if (sel) xs = ldg4(sel + 4 * q);
+      if (out) xo = ldg4(out + 4 * q);
+      if (aux) xa = ldg4(aux + 4 * q);
+      pixel(t.x, xs.x, xo.x, xa.x);
+      pixel(t.y, xs.y, xo.y, xa.y);
+      pixel(t.z, xs.z, xo.z, xa.z);
+      pixel(t.w, xs.w, xo.w, xa.w);
+    }
+    const long long p = (nq << 2) + tid;          // tail (at most 3 pixels)
+    if (p < P) pixel(__ldg(tgt + p), sel ? __ldg(sel + p) : 0.f, out ? __ldg(out + p) : 0.f, aux ? __ldg(aux + p) : 0.f);
+  } else {
+    for (long long p = tid; p < P; p += stride)
+      pixel(__ldg(tgt + p), sel ? __ldg(sel + p) : 0.f, out ? __ldg(out + p) : 0.f, aux ? __ldg(aux + p) : 0.f);
   }
   S = warp_sum(S);
   R = warp_sum(R);
@@ -368,19 +410,39 @@ loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ sel, c
     partials[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
   }
 }
-__global__ void loss_sums_final_kernel(const double* __restrict__ partials, int blocks, double* sums) {
+// fixed-order fold of the per-block partials: thread t sums rows t, t+256, ... then a shared-memory tree
+__global__ void __launch_bounds__(256) loss_sums_final_kernel(const double* __restrict__ partials, int blocks,
+                                                              double* sums, double* pixels_out, double pixels) {
   pdl_wait();
   pdl_trigger();
-  if (threadIdx.x < 3) {
-    double s = 0.0;
-    for (int b = 0; b < blocks; ++b) s += partials[(size_t)b * 3 + threadIdx.x];
-    sums[threadIdx.x] = s;
+  __shared__ double red[3][256];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int b = threadIdx.x; b < blocks; b += 256) {
+    s0 += partials[(size_t)b * 3 + 0];
+    s1 += partials[(size_t)b * 3 + 1];
+    s2 += partials[(size_t)b * 3 + 2];
   }
+  red[0][threadIdx.x] = s0;
+  red[1][threadIdx.x] = s1;
+  red[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + w];
+      red[1][threadIdx.x] += red[1][threadIdx.x + w];
+      red[2][threadIdx.x] += red[2][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) sums[threadIdx.x] = red[threadIdx.x][0];
+  if (threadIdx.x == 3 && pixels_out) *pixels_out = pixels;
 }
-__global__ void loss_finalize_kernel(const double* sums, double P, float lamb, float tc, float* results) {
+__global__ void loss_finalize_kernel(const double* sums, double P, const double* P_dev, float lamb, float tc,
+                                     float* results) {
   pdl_wait();
   pdl_trigger();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (P_dev) P = *P_dev;
     const double S = sums[0], R = sums[1], A = sums[2];
     const double c = S / P;
     const double risk = (S != 0.0) ? R / S : 0.0 / 0.0;
@@ -394,13 +456,16 @@ __global__ void loss_finalize_kernel(const double* sums, double P, float lamb, f
   }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256)
 loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ sel, const float* __restrict__ aux,
-                const float* __restrict__ tgt, long long P, const double* __restrict__ sums, double Pg, float lamb,
-                float tc, const float* __restrict__ g_sel, const float* __restrict__ g_aux, float* __restrict__ d_out,
-                float* __restrict__ d_sel, float* __restrict__ d_aux) {
+                const float* __restrict__ tgt, long long P, const double* __restrict__ sums, double Pg,
+                const double* __restrict__ Pg_dev, float lamb, float tc, const float* __restrict__ g_sel,
+                const float* __restrict__ g_aux, float* __restrict__ d_out, float* __restrict__ d_sel,
+                float* __restrict__ d_aux) {
   pdl_wait();
   pdl_trigger();
+  if (Pg_dev) Pg = *Pg_dev;
   const double S = sums[0], R = sums[1];
   const float gs = g_sel ? *g_sel : 1.f;
   const float ga = g_aux ? *g_aux : 1.f;
@@ -409,14 +474,46 @@ loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ sel, co
   const float invS = (float)(1.0 / S);
   const float k_const = (float)(-R / (S * S) - 2.0 * (double)lamb * d / Pg);  // dL/ds_i minus the l_i/S term
   const float invP = (float)(1.0 / Pg);
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+  const bool sel_path = d_out || d_sel;
+  auto f_aux = [&](float xa, float t) { return ga * (sigmoid_acc(xa) - t) * invP; };
+  auto f_sel = [&](float xs, float xo, float t, float& go, float& gsl) {
+    const float s = sigmoid_acc(xs);
+    go = gs * s * (sigmoid_acc(xo) - t) * invS;
+    gsl = gs * s * (1.f - s) * fmaf(bce_logits(xo, t), invS, k_const);
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long p0 = tid;
+  if (VEC == 4) {
+    const long long nq = P >> 2;
+    for (long long q = tid; q < nq; q += stride) {
+      const float4 t = ldg4(tgt + 4 * q);
+      if (d_aux) {
+        const float4 xa = ldg4(aux + 4 * q);
+        *reinterpret_cast<float4*>(d_aux + 4 * q) = make_float4(f_aux(xa.x, t.x), f_aux(xa.y, t.y), f_aux(xa.z, t.z),
+                                                                f_aux(xa.w, t.w));
+      }
+      if (sel_path) {
+        const float4 xs = ldg4(sel + 4 * q), xo = ldg4(out + 4 * q);
+        float4 go, gl;
+        f_sel(xs.x, xo.x, t.x, go.x, gl.x);
+        f_sel(xs.y, xo.y, t.y, go.y, gl.y);
+        f_sel(xs.z, xo.z, t.z, go.z, gl.z);
+        f_sel(xs.w, xo.w, t.w, go.w, gl.w);
+        if (d_out) *reinterpret_cast<float4*>(d_out + 4 * q) = go;
+        if (d_sel) *reinterpret_cast<float4*>(d_sel + 4 * q) = gl;
+      }
+    }
+    p0 = (nq << 2) + tid;                         // tail (at most 3 pixels)
+  }
+  for (long long p = p0; p < P; p += stride) {
     const float t = __ldg(tgt + p);
-    if (d_aux) d_aux[p] = ga * (sigmoid_acc(__ldg(aux + p)) - t) * invP;
-    if (d_out || d_sel) {
-      const float s = sigmoid_acc(__ldg(sel + p));
-      const float x = __ldg(out + p);
-      if (d_out) d_out[p] = gs * s * (sigmoid_acc(x) - t) * invS;
-      if (d_sel) d_sel[p] = gs * s * (1.f - s) * fmaf(bce_logits(x, t), invS, k_const);
+    if (d_aux) d_aux[p] = f_aux(__ldg(aux + p), t);
+    if (sel_path) {
+      float go, gl;
+      f_sel(__ldg(sel + p), __ldg(out + p), t, go, gl);
+      if (d_out) d_out[p] = go;
+      if (d_sel) d_sel[p] = gl;
     }
   }
 }
@@ -429,25 +526,78 @@ __device__ __forceinline__ int load_label(const void* label, long long p) {
   const long long v = reinterpret_cast<const long long*>(label)[p];
   return (v >= 0 && v < 256) ? (int)v : 255;
 }
-
 template <int LT>
+__device__ __forceinline__ void load_label4(const void* label, long long q, int lab[4]) {
+  if (LT == 0) {
+    const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(label) + q);
+    lab[0] = v.x; lab[1] = v.y; lab[2] = v.z; lab[3] = v.w;
+  } else if (LT == 1) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(label) + q);
+    lab[0] = (int)(uint8_t)(int)v.x; lab[1] = (int)(uint8_t)(int)v.y;
+    lab[2] = (int)(uint8_t)(int)v.z; lab[3] = (int)(uint8_t)(int)v.w;
+  } else {
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(label) + 2 * q);
+    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(label) + 2 * q + 1);
+    lab[0] = (a.x >= 0 && a.x < 256) ? (int)a.x : 255; lab[1] = (a.y >= 0 && a.y < 256) ? (int)a.y : 255;
+    lab[2] = (b.x >= 0 && b.x < 256) ? (int)b.x : 255; lab[3] = (b.y >= 0 && b.y < 256) ? (int)b.y : 255;
+  }
+}
+
+// Coalesced, vectorised integer histogram: 4 pixels per thread per load (two groups in flight), six register
+// counters per thread, one warp reduction + six 64-bit atomics per block at the end (integers: order-independent).
+template <int LT, int VEC>
 __global__ void __launch_bounds__(256)
 metric_hist_kernel(const float* __restrict__ out, const float* __restrict__ sel, const void* __restrict__ label,
                    long long P, float thr_out, float thr_sel, int masked, unsigned long long* __restrict__ counts) {
   pdl_wait();
   pdl_trigger();
   __shared__ unsigned int red[8][6];
-  unsigned int c[6] = {0, 0, 0, 0, 0, 0};
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
-    const int pred = __ldg(out + p) >= thr_out ? 1 : 0;
-    int selected = 1;
-    if (sel) selected = __ldg(sel + p) >= thr_sel ? 1 : 0;
-    const int lab = load_label<LT>(label, p);
-    c[5] += 1;
-    c[4] += selected;
-    const bool use = (lab >= 0 && lab < 2) && (!masked || selected);
-    if (use) c[lab * 2 + pred] += 1;
+  unsigned int c00 = 0, c01 = 0, c10 = 0, c11 = 0, csel = 0, ctot = 0;
+  auto pixel = [&](float xo, float xs, int lab) {
+    const bool pred = xo >= thr_out;
+    const bool selected = sel ? (xs >= thr_sel) : true;
+    ctot += 1;
+    csel += selected ? 1u : 0u;
+    const bool use = (!masked || selected);
+    c00 += (use && lab == 0 && !pred) ? 1u : 0u;
+    c01 += (use && lab == 0 && pred) ? 1u : 0u;
+    c10 += (use && lab == 1 && !pred) ? 1u : 0u;
+    c11 += (use && lab == 1 && pred) ? 1u : 0u;
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long p0 = tid;
+  if (VEC == 4) {
+    const long long nq = P >> 2;
+    for (long long q = tid; q < nq; q += 2 * stride) {
+      const long long q2 = q + stride;
+      const bool two = q2 < nq;
+      int la[4], lb[4] = {0, 0, 0, 0};
+      const float4 oa = ldg4(out + 4 * q);
+      float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), ob = sa, sb = sa;
+      if (sel) sa = ldg4(sel + 4 * q);
+      load_label4<LT>(label, q, la);
+      if (two) {
+        ob = ldg4(out + 4 * q2);
+        if (sel) sb = ldg4(sel + 4 * q2);
+        load_label4<LT>(label, q2, lb);
+      }
+      pixel(oa.x, sa.x, la[0]);
+      pixel(oa.y, sa.y, la[1]);
+      pixel(oa.z, sa.z, la[2]);
+      pixel(oa.w, sa.w, la[3]);
+      if (two) {
+        pixel(ob.x, sb.x, lb[0]);
+        pixel(ob.y, sb.y, lb[1]);
+        pixel(ob.z, sb.z, lb[2]);
+        pixel(ob.w, sb.w, lb[3]);
+      }
+    }
+    p0 = (nq << 2) + tid;                         // tail (at most 3 pixels)
   }
+  for (long long p = p0; p < P; p += stride)
+    pixel(__ldg(out + p), sel ? __ldg(sel + p) : 0.f, load_label<LT>(label, p));
+  const unsigned int c[6] = {c00, c01, c10, c11, csel, ctot};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -476,17 +626,41 @@ adam_kernel(const sunet_adam_tensor* __restrict__ table, float lr, float b1, flo
   const float bc1 = 1.f - powf(b1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
   const float step_size = lr / bc1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < t.numel;
-       i += (long long)gridDim.x * blockDim.x) {
-    float g = t.grad[i];
-    float p = t.param[i];
+  auto upd = [&](float g, float& p, float& m, float& v) {
     if (wd != 0.f) g = fmaf(wd, p, g);
-    const float m = b1 * t.exp_avg[i] + (1.f - b1) * g;
-    const float v = b2 * t.exp_avg_sq[i] + (1.f - b2) * g * g;
+    m = b1 * m + (1.f - b1) * g;
+    v = b2 * v + (1.f - b2) * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p = p - step_size * (m / denom);
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long i0 = tid;
+  const bool vec = ((reinterpret_cast<uintptr_t>(t.param) | reinterpret_cast<uintptr_t>(t.grad) |
+                     reinterpret_cast<uintptr_t>(t.exp_avg) | reinterpret_cast<uintptr_t>(t.exp_avg_sq)) & 15) == 0;
+  if (vec) {
+    const long long nq = t.numel >> 2;
+    for (long long q = tid; q < nq; q += stride) {
+      const float4 g = *reinterpret_cast<const float4*>(t.grad + 4 * q);
+      float4 p = *reinterpret_cast<float4*>(t.param + 4 * q);
+      float4 m = *reinterpret_cast<float4*>(t.exp_avg + 4 * q);
+      float4 v = *reinterpret_cast<float4*>(t.exp_avg_sq + 4 * q);
+      upd(g.x, p.x, m.x, v.x);
+      upd(g.y, p.y, m.y, v.y);
+      upd(g.z, p.z, m.z, v.z);
+      upd(g.w, p.w, m.w, v.w);
+      *reinterpret_cast<float4*>(t.param + 4 * q) = p;
+      *reinterpret_cast<float4*>(t.exp_avg + 4 * q) = m;
+      *reinterpret_cast<float4*>(t.exp_avg_sq + 4 * q) = v;
+    }
+    i0 = (nq << 2) + tid;
+  }
+  for (long long i = i0; i < t.numel; i += stride) {
+    float p = t.param[i], m = t.exp_avg[i], v = t.exp_avg_sq[i];
+    upd(t.grad[i], p, m, v);
+    t.param[i] = p;
     t.exp_avg[i] = m;
     t.exp_avg_sq[i] = v;
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    t.param[i] = p - step_size * (m / denom);
   }
 }
 
@@ -550,7 +724,7 @@ extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_st
   int e = check_launch("heads_bwd");
   if (e) return e;
   HeadG hg = {{dw0, dw1, dw2}, {db0, db1, db2}};
-  launch_k(heads_bwd_reduce_kernel, dim3(1), dim3(256), 0, STREAM, partials, blocks, nheads, hg);
+  launch_k(heads_bwd_reduce_kernel, dim3(3 * 65), dim3(128), 0, STREAM, partials, blocks, nheads, hg);
   return check_launch("heads_bwd_reduce");
 }
 
@@ -586,44 +760,54 @@ extern "C" int sunet_heads_bwd_bn(const float* dlogits, const void* y, int y_pix
   int e = check_launch("heads_bwd_bn");
   if (e) return e;
   HeadG hg = {{dw0, dw1, dw2}, {db0, db1, db2}};
-  launch_k(heads_bwd_reduce_kernel, dim3(1), dim3(256), 0, STREAM, partials, blocks, nheads, hg);
+  launch_k(heads_bwd_reduce_kernel, dim3(3 * 65), dim3(128), 0, STREAM, partials, blocks, nheads, hg);
   return check_launch("heads_bwd_reduce");
 }
 
 extern "C" int sunet_loss_sums(const float* out, const float* sel, const float* aux, const float* target,
-                               long long pixels, double* sums, void* workspace, size_t workspace_bytes,
-                               sunet_stream_t stream_) {
+                               long long pixels, double* sums, double* pixels_out, void* workspace,
+                               size_t workspace_bytes, sunet_stream_t stream_) {
   if (!target || !sums || !workspace || pixels <= 0) return set_error(SUNET_ERR_INVALID, "loss_sums: bad arguments");
   if (out && !sel) return set_error(SUNET_ERR_INVALID, "loss_sums: out given without sel");
-  const int blocks = grid_for(pixels, 256, 8);
+  const bool vec = aligned16(out, sel, aux, target);
+  const int blocks = grid_for(vec ? (pixels + 3) / 4 : pixels, 256, 8);
   if (workspace_bytes < (size_t)blocks * 3 * sizeof(double))
     return set_error(SUNET_ERR_WORKSPACE, "loss_sums: workspace too small");
   double* partials = reinterpret_cast<double*>(workspace);
-  launch_k(loss_sums_kernel, dim3(blocks), dim3(256), 0, STREAM, out, sel, aux, target, pixels, partials);
+  if (vec) launch_k(loss_sums_kernel<4>, dim3(blocks), dim3(256), 0, STREAM, out, sel, aux, target, pixels, partials);
+  else launch_k(loss_sums_kernel<1>, dim3(blocks), dim3(256), 0, STREAM, out, sel, aux, target, pixels, partials);
   int e = check_launch("loss_sums");
   if (e) return e;
-  launch_k(loss_sums_final_kernel, dim3(1), dim3(32), 0, STREAM, partials, blocks, sums);
+  launch_k(loss_sums_final_kernel, dim3(1), dim3(256), 0, STREAM, (const double*)partials, blocks, sums, pixels_out,
+           (double)pixels);
   return check_launch("loss_sums_final");
 }
 
-extern "C" int sunet_loss_finalize(const double* sums, long long global_pixels, float lamb, float target_coverage,
-                                   float* results, sunet_stream_t stream_) {
-  if (!sums || !results || global_pixels <= 0) return set_error(SUNET_ERR_INVALID, "loss_finalize: bad arguments");
-  launch_k(loss_finalize_kernel, dim3(1), dim3(32), 0, STREAM, sums, (double)global_pixels, lamb, target_coverage, results);
+extern "C" int sunet_loss_finalize(const double* sums, long long global_pixels, const double* global_pixels_dev,
+                                   float lamb, float target_coverage, float* results, sunet_stream_t stream_) {
+  if (!sums || !results || (global_pixels <= 0 && !global_pixels_dev))
+    return set_error(SUNET_ERR_INVALID, "loss_finalize: bad arguments");
+  launch_k(loss_finalize_kernel, dim3(1), dim3(32), 0, STREAM, sums, (double)global_pixels, global_pixels_dev, lamb,
+           target_coverage, results);
   return check_launch("loss_finalize");
 }
 
 extern "C" int sunet_loss_bwd(const float* out, const float* sel, const float* aux, const float* target,
-                              long long pixels, const double* sums, long long global_pixels, float lamb,
-                              float target_coverage, const float* g_sel, const float* g_aux, float* d_out,
-                              float* d_sel, float* d_aux, sunet_stream_t stream_) {
-  if (!target || !sums || pixels <= 0 || global_pixels <= 0)
+                              long long pixels, const double* sums, long long global_pixels,
+                              const double* global_pixels_dev, float lamb, float target_coverage, const float* g_sel,
+                              const float* g_aux, float* d_out, float* d_sel, float* d_aux, sunet_stream_t stream_) {
+  if (!target || !sums || pixels <= 0 || (global_pixels <= 0 && !global_pixels_dev))
     return set_error(SUNET_ERR_INVALID, "loss_bwd: bad arguments");
   if ((d_out || d_sel) && (!out || !sel)) return set_error(SUNET_ERR_INVALID, "loss_bwd: d_out/d_sel need out and sel");
   if (d_aux && !aux) return set_error(SUNET_ERR_INVALID, "loss_bwd: d_aux needs aux");
-  launch_k(loss_bwd_kernel, dim3(grid_for(pixels, 256, 8)), dim3(256), 0, STREAM, out, sel, aux, target, pixels, sums,
-                                                                 (double)global_pixels, lamb, target_coverage, g_sel,
-                                                                 g_aux, d_out, d_sel, d_aux);
+  const bool vec = aligned16(out, sel, aux, target) && aligned16(d_out, d_sel, d_aux, nullptr);
+  const int blocks = grid_for(vec ? (pixels + 3) / 4 : pixels, 256, 8);
+  if (vec)
+    launch_k(loss_bwd_kernel<4>, dim3(blocks), dim3(256), 0, STREAM, out, sel, aux, target, pixels, sums,
+             (double)global_pixels, global_pixels_dev, lamb, target_coverage, g_sel, g_aux, d_out, d_sel, d_aux);
+  else
+    launch_k(loss_bwd_kernel<1>, dim3(blocks), dim3(256), 0, STREAM, out, sel, aux, target, pixels, sums,
+             (double)global_pixels, global_pixels_dev, lamb, target_coverage, g_sel, g_aux, d_out, d_sel, d_aux);
   return check_launch("loss_bwd");
 }
 
@@ -632,20 +816,25 @@ extern "C" int sunet_metric_hist(const float* out, const float* sel, const void*
                                  unsigned long long* counts, sunet_stream_t stream_) {
   if (!out || !label || !counts || pixels <= 0) return set_error(SUNET_ERR_INVALID, "metric_hist: bad arguments");
   if (masked && !sel) return set_error(SUNET_ERR_INVALID, "metric_hist: masked counting needs a selection map");
-  const int blocks = grid_for(pixels, 256, 8);
+  const bool vec = aligned16(out, sel, nullptr, nullptr) && (reinterpret_cast<uintptr_t>(label) & 15) == 0;
+  const int blocks = grid_for(vec ? (pixels + 7) / 8 : pixels, 256, 8);
+#define SUNET_HIST(LT)                                                                                             \
+  do {                                                                                                             \
+    if (vec)                                                                                                       \
+      launch_k(metric_hist_kernel<LT, 4>, dim3(blocks), dim3(256), 0, STREAM, out, sel, label, pixels, thr_out,    \
+               thr_sel, masked, counts);                                                                           \
+    else                                                                                                           \
+      launch_k(metric_hist_kernel<LT, 1>, dim3(blocks), dim3(256), 0, STREAM, out, sel, label, pixels, thr_out,    \
+               thr_sel, masked, counts);                                                                           \
+  } while (0)
   switch (label_dtype) {
-    case 0:
-      launch_k(metric_hist_kernel<0>, dim3(blocks), dim3(256), 0, STREAM, out, sel, label, pixels, thr_out, thr_sel, masked, counts);
-      break;
-    case 1:
-      launch_k(metric_hist_kernel<1>, dim3(blocks), dim3(256), 0, STREAM, out, sel, label, pixels, thr_out, thr_sel, masked, counts);
-      break;
-    case 2:
-      launch_k(metric_hist_kernel<2>, dim3(blocks), dim3(256), 0, STREAM, out, sel, label, pixels, thr_out, thr_sel, masked, counts);
-      break;
+    case 0: SUNET_HIST(0); break;
+    case 1: SUNET_HIST(1); break;
+    case 2: SUNET_HIST(2); break;
     default:
       return set_error(SUNET_ERR_INVALID, "metric_hist: bad label dtype %d", label_dtype);
   }
+#undef SUNET_HIST
   return check_launch("metric_hist");
 }
 
@@ -654,8 +843,8 @@ extern "C" int sunet_adam_step(const sunet_adam_tensor* table, int n_tensors, lo
                                const int* step_dev, sunet_stream_t stream_) {
   if (!table || n_tensors <= 0 || max_numel <= 0 || (step <= 0 && !step_dev))
     return set_error(SUNET_ERR_INVALID, "adam_step: bad arguments");
-  long long bx = (max_numel + 256 * 8 - 1) / (256 * 8);
-  if (bx > 64) bx = 64;
+  long long bx = (max_numel + 256 * 16 - 1) / (256 * 16);      // float4 per thread, ~4 trips
+  if (bx > 148) bx = 148;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)n_tensors);
   launch_k(adam_kernel, dim3(grid), dim3(256), 0, STREAM, table, lr, beta1, beta2, eps, weight_decay, step, lr_dev, step_dev);

@@ -280,7 +280,8 @@ class SUNetPlan:
         """fp32 reference-layout parameters -> bf16 kernel operands (every forward; 7.7 M values), one launch."""
         key = tuple(params[f"{ly.name}.0.weight"].data_ptr() for ly in self.order) + tuple(
             params[f"unpool{L}.weight"].data_ptr() for L in (1, 2, 3))
-        if getattr(self, "_pack_key", None) != key:
+        cache = self.__dict__.setdefault("_pack_cache", {})      # one job table per parameter set (ensembles share a plan)
+        if key not in cache:
             jobs = (_lib.PackJob * (len(self.order) + 3))()
             for i, ly in enumerate(self.order):
                 w = params[f"{ly.name}.0.weight"]
@@ -296,9 +297,11 @@ class SUNetPlan:
                 j.kind, j.a, j.b = 2, w.shape[0], w.shape[1]
                 j.w, j.bias, j.wf, j.wd, j.bias4 = (w.data_ptr(), b.data_ptr(), u["wf"].data_ptr(), u["wd"].data_ptr(),
                                                    u["b4"].data_ptr())
-            self._pack_jobs = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device)
-            self._pack_n = len(self.order) + 3
-            self._pack_key = key
+            if len(cache) >= 32:
+                cache.pop(next(iter(cache)))
+            cache[key] = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device)
+        self._pack_jobs = cache[key]
+        self._pack_n = len(self.order) + 3
         K.pack_weights_table(self._pack_jobs, self._pack_n)
 
     # ------------------------------------------------------------------ forward

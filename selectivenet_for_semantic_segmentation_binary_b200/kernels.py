@@ -368,23 +368,27 @@ def heads_bwd_bn(dlogits, y, scale, shift, mean, invstd, weights, dA, dws, dbs, 
                                               workspace.numel(), _stream()), "sunet_heads_bwd_bn")
 
 
-def loss_sums(out, sel, aux, target, sums, workspace) -> None:
+def loss_sums(out, sel, aux, target, sums, workspace, pixels_out=None) -> None:
+    """sums: fp64 [>=3] device tensor; pixels_out: optional fp64 [1] device tensor that receives float(pixels)."""
     P = target.numel()
     _lib.check(_lib.load().sunet_loss_sums(_f32(out), _f32(sel), _f32(aux), _f32(target), P, sums.data_ptr(),
-                                           workspace.data_ptr(), workspace.numel(), _stream()), "sunet_loss_sums")
+                                           _ptr(pixels_out), workspace.data_ptr(), workspace.numel(), _stream()),
+               "sunet_loss_sums")
 
 
-def loss_finalize(sums, global_pixels, lamb, target_coverage, results) -> None:
-    _lib.check(_lib.load().sunet_loss_finalize(sums.data_ptr(), global_pixels, float(lamb), float(target_coverage),
-                                               _f32(results), _stream()), "sunet_loss_finalize")
+def loss_finalize(sums, global_pixels, lamb, target_coverage, results, pixels_dev=None) -> None:
+    """pixels_dev: fp64 [1] device tensor holding the global pixel count (overrides global_pixels)."""
+    _lib.check(_lib.load().sunet_loss_finalize(sums.data_ptr(), int(global_pixels), _ptr(pixels_dev), float(lamb),
+                                               float(target_coverage), _f32(results), _stream()),
+               "sunet_loss_finalize")
 
 
 def loss_bwd(out, sel, aux, target, sums, global_pixels, lamb, target_coverage, g_sel, g_aux, d_out, d_sel,
-             d_aux) -> None:
+             d_aux, pixels_dev=None) -> None:
     P = target.numel()
     _lib.check(_lib.load().sunet_loss_bwd(_f32(out), _f32(sel), _f32(aux), _f32(target), P, sums.data_ptr(),
-                                          global_pixels, float(lamb), float(target_coverage), _f32(g_sel),
-                                          _f32(g_aux), _f32(d_out), _f32(d_sel), _f32(d_aux), _stream()),
+                                          int(global_pixels), _ptr(pixels_dev), float(lamb), float(target_coverage),
+                                          _f32(g_sel), _f32(g_aux), _f32(d_out), _f32(d_sel), _f32(d_aux), _stream()),
                "sunet_loss_bwd")
 
 
@@ -399,6 +403,30 @@ def metric_hist(out, sel, label, thr_out, thr_sel, masked, counts) -> None:
     _lib.check(_lib.load().sunet_metric_hist(_f32(out), _f32(sel), label.data_ptr(), _LABEL_DTYPES[label.dtype], P,
                                              float(thr_out), float(thr_sel), int(bool(masked)), counts.data_ptr(),
                                              _stream()), "sunet_metric_hist")
+
+
+def minmax_f32(x: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor) -> None:
+    """out[0], out[1] = min, max of a contiguous fp32 tensor (the batch-wide extrema eval.py's fn_scale_minmax uses)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda and out.dtype == torch.float32 and out.numel() >= 2
+    _lib.check(_lib.load().sunet_minmax_f32(x.data_ptr(), x.numel(), out.data_ptr(), workspace.data_ptr(),
+                                            workspace.numel(), _stream()), "sunet_minmax_f32")
+
+
+def ensemble_mean(maps, scale: str, mean: torch.Tensor, minmax=None) -> None:
+    """mean = np.mean([scale(m) for m in maps], axis=0) with numpy's float32 order of operations (eval.py:209-222).
+    maps: list of contiguous fp32 CUDA tensors of equal numel; minmax: list of device (min, max) pairs (scale='minmax')."""
+    n = len(maps)
+    P = maps[0].numel()
+    for m in maps:
+        assert m.dtype == torch.float32 and m.is_contiguous() and m.is_cuda and m.numel() == P
+    assert mean.dtype == torch.float32 and mean.is_contiguous() and mean.numel() == P
+    arr = (C.c_void_p * n)(*[m.data_ptr() for m in maps])
+    mm = None
+    if minmax is not None:
+        assert len(minmax) == n
+        mm = (C.c_void_p * n)(*[t.data_ptr() for t in minmax])
+    _lib.check(_lib.load().sunet_ensemble_mean(arr, mm, n, P, _lib.SCALE_MODES[scale], mean.data_ptr(), _stream()),
+               "sunet_ensemble_mean")
 
 
 def adam_step(table_dev, n_tensors, max_numel, lr, beta1, beta2, eps, weight_decay, step, lr_dev=None,

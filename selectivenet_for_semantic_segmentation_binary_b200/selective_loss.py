@@ -49,14 +49,13 @@ def _require_cuda(*ts):
 
 
 def _global_sums(sums: torch.Tensor, local_pixels: int) -> int:
-    """All-reduce [S, R, A] and the pixel count when data parallel; returns the global pixel count."""
+    """All-reduce [S, R, A, pixels] (one fp64 buffer) when data parallel; returns the global pixel count.
+    `sums` is the fp64 [4] buffer sunet_loss_sums filled (sums[3] = this shard's pixel count)."""
     if not _DP_ENABLED:
         return local_pixels
-    import torch.distributed as dist
-    buf = torch.cat([sums, torch.tensor([float(local_pixels)], dtype=torch.float64, device=sums.device)])
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=_DP_GROUP)
-    sums.copy_(buf[:3])
-    return int(round(buf[3].item()))
+    from .trainer import exchange_loss_sums
+    exchange_loss_sums(sums, _DP_GROUP)
+    return int(round(sums[3].item()))
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -69,8 +68,8 @@ class _SelectiveRisk(torch.autograd.Function):
         _require_cuda(output, selection, target)
         out, sel, tgt = _f32c(output), _f32c(selection), _f32c(target)
         dev = out.device
-        sums = torch.zeros(3, dtype=torch.float64, device=dev)
-        K.loss_sums(out, sel, None, tgt, sums, _workspace(dev))
+        sums = torch.zeros(4, dtype=torch.float64, device=dev)
+        K.loss_sums(out, sel, None, tgt, sums, _workspace(dev), pixels_out=sums[3:4])
         P = _global_sums(sums, tgt.numel())
         res = torch.empty(4, device=dev)
         K.loss_finalize(sums, P, lamb, target_coverage, res)
@@ -114,8 +113,8 @@ class _BCEMean(torch.autograd.Function):
         _require_cuda(logits, target)
         x, tgt = _f32c(logits), _f32c(target)
         dev = x.device
-        sums = torch.zeros(3, dtype=torch.float64, device=dev)
-        K.loss_sums(None, None, x, tgt, sums, _workspace(dev))
+        sums = torch.zeros(4, dtype=torch.float64, device=dev)
+        K.loss_sums(None, None, x, tgt, sums, _workspace(dev), pixels_out=sums[3:4])
         P = _global_sums(sums, tgt.numel())
         res = torch.empty(4, device=dev)
         K.loss_finalize(sums, P, 0.0, 0.0, res)

@@ -1,12 +1,14 @@
-"""Thin reader for the reference's on-disk patch layout, so train.py works on real data too.
+"""Reader for the reference's on-disk patch layout and its train/valid/test lists, so train.py / eval.py work on
+real data too.
 
-The reference's input pipeline (/root/reference/utils/data_utils.py:94-236: PatchDataset + Normalization
-+ RandomFlip + ToTensor behind a 16-worker DataLoader) is OUT OF SCOPE of the hot path (SURVEY.md §8(f)
-"next"); the benchmark and the tests use synthetic tensors.  This module only keeps the CLI usable:
-it reads ``{data_dir}/{mag}x_{size}/{id}_input.jpg`` / ``{id}_label.png`` for the ids listed in
-``{data_dir}/{k}-fold_{tumorable,non_tumorable}_data.npy`` (all folds except ``fold`` = training set,
-data_utils.py:56-74), applies ``/255`` and ``Normalization(0.5, 0.5)`` and a random horizontal/vertical
-flip, and yields float32 NCHW batches.  RGB input only (the stain transforms need skimage/cv2).
+Mirrors the data-format side of /root/reference/utils/data_utils.py: ``split_train_valid`` / ``construct_train_valid``
+/ ``construct_test`` (:46-90 — every row of ``{data_dir}/{k}-fold_{tumorable,non_tumorable}_data.npy`` is a pair
+``(input_file, label_file)``; the training folds are split 80/20 into train/valid with ``np.random.seed(42)``) and
+``PatchDataset`` (:170-236 — ``{data_dir}/{mag}x_{size}/{input_file}`` read with PIL, ``/255`` -> float32, label
+``convert('L')/255`` -> uint8).  JPEG decode and the 16-worker DataLoader are OUT OF SCOPE of the hot path (SURVEY.md
+§8(f) "next"); the benchmark and the tests use synthetic tensors, and the fast path for decoded patches is
+``SUNetTrainer.step_u8`` (normalisation, flips, layout and im2col in one kernel).  RGB input only (the stain
+transforms ``RGB2GH`` / ``H_RGB`` need skimage and cv2, which this image does not have).
 """
 import os
 
@@ -14,43 +16,86 @@ import numpy as np
 import torch
 
 
-class PatchArrays:
-    def __init__(self, data_dir, fold, patch_mag, patch_size, input_type='RGB', seed=42):
-        if 'RGB' not in input_type or input_type != 'RGB':
-            raise SystemExit("only --input_type RGB is read from disk (GH / H_RGB need skimage; SURVEY.md §2)")
-        self.dir = os.path.join(data_dir, f'{patch_mag}x_{patch_size}')
-        ids = []
-        for k in range(1, 6):
-            if k == fold:
-                continue
-            for kind in ('tumorable', 'non_tumorable'):
-                p = os.path.join(data_dir, f'{k}-fold_{kind}_data.npy')
-                if os.path.exists(p):
-                    ids += [str(i) for i in np.load(p, allow_pickle=True).tolist()]
-        if not ids:
-            raise SystemExit(f'no fold lists under {data_dir}: pass --synthetic N to train on synthetic patches')
-        self.ids = ids
-        self.rng = np.random.default_rng(seed)
+def split_train_valid(TRAIN_list, valid_ratio=0.2, rng=None):
+    """data_utils.py:49-53; `rng` is the stream np.random.seed(42) started at import time in the reference."""
+    rng = np.random if rng is None else rng
+    total_n = len(TRAIN_list)
+    valid_idx = rng.choice(total_n, size=int(total_n * valid_ratio), replace=False)
+    train_idx = np.setdiff1d([i for i in range(total_n)], valid_idx)
+    return TRAIN_list[train_idx], TRAIN_list[valid_idx]
 
-    def _load(self, pid):
+
+def construct_train_valid(data_dir, test_fold=5):
+    """data_utils.py:55-76: all folds except `test_fold`, tumorable and non-tumorable lists split 80/20 separately
+    (tumorable first — the order fixes the random stream), then stacked."""
+    folds = [1, 2, 3, 4, 5]
+    folds.remove(test_fold)
+    tumorable, non_tumorable = [], []
+    for i in folds:
+        tumorable.append(np.load(f'{data_dir}/{i}-fold_tumorable_data.npy', allow_pickle=True))
+        non_tumorable.append(np.load(f'{data_dir}/{i}-fold_non_tumorable_data.npy', allow_pickle=True))
+    tumorable = np.concatenate(tumorable)
+    non_tumorable = np.concatenate(non_tumorable)
+    rng = np.random.RandomState(42)          # == the global stream right after the reference's np.random.seed(42)
+    t_train, t_valid = split_train_valid(tumorable, 0.2, rng)
+    n_train, n_valid = split_train_valid(non_tumorable, 0.2, rng)
+    return np.vstack([t_train, n_train]), np.vstack([t_valid, n_valid])
+
+
+def construct_test(data_dir, test_fold=1):
+    """data_utils.py:78-90."""
+    tumorable = np.array(np.load(f'{data_dir}/{test_fold}-fold_tumorable_data.npy', allow_pickle=True))
+    non_tumorable = np.array(np.load(f'{data_dir}/{test_fold}-fold_non_tumorable_data.npy', allow_pickle=True))
+    return np.vstack([tumorable, non_tumorable])
+
+
+class PatchArrays:
+    """PatchDataset + the reference's transforms + DataLoader(drop_last=False) as a plain batch iterator.
+
+    data_list rows are ``(input_file, label_file)`` (data_utils.py:173-199).  ``train=True``: shuffled every epoch,
+    Normalization(0.5, 0.5) + RandomFlip + ToTensor (train.py:367); ``train=False``: in order, no flips (:368)."""
+
+    def __init__(self, data_dir, data_list, patch_mag=200, patch_size=256, input_type='RGB', train=True, seed=0):
+        if input_type != 'RGB':
+            raise SystemExit("only --input_type RGB is read from disk (GH / H_RGB need skimage + cv2; SURVEY.md §2)")
+        self.dir = os.path.join(data_dir, f'{patch_mag}x_{patch_size}')
+        self.inputs, self.labels = [], []
+        for f in data_list:
+            assert str(f[0]).split('_input')[0] == str(f[1]).split('_label')[0], \
+                f'check the pairness btw input {f[0]} and label {f[1]}'
+            self.inputs.append(str(f[0]))
+            self.labels.append(str(f[1]))
+        self.train = train
+        self.rng = np.random.RandomState(seed)
+
+    def __len__(self):
+        return len(self.inputs)
+
+    def ids(self):
+        return [f.split('_input')[0] for f in self.inputs]
+
+    def _load(self, i):
         from PIL import Image
-        x = np.asarray(Image.open(os.path.join(self.dir, f'{pid}_input.jpg')).convert('RGB'), dtype=np.float32) / 255.0
-        y = np.asarray(Image.open(os.path.join(self.dir, f'{pid}_label.png')), dtype=np.float32)
-        if y.ndim == 3:
-            y = y[..., 0]
-        y = (y / 255.0 if y.max() > 1 else y).astype(np.uint8).astype(np.float32)
-        x = (x - 0.5) / 0.5                                   # Normalization(mean=0.5, std=0.5)
-        if self.rng.random() > 0.5:                           # RandomFlip
-            x, y = x[:, ::-1], y[:, ::-1]
-        if self.rng.random() > 0.5:
-            x, y = x[::-1], y[::-1]
-        return np.ascontiguousarray(x.transpose(2, 0, 1)), np.ascontiguousarray(y)
+        x = np.array(Image.open(os.path.join(self.dir, self.inputs[i])))
+        y = np.array(Image.open(os.path.join(self.dir, self.labels[i])).convert("L"))
+        x, y = (x / 255.0).astype(np.float32), (y / 255.0).astype(np.uint8)        # data_utils.py:216-217
+        x = (x - 0.5) / 0.5                                                        # Normalization(mean=0.5, std=0.5)
+        if self.train:                                                             # RandomFlip: two draws per sample
+            if self.rng.rand() > 0.5:
+                y, x = np.fliplr(y), np.fliplr(x)
+            if self.rng.rand() > 0.5:
+                y, x = np.flipud(y), np.flipud(x)
+        return np.ascontiguousarray(x.transpose(2, 0, 1).astype(np.float32)), np.ascontiguousarray(y)
+
+    def n_batches(self, batch_size):
+        return -(-len(self) // batch_size)
 
     def batches(self, batch_size):
-        order = self.rng.permutation(len(self.ids))
-        for i in range(0, len(order) - batch_size + 1, batch_size):
-            xs, ys = zip(*(self._load(self.ids[j]) for j in order[i:i + batch_size]))
-            yield torch.from_numpy(np.stack(xs)), torch.from_numpy(np.stack(ys))
+        """float32 NCHW inputs and float32 {0,1} labels; the last batch may be short (drop_last=False)."""
+        order = self.rng.permutation(len(self)) if self.train else np.arange(len(self))
+        for i in range(0, len(order), batch_size):
+            xs, ys = zip(*(self._load(j) for j in order[i:i + batch_size]))
+            yield torch.from_numpy(np.stack(xs)), torch.from_numpy(np.stack(ys).astype(np.float32))
 
 
 # ------------------------------------------------------------------ the reference's transform objects

@@ -24,7 +24,7 @@ def test_header_symbols_exported(built_lib):
 def test_binding_table_matches_header(built_lib):
     from selectivenet_for_semantic_segmentation_binary_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared()
-    assert built_lib.sunet_abi_version() == 1
+    assert built_lib.sunet_abi_version() == 2
     assert built_lib.sunet_launch_count() == 0
 
 
