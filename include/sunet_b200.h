@@ -306,6 +306,48 @@ int sunet_ensemble_mean(const float* const* maps, const float* const* minmax, in
                         int scale, float* mean, sunet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32 CHECK MODE (north_star: logits / loss within 1e-4 "in an fp32 check mode"): slow SIMT fp32 twins of every op
+ * of the path, selected with SUNET_CHECK_FP32=1.  Activations NHWC fp32; parameters in the reference's own layouts
+ * (Conv2d [co][ci][3][3], ConvTranspose2d [ci][co][2][2]); fp64 accumulation for every reduction over pixels.
+ * Same reference citations as the fast entry points above (model.py:9-15,31,44-45,83,96-101; train.py:208).
+ * ---------------------------------------------------------------------------------------- */
+/* y[b,h,w,co] = bias[co] + sum_{r,s,ci} [x0 | x1][b,h+r-1,w+s-1,ci] * w[co][ci][r][s]  (x1 / bias may be NULL) */
+int sunet_f32_conv3x3_fwd(const float* x0, int c0, const float* x1, int c1, const float* w, const float* bias, float* y,
+                          int batch, int height, int width, int cout, sunet_stream_t stream);
+/* input gradient; channels [0,c0) go to dx0, [c0,c0+c1) to dx1 (the [d_up | d_skip] halves of a decoder block) */
+int sunet_f32_conv3x3_dgrad(const float* dy, const float* w, float* dx0, int c0, float* dx1, int c1, int batch,
+                            int height, int width, int cout, sunet_stream_t stream);
+int sunet_f32_conv3x3_wgrad(const float* dy, const float* x0, int c0, const float* x1, int c1, float* dw, int batch,
+                            int height, int width, int cout, sunet_stream_t stream);
+/* ConvTranspose2d(k2,s2): x [b][h][w][cin] -> y [b][2h][2w][cout]; (height, width) are the INPUT grid */
+int sunet_f32_convT_fwd(const float* x, const float* w, const float* bias, float* y, int batch, int height, int width,
+                        int cin, int cout, sunet_stream_t stream);
+int sunet_f32_convT_dgrad(const float* dy, const float* w, float* dx, int batch, int height, int width, int cin,
+                          int cout, sunet_stream_t stream);
+int sunet_f32_convT_wgrad(const float* dy, const float* x, float* dw, float* dbias, int batch, int height, int width,
+                          int cin, int cout, sunet_stream_t stream);
+/* BatchNorm2d(train) statistics of the bias-free conv output y [pixels][channels] + running-stat update -> the
+ * per-channel scale / shift / mean / invstd (same outputs as sunet_bn_finalize) */
+int sunet_f32_bn_stats(const float* y, long long pixels, int channels, const float* gamma, const float* beta,
+                       const float* conv_bias, float* running_mean, float* running_var, long long* num_batches_tracked,
+                       float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
+                       sunet_stream_t stream);
+/* a = relu(y*scale + shift); pooled (optional) = MaxPool2d(2)(a) */
+int sunet_f32_bn_relu_pool(const float* y, const float* scale, const float* shift, float* a, float* pooled, int batch,
+                           int height, int width, int channels, sunet_stream_t stream);
+/* backward of BN(train) + ReLU (+ skip / MaxPool fan-in): g = (dA + dPool routed to the first maximum) * (a > 0),
+ * dgamma, dbeta, dy = scale*(g - sum g/n - xhat*sum(g*xhat)/n).  dA or dPool may be NULL.  workspace >= 16*channels B */
+int sunet_f32_bn_relu_pool_bwd(const float* dA, const float* dPool, const float* y, const float* a, const float* scale,
+                               const float* mean, const float* invstd, float* dgamma, float* dbeta, float* dy, int batch,
+                               int height, int width, int channels, void* workspace, size_t workspace_bytes,
+                               sunet_stream_t stream);
+/* heads: w [nheads][channels], b [nheads], logits [nheads][pixels]; backward adds into dA when accumulate != 0 */
+int sunet_f32_heads_fwd(const float* a, const float* w, const float* b, int nheads, float* logits, long long pixels,
+                        int channels, sunet_stream_t stream);
+int sunet_f32_heads_bwd(const float* dlogits, const float* a, const float* w, int nheads, float* dA, int accumulate,
+                        float* dw, float* db, long long pixels, int channels, sunet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimizer: Adam over a table of tensors in one launch (train.py:88-92,209)
  * ---------------------------------------------------------------------------------------- */
 typedef struct sunet_adam_tensor {

@@ -110,6 +110,17 @@ SIGNATURES = {
     "sunet_metric_hist": [_vp, _vp, _vp, _i, _ll, _f, _f, _i, _vp, _vp],
     "sunet_minmax_f32": [_vp, _ll, _vp, _vp, _sz, _vp],
     "sunet_ensemble_mean": [_vp, _vp, _i, _ll, _i, _vp, _vp],
+    "sunet_f32_conv3x3_fwd": [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "sunet_f32_conv3x3_dgrad": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "sunet_f32_conv3x3_wgrad": [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "sunet_f32_convT_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "sunet_f32_convT_dgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "sunet_f32_convT_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "sunet_f32_bn_stats": [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
+    "sunet_f32_bn_relu_pool": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "sunet_f32_bn_relu_pool_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp],
+    "sunet_f32_heads_fwd": [_vp, _vp, _vp, _i, _vp, _ll, _i, _vp],
+    "sunet_f32_heads_bwd": [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _ll, _i, _vp],
     "sunet_adam_step": [_vp, _i, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp],
 }
 _RESTYPES = {"sunet_last_error": C.c_char_p, "sunet_launch_count": C.c_longlong}

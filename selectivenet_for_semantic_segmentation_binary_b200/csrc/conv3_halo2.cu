@@ -39,17 +39,24 @@ struct Halo2Params {
 // TILES = M=128 tiles per CTA and block: 2 (16x16 block) for BN <= 128, 1 (8 wide x 16 tall) for BN = 256
 // BNB = fused BN-backward reduction in the epilogue: two extra 16 KB slots hold the matching tiles of y (the
 // conv output the BN normalised), paid for with one or two weight stages.
-template <int BN, bool BNB = false>
+// AST = halo (A) stages.  With 2 stages the TMA load of the next halo tile has exactly one chunk of MMAs (72 x N/2
+// tensor cycles: 2 304 cycles = 1.3 us for N = 64) to arrive, and the level-1 layers have ONE 64-channel chunk per
+// block.  A third stage (SUNET_HALO2_AST=3, paid for with weight stages and y slots) was measured on B200 and changes
+// nothing: 0.550 vs 0.548 ms for 128 x 256^2 x 64->64, 33.06 vs 33.18 ms per step (profiles/r02/halo_stages_ab.log) —
+// the N = 64 kernel is bound by the shared-memory port (operand reads 65 % + epilogue 27 % of its wavefronts), not
+// by the latency of the halo load.  Two stages stay the default.
+template <int BN, bool BNB = false, int AST = 2>
 struct H2Cfg {
   static constexpr int TILES = (BN == 256) ? 1 : 2;
   static constexpr int PITCH = 8 * TILES + 2;
   static constexpr int A_TX = 18 * PITCH * 128;
   static constexpr int A_SLOT = (A_TX + 1023) / 1024 * 1024;
-  static constexpr int A_STAGES = 2;
+  static constexpr int A_STAGES = AST;
   static constexpr int B_HALF = (BN / 2) * 128;      // this CTA's half of one weight tile
-  static constexpr int B_STAGES = (BN == 256) ? (BNB ? 7 : 8) : ((BNB && BN == 128) ? 9 : 10);
+  static constexpr int B_STAGES = (AST == 3) ? ((BN == 64) ? (BNB ? 8 : 10) : 8)
+                                             : ((BN == 256) ? (BNB ? 7 : 8) : ((BNB && BN == 128) ? 9 : 10));
   static constexpr int STG_BYTES = 128 * 128;
-  static constexpr int Y_SLOTS = BNB ? ((BN == 64) ? 4 : 2) : 0;      // power of two
+  static constexpr int Y_SLOTS = BNB ? ((BN == 64 && AST == 2) ? 4 : 2) : 0;      // power of two
   static constexpr int EP_BYTES = BNB ? 0 : 2 * BN * 4;   // inference epilogue: this CTA's scale / shift columns
   static constexpr int SMEM =
       A_STAGES * A_SLOT + B_STAGES * B_HALF + (2 + Y_SLOTS) * STG_BYTES + 1024 + 512 + EP_BYTES;
@@ -59,14 +66,14 @@ struct H2Cfg {
 
 constexpr int kH2Threads = 192;
 
-template <int BN, bool BNB>
+template <int BN, bool BNB, int AST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
 conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
                    const __grid_constant__ CUtensorMap mapY, const Halo2Params p) {
   pdl_wait();
   pdl_trigger();
-  using C = H2Cfg<BN, BNB>;
+  using C = H2Cfg<BN, BNB, AST>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -461,19 +468,30 @@ static int halo2_map(CUtensorMap* m, const void* base, int C, int S, int B, int 
   return make_tmap_bf16_5d(m, base, dims, str, box);
 }
 
-template <int BN, bool BNB>
+template <int BN, bool BNB, int AST>
 static int halo2_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d,
                           const CUtensorMap& y, const Halo2Params& p, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    int e = check_cuda(cudaFuncSetAttribute(conv3_halo2_kernel<BN, BNB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            H2Cfg<BN, BNB>::SMEM),
+    int e = check_cuda(cudaFuncSetAttribute(conv3_halo2_kernel<BN, BNB, AST>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<BN, BNB, AST>::SMEM),
                        "cudaFuncSetAttribute(conv3_halo2)");
     if (e) return e;
     attr_set = true;
   }
-  launch_k(conv3_halo2_kernel<BN, BNB>, dim3(grid), dim3(kH2Threads), H2Cfg<BN, BNB>::SMEM, stream, a0, a1, b, d, y, p);
+  launch_k(conv3_halo2_kernel<BN, BNB, AST>, dim3(grid), dim3(kH2Threads), H2Cfg<BN, BNB, AST>::SMEM, stream, a0, a1, b,
+           d, y, p);
   return check_launch("conv3_halo2_kernel");
+}
+
+// halo stages: 2 (default); SUNET_HALO2_AST=3 selects the three-stage variants where shared memory allows them
+// (N = 64 both forms, N = 128 without the BNB y slots) — an A/B timing knob, see H2Cfg
+static int halo2_ast() {
+  static const int v = [] {
+    const char* e = getenv("SUNET_HALO2_AST");
+    return (e && atoi(e) == 3) ? 3 : 2;
+  }();
+  return v;
 }
 
 bool conv3_halo2_eligible(const sunet_conv_gemm_args* a) {
@@ -551,14 +569,20 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   p.ep_scale = a->ep_scale;
   p.ep_shift = a->ep_shift;
   const int grid = halo2_slots(B, H, W, p.n_tiles, bw) * p.n_tiles * 2;
+  const bool a3 = halo2_ast() == 3;
   if (bnb) {
-    if (bn == 256) return halo2_launch_t<256, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
-    if (bn == 128) return halo2_launch_t<128, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
-    return halo2_launch_t<64, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    if (bn == 256) return halo2_launch_t<256, true, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    if (bn == 128) return halo2_launch_t<128, true, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    if (a3) return halo2_launch_t<64, true, 3>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    return halo2_launch_t<64, true, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
   }
-  if (bn == 256) return halo2_launch_t<256, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
-  if (bn == 128) return halo2_launch_t<128, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
-  return halo2_launch_t<64, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  if (bn == 256) return halo2_launch_t<256, false, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  if (bn == 128) {
+    if (a3) return halo2_launch_t<128, false, 3>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    return halo2_launch_t<128, false, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  }
+  if (a3) return halo2_launch_t<64, false, 3>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  return halo2_launch_t<64, false, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
 }
 
 }  // namespace sunet

@@ -18,7 +18,17 @@ from typing import Dict, Tuple
 import torch
 import torch.nn as nn
 
+import os
+
 from .engine import FlatGrads, SUNetPlan, param_order
+
+
+def _plan_class():
+    """SUNET_CHECK_FP32=1: the slow fp32 check mode (engine_fp32.SUNetPlanF32) instead of the bf16 tensor-core plan."""
+    if os.environ.get("SUNET_CHECK_FP32", "0") != "0":
+        from .engine_fp32 import SUNetPlanF32
+        return SUNetPlanF32
+    return SUNetPlan
 
 
 def CBR_2D(in_ch, out_ch, k_size=3, stride=1, padding=1, bias=True):
@@ -129,7 +139,7 @@ class UNet_B(nn.Module):
         if plan is None:
             if len(self._plans) >= 4:
                 self._plans.pop(next(iter(self._plans)))
-            plan = SUNetPlan(batch, height, width, self.input_ch, self.selective, device, n_cls=self._N_CLS)
+            plan = _plan_class()(batch, height, width, self.input_ch, self.selective, device, n_cls=self._N_CLS)
             self._plans[key] = plan
         return plan
 
@@ -148,8 +158,8 @@ class UNet_B(nn.Module):
         if plan is None:
             if len(self._plans) >= 4:        # plans own GBs of activations: keep a few shapes only
                 self._plans.pop(next(iter(self._plans)))
-            plan = SUNetPlan(x.shape[0], x.shape[2], x.shape[3], self.input_ch, self.selective, x.device,
-                             n_cls=self._N_CLS)
+            plan = _plan_class()(x.shape[0], x.shape[2], x.shape[3], self.input_ch, self.selective, x.device,
+                                 n_cls=self._N_CLS)
             self._plans[key] = plan
         return plan
 

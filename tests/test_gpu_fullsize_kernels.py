@@ -1,6 +1,6 @@
 """Per-kernel parity at the REAL layer shapes of the configurations BASELINE.json is quoted on (batch 128 of 256x256
 patches on one GPU, 16-patch shards on eight), against GPU fp32 torch (TF32 off) on the same bf16-rounded inputs, at
-the tolerances DESIGN.md states: 3e-3 of max|ref| for bf16 outputs (half an ulp of bf16 is 2e-3 of the value),
+the tolerances DESIGN.md states: 4e-3 of max|ref| for bf16 outputs (half an ulp of bf16 is 2^-9 .. 2^-8 of the value),
 1e-3 for fp32 reductions, exact equality where two of our kernels must agree bit for bit.
 
 Shapes: the 16-patch shard of level 1 (16 x 256^2 x 64 -> 64, and the two-source decoder form 64 + 64 -> 64), the
@@ -24,7 +24,7 @@ probe = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(probe)
 nhwc, nchw = probe.nhwc, probe.nchw
 
-TOL_BF16 = 3e-3      # bf16 outputs, relative to max|ref|
+TOL_BF16 = 4e-3      # bf16 outputs, relative to max|ref|: half an ulp of bf16 is up to 2^-8 = 3.9e-3 of the value
 TOL_RED = 1e-3       # fp32 reductions, relative to max|ref|
 
 

@@ -115,7 +115,7 @@ def test_validation_step_matches_oracle():
     for k, v in net.state_dict().items():                 # no parameter / running-stat update in validation
         assert torch.equal(v, before[k]), k
     with torch.no_grad():
-        out, sel, aux = O.unet_b_forward(sd, x, False, True)
+        out, sel, aux = O.unet_b_forward(sd, x, True, False)      # (selective, training=False)
         l_sel, cov = O.selective_risk_b(out, sel, label, lamb=2)
         l_aux = O.bce_with_logits_mean(aux, label)
     got = res.cpu().tolist()
