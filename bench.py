@@ -415,9 +415,10 @@ def run_ours(args):
     lo, hi = chunk_bounds(gb, world, rank)
     b = hi - lo
     torch.manual_seed(0)
-    net = UNet_B("RGB", selective=True).to(dev)
+    sel_net = not args.non_selective
+    net = UNet_B("RGB", selective=sel_net).to(dev)
     net.train()
-    ev = Evaluator(2, True, device=dev)
+    ev = Evaluator(2, sel_net, device=dev)
     tr = SUNetTrainer(net, lr=1e-3, s_lamb=2, process_group=group, world_size=world, evaluator=ev,
                       use_cuda_graph=not args.no_graph)
     g = torch.Generator().manual_seed(1234)
@@ -574,7 +575,7 @@ def run_ours(args):
         roof = None
 
     evalb = None
-    if not args.no_eval:
+    if not args.no_eval and sel_net:
         evalb = eval_block(net, world, rank, dev, args.eval_patches, args.size, min(128, max(1, args.eval_patches // world)),
                            K, torch, dist)
     graph_on = tr.graph_active("train")
@@ -599,8 +600,11 @@ def run_ours(args):
             "metric": "SUNet_B train patches/sec (256^2, bf16)", "value": value, "unit": "patches/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "SUNet_B (UNet_B --selective 1 --s_lamb 2, BCElogit) train step: fwd + aux BCE + "
-                                   "selective risk + bwd + Adam + confusion matrix, 256x256 RGB patches, random init",
+            "config": {"workload": ("SUNet_B (UNet_B --selective 1 --s_lamb 2, BCElogit) train step: fwd + aux BCE + "
+                                    "selective risk + bwd + Adam + confusion matrix, 256x256 RGB patches, random init")
+                       if sel_net and args.size == 256 else
+                       (f"{'SUNet_B' if sel_net else 'UNet_B (non-selective, BCElogit)'} train step, {args.size}x{args.size} "
+                        f"RGB patches, random init (BASELINE configs[4] sweep point)"),
                        "global_batch": gb, "per_gpu_batch": b, "patch": args.size, "parallelism": f"dp{world}",
                        "l2": "inputs_exceed_l2 (activations ~120 MB/patch >> 126 MB L2)",
                        "cuda_graph": bool(graph_on)},
@@ -631,6 +635,8 @@ def run_ours(args):
             line["eval"] = evalb
         if dp_parity is not None:
             line["dp_parity"] = dp_parity
+        if args.report_memory:
+            line["peak_gb"] = torch.cuda.max_memory_allocated(dev) / 1e9
         line["kernel_sha"] = kernel_source_sha()
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -740,6 +746,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-u8", action="store_true", help="skip the extra end-to-end pass fed with uint8 patches")
     ap.add_argument("--launch-table", default=None, help="write per-launch tensor-core timings of one step here")
+    ap.add_argument("--report-memory", action="store_true", help="add peak_gb (torch peak allocated) to the line")
+    ap.add_argument("--non-selective", action="store_true", help="plain UNet_B + BCElogit (configs[4] sweep)")
     ap.add_argument("--no-stock", action="store_true", help="skip the stock-PyTorch (cuDNN) GPU baseline leg")
     ap.add_argument("--no-eval", action="store_true", help="skip the evaluation block (BASELINE configs[3])")
     ap.add_argument("--no-dp-parity", action="store_true", help="skip the data-parallel parity step (N > 1)")

@@ -160,14 +160,15 @@ int sunet_pack_convT_weights(const float* w, const float* bias, void* wf, void* 
  *   kind 3: first conv, paired-pixel form (a = 64, b = cin; wf as sunet_pack_conv1_pair_weights)
  *   kind 2: ConvTranspose2d (a = cin, b = cout; wf, wd, bias, bias4 as sunet_pack_convT_weights) */
 typedef struct sunet_pack_job {
-  int kind, a, b, pad_;
+  int kind, a, b, tile_start;  /* first block of this job in the flat grid: prefix sum of (a/32)*(b/32) for kinds 0
+                                  and 2, 1 for kinds 1 and 3; total_tiles = the sum over all jobs */
   const float* w;
   const float* bias;
   void* wf;
   void* wd;
   float* bias4;
 } sunet_pack_job;
-int sunet_pack_weights_table(const sunet_pack_job* jobs_dev, int n_jobs, sunet_stream_t stream);
+int sunet_pack_weights_table(const sunet_pack_job* jobs_dev, int n_jobs, int total_tiles, sunet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNorm2d + ReLU (+ MaxPool2d(2)), model.py:12-13,31,35,39

@@ -83,6 +83,29 @@ def main():
     a = torch.empty_like(y)
     t = timeit(lambda: K.heads_bwd(dl, a, wts, dA, dws, dbs, ws))
     rows.append(("heads_bwd (stored a)  256x256x64", 4 * y.numel() + 12 * P, t))
+    # losses / metric / Adam (vectorised in round 2).  P2 = 512 patches of 256^2 so every array exceeds the 126 MB L2.
+    P2 = 512 * 256 * 256
+    lg = torch.randn(3, P2, device=dev)
+    tgt = (torch.rand(P2, device=dev) < 0.4).float()
+    lab8 = tgt.to(torch.uint8)
+    sums = torch.zeros(4, dtype=torch.float64, device=dev)
+    dlg = torch.empty(3, P2, device=dev)
+    cnt = torch.zeros(6, dtype=torch.int64, device=dev)
+    t = timeit(lambda: K.loss_sums(lg[0], lg[1], lg[2], tgt, sums, ws, pixels_out=sums[3:4]))
+    rows.append(("loss_sums (3 logits + label f32)", 16 * P2, t))
+    t = timeit(lambda: K.loss_bwd(lg[0], lg[1], lg[2], tgt, sums, P2, 2.0, 0.8, None, None, dlg[0], dlg[1], dlg[2]))
+    rows.append(("loss_bwd (4 reads, 3 writes)", 28 * P2, t))
+    t = timeit(lambda: K.metric_hist(lg[0], lg[1], lab8, 1e-7, 1e-7, True, cnt))
+    rows.append(("metric_hist (2 logits + u8 label)", 9 * P2, t))
+    t = timeit(lambda: K.metric_hist(lg[0], lg[1], tgt, 1e-7, 1e-7, True, cnt))
+    rows.append(("metric_hist (2 logits + f32 label)", 12 * P2, t))
+    del lg, dlg
+    from selectivenet_for_semantic_segmentation_binary_b200.optim import Adam
+    big = [torch.nn.Parameter(torch.randn(64 * 1024 * 1024, device=dev))]          # 268 MB per array
+    big[0].grad = torch.randn_like(big[0])
+    opt = Adam(big, lr=1e-3)
+    t = timeit(lambda: opt.step())
+    rows.append(("adam (one 64 Mi-element tensor)", 28 * big[0].numel(), t))
     for name, nbytes, t in rows:
         gbs = nbytes / t / 1e6
         print(f"{name:34s} {t:8.4f} ms  {gbs:8.1f} GB/s  {100 * gbs / peak:5.1f}% of {peak:.0f}", flush=True)

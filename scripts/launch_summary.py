@@ -57,7 +57,11 @@ def traffic_json(path, out):
         elif r[mi].startswith("gpu__time"):
             n += 1
             t += v
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import kernel_source_sha          # the stamp bench.py checks before it trusts this file
     json.dump({"kernel_family": "G1 (conv3_halo2_kernel*, conv_gemm_kernel*)", "launches": n,
+               "kernel_sha": kernel_source_sha(),
                "dram_bytes_per_launch": tot / n, "avg_launch_ns_under_ncu": t / n,
                "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
                          "(scripts/ncu_launches.sh), file " + path.split("/")[-1]}, open(out, "w"), indent=1)

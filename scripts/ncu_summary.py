@@ -19,6 +19,7 @@ KEYS = [
     ("launch__shared_mem_per_block_dynamic", "dyn smem"),
     ("launch__grid_size", "grid"),
     ("sm__cycles_elapsed.avg.per_second", "sm clk"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
 ]
 
 
@@ -40,7 +41,11 @@ def main():
             for k, _ in KEYS:
                 v = d.get(k)
                 cells.append("-" if v in (None, "") else f"{v} {u.get(k, '')}".strip())
-            print(f"| {path.split('/')[-1]} | {name} | " + " | ".join(cells) + " |")
+            stalls = sorted(((float(v.replace(",", "")), k) for k, v in d.items()
+                             if "issue_stalled" in k and k.endswith("_per_warp_active.pct") and v not in ("", None)),
+                            reverse=True)[:3]
+            top = "; ".join(f"{k.split('issue_stalled_')[1].split('_per_warp')[0]} {x:.0f}%" for x, k in stalls)
+            print(f"| {path.split('/')[-1]} | {name} | " + " | ".join(cells) + " |" + (f" stalls: {top}" if top else ""))
 
 
 if __name__ == "__main__":

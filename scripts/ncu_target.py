@@ -1,6 +1,7 @@
 """Small single-kernel workloads for `ncu --set full` (B200_PROFILING.md: keep the profiled command short).
 
-    python scripts/ncu_target.py conv64|conv128|conv256|wgrad128|wgrad256|wgrad64|bnbwd|bnfwd
+    python scripts/ncu_target.py conv64|conv128|conv256|wgrad128|wgrad256|wgrad64|bnbwd|bnfwd|headsbwd|headsfwd|hist|
+                                 losssums|lossbwd|adam
 
 Shapes are the bench shapes (batch 128 of 256x256 patches) of the corresponding SUNet_B layer.
 """
@@ -48,7 +49,61 @@ def bn(B, H, W, C, bwd, iters=3):
             K.bn_relu_pool(y, sc, sh, out, None)
 
 
+def heads(bwd, iters=3, B=128):
+    P = B * 256 * 256
+    y = (torch.randn(B, 256, 256, 64, device="cuda") * 1.5 + 0.3).to(torch.bfloat16)
+    sc, sh, mu, isd = (torch.rand(64, device="cuda") + 0.5 for _ in range(4))
+    wts = [torch.randn(1, 64, 1, 1, device="cuda") for _ in range(3)]
+    bss = [torch.randn(1, device="cuda") for _ in range(3)]
+    ws = K.new_workspace("cuda")
+    if bwd:
+        dA = torch.empty_like(y)
+        dl = torch.randn(3, P, device="cuda")
+        dws, dbs = [torch.empty_like(w) for w in wts], [torch.empty_like(b) for b in bss]
+        part = torch.empty(K.heads_bwd_bn_rows(P), 64, 2, device="cuda")
+        for _ in range(iters):
+            K.heads_bwd_bn(dl, y, sc, sh, mu, isd, wts, dA, dws, dbs, part, ws)
+    else:
+        logits = torch.empty(3, P, device="cuda")
+        for _ in range(iters):
+            K.bn_relu_heads(y, sc, sh, None, wts, bss, logits)
+
+
+def small(which, iters=3):
+    P = 512 * 256 * 256                     # 302+ MB per launch: larger than the 126 MB L2
+    lg = torch.randn(3, P, device="cuda")
+    tgt = (torch.rand(P, device="cuda") < 0.4).float()
+    ws = K.new_workspace("cuda")
+    sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+    if which == "hist":
+        lab8 = tgt.to(torch.uint8)
+        cnt = torch.zeros(6, dtype=torch.int64, device="cuda")
+        for _ in range(iters):
+            K.metric_hist(lg[0], lg[1], lab8, 1e-7, 1e-7, True, cnt)
+    elif which == "losssums":
+        for _ in range(iters):
+            K.loss_sums(lg[0], lg[1], lg[2], tgt, sums, ws, pixels_out=sums[3:4])
+    elif which == "lossbwd":
+        K.loss_sums(lg[0], lg[1], lg[2], tgt, sums, ws, pixels_out=sums[3:4])
+        d = torch.empty(3, P, device="cuda")
+        for _ in range(iters):
+            K.loss_bwd(lg[0], lg[1], lg[2], tgt, sums, P, 2.0, 0.8, None, None, d[0], d[1], d[2])
+    elif which == "adam":
+        from selectivenet_for_semantic_segmentation_binary_b200.optim import Adam
+        p = [torch.nn.Parameter(torch.randn(64 * 1024 * 1024, device="cuda"))]
+        p[0].grad = torch.randn_like(p[0])
+        opt = Adam(p, lr=1e-3)
+        for _ in range(iters):
+            opt.step()
+
+
 MODES = {
+    "headsbwd": lambda: heads(True),
+    "headsfwd": lambda: heads(False),
+    "hist": lambda: small("hist"),
+    "losssums": lambda: small("losssums"),
+    "lossbwd": lambda: small("lossbwd"),
+    "adam": lambda: small("adam"),
     "conv64": lambda: conv(128, 256, 256, 64, 64),
     "conv512": lambda: conv(128, 32, 32, 512, 512),
     "conv128": lambda: conv(128, 128, 128, 128, 128),

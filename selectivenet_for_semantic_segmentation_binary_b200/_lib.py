@@ -51,7 +51,7 @@ class WgradGemmArgs(C.Structure):
 
 class PackJob(C.Structure):
     _fields_ = [
-        ("kind", C.c_int), ("a", C.c_int), ("b", C.c_int), ("pad_", C.c_int),
+        ("kind", C.c_int), ("a", C.c_int), ("b", C.c_int), ("tile_start", C.c_int),
         ("w", C.c_void_p), ("bias", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p), ("bias4", C.c_void_p),
     ]
 
@@ -85,7 +85,7 @@ SIGNATURES = {
     "sunet_pack_conv3x3_weights": [_vp, _vp, _vp, _i, _i, _vp],
     "sunet_pack_conv1_weights": [_vp, _vp, _i, _i, _vp],
     "sunet_pack_convT_weights": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
-    "sunet_pack_weights_table": [_vp, _i, _vp],
+    "sunet_pack_weights_table": [_vp, _i, _i, _vp],
     "sunet_bn_finalize": [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "sunet_bn_eval_affine": [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp],
     "sunet_bn_relu_pool": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],

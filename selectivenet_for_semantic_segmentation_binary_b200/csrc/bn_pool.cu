@@ -269,14 +269,13 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, const float* __re
 // A block moves a 32(a) x 32(b) x T tile through shared memory so that the fp32 reads and both bf16 writes are
 // contiguous runs (the element-wise form of this kernel read with stride T and wrote with stride T*An).
 template <int T, bool CONVT>
-__device__ __forceinline__ void pack_tile(const sunet_pack_job& j, float (*tile)[32 * 9 + 1]) {
+__device__ __forceinline__ void pack_tile(const sunet_pack_job& j, float (*tile)[32 * 9 + 1], int tix) {
   const int An = j.a, Bn = j.b;
-  const int tiles_b = Bn >> 5, tiles = (An >> 5) * tiles_b;
+  const int tiles_b = Bn >> 5;
   __nv_bfloat16* out_b = reinterpret_cast<__nv_bfloat16*>(CONVT ? j.wd : j.wf);
   __nv_bfloat16* out_a = reinterpret_cast<__nv_bfloat16*>(CONVT ? j.wf : j.wd);
-  for (int tix = blockIdx.x; tix < tiles; tix += gridDim.x) {
+  {
     const int a0 = (tix / tiles_b) << 5, b0 = (tix % tiles_b) << 5;
-    __syncthreads();
     for (int i = threadIdx.x; i < 32 * 32 * T; i += 256) {
       const int al = i / (32 * T), r = i - al * (32 * T);
       tile[al][r] = j.w[((size_t)(a0 + al) * Bn + b0) * T + r];
@@ -296,19 +295,34 @@ __device__ __forceinline__ void pack_tile(const sunet_pack_job& j, float (*tile)
   }
 }
 
-// One launch packs every weight tensor of the network (table of jobs): 17 launches -> 1.
+// One launch packs every weight tensor of the network (table of jobs): 17 launches -> 1.  The grid is FLAT over the
+// 32x32 channel tiles of all jobs (job j owns blocks [tile_start_j, tile_start_{j+1})): with one block column per job
+// the 512x512 layer's 256 tiles were moved by 96 blocks while 1 500 others idled (84 us per step, 0.4 TB/s).
+__device__ __forceinline__ int pack_job_tiles(const sunet_pack_job& j) {
+  return (j.kind == 0 || j.kind == 2) ? (j.a >> 5) * (j.b >> 5) : 1;
+}
 __global__ void __launch_bounds__(256)
-pack_table_kernel(const sunet_pack_job* __restrict__ jobs) {
+pack_table_kernel(const sunet_pack_job* __restrict__ jobs, int n_jobs) {
   pdl_wait();
   pdl_trigger();
   __shared__ float tile[32][32 * 9 + 1];
-  const sunet_pack_job j = jobs[blockIdx.y];
+  __shared__ int s_job, s_tix;
+  if (threadIdx.x == 0) {
+    int jb = 0;
+    while (jb + 1 < n_jobs && (int)blockIdx.x >= jobs[jb + 1].tile_start) ++jb;
+    s_job = jb;
+    s_tix = (int)blockIdx.x - jobs[jb].tile_start;
+  }
+  __syncthreads();
+  const sunet_pack_job j = jobs[s_job];
+  const int tix = s_tix;
+  if (tix >= pack_job_tiles(j)) return;
   if (j.kind == 0) {            // conv3x3: a = cout, b = cin
-    pack_tile<9, false>(j, tile);
+    pack_tile<9, false>(j, tile, tix);
   } else if (j.kind == 1) {     // first conv: a = cout, b = cin, K padded to 64
     const int co_n = j.a, cin = j.b;
     __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < co_n * 64; i += gridDim.x * blockDim.x) {
+    for (int i = threadIdx.x; i < co_n * 64; i += blockDim.x) {
       const int k = i & 63, co = i >> 6;
       float v = 0.f;
       if (k < 9 * cin) {
@@ -319,13 +333,11 @@ pack_table_kernel(const sunet_pack_job* __restrict__ jobs) {
     }
   } else if (j.kind == 3) {     // first conv, paired-pixel form: a = 64 (cout), b = cin
     __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(j.wf);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 64; i += gridDim.x * blockDim.x)
-      wf[i] = __float2bfloat16_rn(conv1_pair_weight(j.w, j.b, i));
+    for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) wf[i] = __float2bfloat16_rn(conv1_pair_weight(j.w, j.b, i));
   } else {                      // ConvTranspose2d: a = cin, b = cout
-    pack_tile<4, true>(j, tile);
-    if (j.bias4)
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * j.b; i += gridDim.x * blockDim.x)
-        j.bias4[i] = j.bias ? j.bias[i % j.b] : 0.f;
+    pack_tile<4, true>(j, tile, tix);
+    if (j.bias4 && tix == 0)
+      for (int i = threadIdx.x; i < 4 * j.b; i += blockDim.x) j.bias4[i] = j.bias ? j.bias[i % j.b] : 0.f;
   }
 }
 
@@ -383,14 +395,20 @@ __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, con
   shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
 }
 
-__global__ void colsum_finalize_kernel(const float* stats, int rows, int n_total, int col_offset, int C, float* out) {
+// one warp per channel (lanes stride over the per-CTA rows, fixed-order fp64 tree): the serial per-thread loop over
+// up to 296 rows took 14 us per launch
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const float* stats, int rows, int n_total, int col_offset, int C, float* out) {
   pdl_wait();
   pdl_trigger();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0;
-  for (int r = 0; r < rows; ++r) s += (double)stats[((size_t)r * n_total + col_offset + c) * 2];
-  out[c] = (float)s;
+  for (int r = lane; r < rows; r += 32) s += (double)stats[((size_t)r * n_total + col_offset + c) * 2];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[c] = (float)s;
 }
 
 // ------------------------------------------------------------------ BN + ReLU (+ pool) forward
@@ -971,10 +989,11 @@ extern "C" int sunet_pack_convT_weights(const float* w, const float* bias, void*
   return check_launch("pack_convT_weights");
 }
 
-extern "C" int sunet_pack_weights_table(const sunet_pack_job* jobs_dev, int n_jobs, sunet_stream_t stream_) {
-  if (!jobs_dev || n_jobs <= 0) return set_error(SUNET_ERR_INVALID, "pack_weights_table: bad arguments");
-  dim3 grid(96, (unsigned)n_jobs);
-  launch_k(pack_table_kernel, dim3(grid), dim3(256), 0, STREAM, jobs_dev);
+extern "C" int sunet_pack_weights_table(const sunet_pack_job* jobs_dev, int n_jobs, int total_tiles,
+                                        sunet_stream_t stream_) {
+  if (!jobs_dev || n_jobs <= 0 || total_tiles <= 0)
+    return set_error(SUNET_ERR_INVALID, "pack_weights_table: bad arguments");
+  launch_k(pack_table_kernel, dim3((unsigned)total_tiles), dim3(256), 0, STREAM, jobs_dev, n_jobs);
   return check_launch("pack_weights_table");
 }
 
@@ -1007,7 +1026,7 @@ extern "C" int sunet_colsum_finalize(const float* stats, int rows, int n_total, 
                                      float* out, sunet_stream_t stream_) {
   if (!stats || !out || rows <= 0 || channels <= 0 || col_offset < 0 || col_offset + channels > n_total)
     return set_error(SUNET_ERR_INVALID, "colsum_finalize: bad arguments");
-  launch_k(colsum_finalize_kernel, dim3((channels + 127) / 128), dim3(128), 0, STREAM, stats, rows, n_total, col_offset, channels, out);
+  launch_k(colsum_finalize_kernel, dim3((channels + 7) / 8), dim3(256), 0, STREAM, stats, rows, n_total, col_offset, channels, out);
   return check_launch("colsum_finalize");
 }
 

@@ -1,8 +1,9 @@
 // fp32 CHECK MODE (BASELINE.json north_star: "logits and loss must agree within 2e-2 relative in bf16, or 1e-4 in an
 // fp32 check mode").  Slow, obviously-correct SIMT fp32 twins of every op of the hot path: NHWC fp32 activations,
-// parameters read in the reference's own layouts (no repack), fp32 FMA accumulation for the contractions and fp64
-// accumulation for every reduction over pixels.  Selected with SUNET_CHECK_FP32=1 (engine_fp32.SUNetPlanF32); the
-// losses, the counting kernel and Adam are already fp32 and are shared with the fast path.  Test infrastructure of
+// parameters read in the reference's own layouts (no repack), fp64 accumulation inside every contraction and every
+// reduction over pixels (values are STORED in fp32: the only roundings are one per stored element).  Selected with
+// SUNET_CHECK_FP32=1 (engine_fp32.SUNetPlanF32); the losses, the counting kernel and Adam are already fp32 and are
+// shared with the fast path.  Test infrastructure of
 // the product path's ORCHESTRATION (layer order, concat order, BatchNorm bookkeeping, pool routing, loss plumbing):
 // with fp32 numerics a wrong tap, a swapped concat half or a missed term shows up at 1e-1, not inside bf16 noise.
 // Nothing here is tuned; it is never used by bench.py.
@@ -33,7 +34,7 @@ f32_conv3x3_fwd_kernel(const float* __restrict__ x0, int c0, const float* __rest
     const int co = (int)(i % Cout);
     const long long p = i / Cout;
     const int xx = (int)(p % W), yy = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
-    float acc = bias ? bias[co] : 0.f;
+    double acc = bias ? (double)bias[co] : 0.0;
     for (int r = 0; r < 3; ++r) {
       const int iy = yy + r - 1;
       if (iy < 0 || iy >= H) continue;
@@ -43,14 +44,14 @@ f32_conv3x3_fwd_kernel(const float* __restrict__ x0, int c0, const float* __rest
         const long long q = ((long long)n * H + iy) * W + ix;
         const float* wp = w + ((long long)co * Cin) * 9 + r * 3 + s;
         const float* a = x0 + q * c0;
-        for (int ci = 0; ci < c0; ++ci) acc = fmaf(a[ci], wp[(long long)ci * 9], acc);
+        for (int ci = 0; ci < c0; ++ci) acc += (double)a[ci] * (double)wp[(long long)ci * 9];
         if (c1) {
           const float* b = x1 + q * c1;
-          for (int ci = 0; ci < c1; ++ci) acc = fmaf(b[ci], wp[(long long)(c0 + ci) * 9], acc);
+          for (int ci = 0; ci < c1; ++ci) acc += (double)b[ci] * (double)wp[(long long)(c0 + ci) * 9];
         }
       }
     }
-    y[i] = acc;
+    y[i] = (float)acc;
   }
 }
 
@@ -64,7 +65,7 @@ f32_conv3x3_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__
     const int ci = (int)(i % Cin);
     const long long p = i / Cin;
     const int xx = (int)(p % W), yy = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
-    float acc = 0.f;
+    double acc = 0.0;
     for (int r = 0; r < 3; ++r) {
       const int oy = yy - (r - 1);
       if (oy < 0 || oy >= H) continue;
@@ -73,11 +74,11 @@ f32_conv3x3_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__
         if (ox < 0 || ox >= W) continue;
         const float* g = dy + (((long long)n * H + oy) * W + ox) * Cout;
         const float* wp = w + (long long)ci * 9 + r * 3 + s;
-        for (int co = 0; co < Cout; ++co) acc = fmaf(g[co], wp[(long long)co * Cin * 9], acc);
+        for (int co = 0; co < Cout; ++co) acc += (double)g[co] * (double)wp[(long long)co * Cin * 9];
       }
     }
-    if (ci < c0) dx0[p * c0 + ci] = acc;
-    else dx1[p * c1 + (ci - c0)] = acc;
+    if (ci < c0) dx0[p * c0 + ci] = (float)acc;
+    else dx1[p * c1 + (ci - c0)] = (float)acc;
   }
 }
 
@@ -129,9 +130,9 @@ f32_convT_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     const int X = (int)(p % (2 * wd)), Y = (int)((p / (2 * wd)) % (2 * h)), n = (int)(p / ((long long)4 * wd * h));
     const float* a = x + (((long long)n * h + (Y >> 1)) * wd + (X >> 1)) * Cin;
     const float* wp = w + (long long)co * 4 + (Y & 1) * 2 + (X & 1);
-    float acc = bias[co];
-    for (int ci = 0; ci < Cin; ++ci) acc = fmaf(a[ci], wp[(long long)ci * Cout * 4], acc);
-    y[i] = acc;
+    double acc = (double)bias[co];
+    for (int ci = 0; ci < Cin; ++ci) acc += (double)a[ci] * (double)wp[(long long)ci * Cout * 4];
+    y[i] = (float)acc;
   }
 }
 __global__ void __launch_bounds__(256)
@@ -142,14 +143,14 @@ f32_convT_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w
     const int ci = (int)(i % Cin);
     const long long p = i / Cin;
     const int xx = (int)(p % wd), yy = (int)((p / wd) % h), n = (int)(p / ((long long)wd * h));
-    float acc = 0.f;
+    double acc = 0.0;
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
         const float* g = dy + (((long long)n * 2 * h + 2 * yy + a) * 2 * wd + 2 * xx + b) * Cout;
         const float* wp = w + (long long)ci * Cout * 4 + a * 2 + b;
-        for (int co = 0; co < Cout; ++co) acc = fmaf(g[co], wp[(long long)co * 4], acc);
+        for (int co = 0; co < Cout; ++co) acc += (double)g[co] * (double)wp[(long long)co * 4];
       }
-    dx[i] = acc;
+    dx[i] = (float)acc;
   }
 }
 // dw[ci][co][a][b] = sum_p x[p][ci] * dy[2p + (a,b)][co]; dbias[co] = sum over all output pixels of dy (block co when ci == 0)
@@ -241,7 +242,7 @@ f32_bn_relu_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                    float* __restrict__ a, long long total, int C) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
-    a[i] = fmaxf(fmaf(y[i], scale[c], shift[c]), 0.f);
+    a[i] = fmaxf((float)((double)y[i] * (double)scale[c] + (double)shift[c]), 0.f);
   }
 }
 __global__ void __launch_bounds__(256)
@@ -335,9 +336,9 @@ f32_heads_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w, c
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int h = (int)(i / P);
     const long long p = i % P;
-    float acc = b[h];
-    for (int c = 0; c < C; ++c) acc = fmaf(a[p * C + c], w[h * C + c], acc);
-    logits[i] = acc;
+    double acc = (double)b[h];
+    for (int c = 0; c < C; ++c) acc += (double)a[p * C + c] * (double)w[h * C + c];
+    logits[i] = (float)acc;
   }
 }
 __global__ void __launch_bounds__(256)
@@ -347,9 +348,9 @@ f32_heads_bwd_dA_kernel(const float* __restrict__ dl, const float* __restrict__ 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long p = i / C;
-    float acc = accumulate ? dA[i] : 0.f;
-    for (int h = 0; h < nheads; ++h) acc = fmaf(dl[(long long)h * P + p], w[h * C + c], acc);
-    dA[i] = acc;
+    double acc = accumulate ? (double)dA[i] : 0.0;
+    for (int h = 0; h < nheads; ++h) acc += (double)dl[(long long)h * P + p] * (double)w[h * C + c];
+    dA[i] = (float)acc;
   }
 }
 // one block per (head, channel | bias): dw[h][c] = sum_p dl[h][p] * a[p][c]; db[h] = sum_p dl[h][p]

@@ -36,6 +36,16 @@ __device__ __forceinline__ float bce_logits(float x, float t) {
   return fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
 }
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// Phase-1 reductions (sums over millions of pixels, consumed at 1e-5 relative): MUFU-based forms, ~28 instructions
+// per pixel instead of ~95 — the precise expf / log1pf / division made loss_sums ALU-bound at 58 % of the HBM
+// roofline (profiles/r02/ew_bw_stream_kernels.log).  Per-pixel absolute error <= ~2e-7 (ex2.approx / lg2.approx / rcp),
+// i.e. <= 4e-7 of a mean loss of O(0.5); the per-pixel GRADIENTS (loss_bwd) keep the precise forms.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float bce_logits_fast(float x, float t) {
+  const float z = __expf(-fabsf(x));
+  const float l1p = z < 1e-4f ? z * fmaf(-0.5f, z, 1.f) : __logf(1.f + z);
+  return fmaxf(x, 0.f) - x * t + l1p;
+}
 
 // ------------------------------------------------------------------ heads forward
 struct HeadW {
@@ -367,11 +377,11 @@ loss_sums_kernel(const float* __restrict__ out, const float* __restrict__ sel, c
   float S = 0.f, R = 0.f, A = 0.f;
   auto pixel = [&](float t, float xs, float xo, float xa) {
     if (sel) {
-      const float s = sigmoid_acc(xs);
+      const float s = sigmoid_fast(xs);
       S += s;
-      if (out) R = fmaf(bce_logits(xo, t), s, R);
+      if (out) R = fmaf(bce_logits_fast(xo, t), s, R);
     }
-    if (aux) A += bce_logits(xa, t);
+    if (aux) A += bce_logits_fast(xa, t);
   };
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -844,7 +854,8 @@ extern "C" int sunet_adam_step(const sunet_adam_tensor* table, int n_tensors, lo
   if (!table || n_tensors <= 0 || max_numel <= 0 || (step <= 0 && !step_dev))
     return set_error(SUNET_ERR_INVALID, "adam_step: bad arguments");
   long long bx = (max_numel + 256 * 16 - 1) / (256 * 16);      // float4 per thread, ~4 trips
-  if (bx > 148) bx = 148;
+  const long long cap = (long long)num_sms() * 8 / (n_tensors < 8 ? 1 : 8);     // few tensors: fill the SMs from x alone
+  if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)n_tensors);
   launch_k(adam_kernel, dim3(grid), dim3(256), 0, STREAM, table, lr, beta1, beta2, eps, weight_decay, step, lr_dev, step_dev);

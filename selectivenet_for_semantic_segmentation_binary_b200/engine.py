@@ -297,12 +297,16 @@ class SUNetPlan:
                 j.kind, j.a, j.b = 2, w.shape[0], w.shape[1]
                 j.w, j.bias, j.wf, j.wd, j.bias4 = (w.data_ptr(), b.data_ptr(), u["wf"].data_ptr(), u["wd"].data_ptr(),
                                                    u["b4"].data_ptr())
+            start = 0                                     # flat grid: job j owns blocks [tile_start_j, tile_start_{j+1})
+            for j in jobs:
+                j.tile_start = start
+                start += (j.a // 32) * (j.b // 32) if j.kind in (0, 2) else 1
             if len(cache) >= 32:
                 cache.pop(next(iter(cache)))
-            cache[key] = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device)
-        self._pack_jobs = cache[key]
+            cache[key] = (torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device), start)
+        self._pack_jobs, self._pack_tiles = cache[key]
         self._pack_n = len(self.order) + 3
-        K.pack_weights_table(self._pack_jobs, self._pack_n)
+        K.pack_weights_table(self._pack_jobs, self._pack_n, self._pack_tiles)
 
     # ------------------------------------------------------------------ forward
     def _cbr_fwd_eval_fused(self, ly: _Layer, params, buffers) -> bool:

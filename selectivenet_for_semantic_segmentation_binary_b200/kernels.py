@@ -208,8 +208,8 @@ def pack_convT_weights(w, bias, wf, wd, bias4) -> None:
                                                     _stream()), "sunet_pack_convT_weights")
 
 
-def pack_weights_table(table_dev: torch.Tensor, n_jobs: int) -> None:
-    _lib.check(_lib.load().sunet_pack_weights_table(table_dev.data_ptr(), n_jobs, _stream()),
+def pack_weights_table(table_dev: torch.Tensor, n_jobs: int, total_tiles: int) -> None:
+    _lib.check(_lib.load().sunet_pack_weights_table(table_dev.data_ptr(), n_jobs, total_tiles, _stream()),
                "sunet_pack_weights_table")
 
 

@@ -39,6 +39,14 @@ def test_fp32_check_mode_matches_oracle(monkeypatch, batch, h, w, selective):
     label = (torch.rand(batch, h, w, generator=g) < 0.4).float()
     ref_loss, ref = O.train_losses(sd, x, label, s_lamb=2, selective=selective)
     ref_loss.backward()
+    # the same oracle evaluated in float64: the yardstick for the gradient bound (two fp32 executions of this graph —
+    # oneDNN on the CPU and any GPU path — already differ by ~3e-3 on the deepest tensor's gradient)
+    sd64 = {k: (v.detach().double() if v.is_floating_point() else v.detach().clone()) for k, v in
+            O.init_state_dict(0, "RGB", selective).items()}
+    for n in names:
+        sd64[n].requires_grad_(True)
+    ref64_loss, ref64 = O.train_losses(sd64, x.double(), label.double(), s_lamb=2, selective=selective)
+    ref64_loss.backward()
     net.train()
     lab = label.cuda()
     if selective:
@@ -65,11 +73,13 @@ def test_fp32_check_mode_matches_oracle(monkeypatch, batch, h, w, selective):
         if n.endswith(".0.bias") and "layer" in n:       # conv bias feeding BatchNorm: true gradient is exactly 0
             assert gg.abs().max().item() <= 1e-6, n
             continue
-        c = _cos(gg, gr)
+        c, c32 = _cos(gg, sd64[n].grad), _cos(gg, gr)
         worst = min(worst, c)
-        assert c > 0.99999, (n, c)
-        assert abs(gg.norm().item() / gr.norm().item() - 1) < 1e-3, n
-    print("fp32 check mode: worst gradient cosine", worst)
+        assert c > 0.99999, (n, c)                       # vs the float64 evaluation of the reference graph
+        assert c32 > 0.9999, (n, c32)                    # vs its fp32 CPU execution (which carries its own rounding)
+        assert abs(gg.norm().item() / sd64[n].grad.norm().item() - 1) < 1e-3, n
+    assert _rel(out.detach().cpu(), ref64["output"].detach()) < 1e-4
+    print("fp32 check mode: worst gradient cosine vs the float64 oracle", worst)
     for k, v in net.named_buffers():                     # running statistics after the step
         if "num_batches" in k:
             assert int(v.item()) == 1
@@ -97,8 +107,11 @@ def test_fp32_check_mode_trainer_step_and_eval(monkeypatch):
         got = tr.step(x.cuda(), label.cuda())[3].item()
         assert abs(got - ref_loss.item()) < 2e-4 * abs(ref_loss.item()), (got, ref_loss.item())
     params = dict(net.named_parameters())
+    # three Adam steps: early Adam moves every weight by ~lr * sign(g), so an element whose gradient is at rounding level
+    # may step the other way; compare the update DIRECTION of whole tensors
+    sd0 = O.init_state_dict(2, "RGB", True)
     for n in ("decoder_layer_4_1.0.weight", "encoder_layer_1_1.0.weight", "unpool2.weight", "conv_select.weight"):
-        assert _rel(params[n].detach().cpu(), sd[n].detach()) < 2e-3, n      # three Adam steps (sign-like updates)
+        assert _cos(params[n].detach().cpu() - sd0[n], sd[n].detach() - sd0[n]) > 0.999, n
     net.eval()
     with torch.no_grad():
         out, sel, aux = net(x.cuda())
