@@ -183,80 +183,75 @@ struct HeadBN {
   int adds;                      // its pixel stride (may alias dA: each element is read and then written by one thread)
 };
 
-// shared-memory load the compiler may not hoist out of the pixel loop (it would turn back into 48 registers)
-__device__ __forceinline__ float2 lds_f32x2(const float* p) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
-  return v;
-}
-
+// Thread mapping: 16 lanes per pixel, 4 channels per lane (one 8-byte load), 16 pixels per block and trip, U trips in
+// flight.  With 4 channels per lane the 24 per-channel constants (3 head weights, scale, shift, mean) and the 23
+// accumulators fit in registers.  The first version used 8 lanes x 8 channels and re-read the constants from shared
+// memory for every pixel because 48 constants + 43 accumulators did not fit: 24 broadcast loads per lane and pixel put it
+// on the shared-memory port (ncu, profiles/r02/ncu_full_small_kernels.md: LSU wavefronts 82-83 % of peak, DRAM 31 %,
+// 0.85-0.89 ms for 2.25 GB), and wider loads do not help — a broadcast only merges lanes of one 128-byte wavefront.
 template <bool BN>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
                  __nv_bfloat16* __restrict__ dA, int das, float* __restrict__ partials, long long P, HeadBN bn) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float red[256][28];
-  // per-channel constants live in shared memory and are re-read per pixel (six 16-byte broadcast loads): keeping
-  // 48 of them in registers next to the 40 accumulators left room for only two pixels in flight per thread
-  __shared__ __align__(16) float s_w[3][64];
-  __shared__ __align__(16) float s_bn[3][64];      // scale, shift, mean
-  const int sub = threadIdx.x & 7;
-  if (threadIdx.x < 192) {
-    const int h = threadIdx.x >> 6, c = threadIdx.x & 63;
-    s_w[h][c] = (h < nheads) ? __ldg(hw.w[h] + c) : 0.f;
-    if (BN) s_bn[h][c] = __ldg((h == 0 ? bn.scale : (h == 1 ? bn.shift : bn.mean)) + c);
+  __shared__ float red[256][16];
+  const int sub = threadIdx.x & 15;           // channels [4*sub, 4*sub + 4)
+  const int pslot = threadIdx.x >> 4;         // pixel slot of this thread within a 16-pixel trip
+  float w[3][4], sc[4], sh[4], mu[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int h = 0; h < 3; ++h) w[h][j] = (h < nheads) ? __ldg(hw.w[h] + sub * 4 + j) : 0.f;
+    sc[j] = BN ? __ldg(bn.scale + sub * 4 + j) : 0.f;
+    sh[j] = BN ? __ldg(bn.shift + sub * 4 + j) : 0.f;
+    mu[j] = BN ? __ldg(bn.mean + sub * 4 + j) : 0.f;
   }
-  __syncthreads();
-  float sg[8], sgy[8];
-  float dw[3][8];
+  float sg[4], sgy[4], dw[3][4];
   float db[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sg[j] = sgy[j] = 0.f;
+  for (int j = 0; j < 4; ++j) {
+    sg[j] = sgy[j] = 0.f;
 #pragma unroll
-  for (int h = 0; h < 3; ++h)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dw[h][j] = 0.f;
+    for (int h = 0; h < 3; ++h) dw[h][j] = 0.f;
+  }
   // U pixels per thread per trip: all loads are issued before any is consumed
-  constexpr int U = 4;
-  const long long ppb = (long long)(blockDim.x >> 3);                 // pixels per block per sub-trip
-  for (long long p0 = blockIdx.x * ppb * U + (threadIdx.x >> 3); p0 < P; p0 += (long long)gridDim.x * ppb * U) {
+  constexpr int U = 2;
+  constexpr long long ppb = 16;                                       // pixels per block per sub-trip
+  for (long long p0 = blockIdx.x * ppb * U + pslot; p0 < P; p0 += (long long)gridDim.x * ppb * U) {
     float g[U][3];
-    bf16x8 v[U];
+    uint2 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long p = p0 + u * ppb;
       if (p < P) {
 #pragma unroll
         for (int h = 0; h < 3; ++h) g[u][h] = (h < nheads) ? __ldg(dl + (long long)h * P + p) : 0.f;
-        v[u] = *reinterpret_cast<const bf16x8*>(a + p * as + sub * 8);
+        v[u] = *reinterpret_cast<const uint2*>(a + p * as + sub * 4);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long p = p0 + u * ppb;
       if (p < P) {
-        bf16x8 ov;
+        uint32_t ow[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {           // channel pair i of this thread's 8 channels
-          const int c = sub * 8 + 2 * i;
-          const float2 w0 = lds_f32x2(&s_w[0][c]);
-          const float2 w1 = lds_f32x2(&s_w[1][c]);
-          const float2 w2 = lds_f32x2(&s_w[2][c]);
-          float a0 = bf16lo(v[u].w[i]), a1 = bf16hi(v[u].w[i]);
+        for (int i = 0; i < 2; ++i) {           // channel pair i of this thread's 4 channels
+          const int c = sub * 4 + 2 * i;
+          const uint32_t vw = i ? v[u].y : v[u].x;
+          float a0 = bf16lo(vw), a1 = bf16hi(vw);
           float y0 = 0.f, y1 = 0.f;
           if (BN) {
-            const float2 sc = lds_f32x2(&s_bn[0][c]);
-            const float2 sh = lds_f32x2(&s_bn[1][c]);
             y0 = a0;
             y1 = a1;
             // the activation bn_relu_heads fed to the heads: relu(bn(y)) rounded to bf16
-            const uint32_t r = pack_bf16x2(fmaxf(fmaf(y0, sc.x, sh.x), 0.f), fmaxf(fmaf(y1, sc.y, sh.y), 0.f));
+            const uint32_t r = pack_bf16x2(fmaxf(fmaf(y0, sc[2 * i], sh[2 * i]), 0.f),
+                                           fmaxf(fmaf(y1, sc[2 * i + 1], sh[2 * i + 1]), 0.f));
             a0 = bf16lo(r);
             a1 = bf16hi(r);
           }
-          float o0 = g[u][0] * w0.x + g[u][1] * w1.x + g[u][2] * w2.x;
-          float o1 = g[u][0] * w0.y + g[u][1] * w1.y + g[u][2] * w2.y;
+          float o0 = g[u][0] * w[0][2 * i] + g[u][1] * w[1][2 * i] + g[u][2] * w[2][2 * i];
+          float o1 = g[u][0] * w[0][2 * i + 1] + g[u][1] * w[1][2 * i + 1] + g[u][2] * w[2][2 * i + 1];
           if (BN && bn.addend != nullptr) {     // more than three heads (UNet, n_cls = 2): second call adds the first
             const uint32_t aw = *reinterpret_cast<const uint32_t*>(bn.addend + p * bn.adds + c);
             o0 += bf16lo(aw);
@@ -267,18 +262,17 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
             dw[h][2 * i] = fmaf(g[u][h], a0, dw[h][2 * i]);
             dw[h][2 * i + 1] = fmaf(g[u][h], a1, dw[h][2 * i + 1]);
           }
-          ov.w[i] = pack_bf16x2(o0, o1);
+          ow[i] = pack_bf16x2(o0, o1);
           if (BN) {
-            const float2 mu = lds_f32x2(&s_bn[2][c]);
-            const float g0 = a0 > 0.f ? bf16lo(ov.w[i]) : 0.f;
-            const float g1 = a1 > 0.f ? bf16hi(ov.w[i]) : 0.f;
+            const float g0 = a0 > 0.f ? bf16lo(ow[i]) : 0.f;
+            const float g1 = a1 > 0.f ? bf16hi(ow[i]) : 0.f;
             sg[2 * i] += g0;
             sg[2 * i + 1] += g1;
-            sgy[2 * i] = fmaf(g0, y0 - mu.x, sgy[2 * i]);
-            sgy[2 * i + 1] = fmaf(g1, y1 - mu.y, sgy[2 * i + 1]);
+            sgy[2 * i] = fmaf(g0, y0 - mu[2 * i], sgy[2 * i]);
+            sgy[2 * i + 1] = fmaf(g1, y1 - mu[2 * i + 1], sgy[2 * i + 1]);
           }
         }
-        *reinterpret_cast<bf16x8*>(dA + p * das + sub * 8) = ov;
+        *reinterpret_cast<uint2*>(dA + p * das + sub * 4) = make_uint2(ow[0], ow[1]);
         if (sub == 0) {
 #pragma unroll
           for (int h = 0; h < 3; ++h) db[h] += g[u][h];
@@ -286,11 +280,12 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
       }
     }
   }
+  // block reduction over the 16 pixel slots (fixed order): red[t][h*4 + j] = dw, red[t][12 + h] = db
 #pragma unroll
   for (int h = 0; h < 3; ++h) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[threadIdx.x][h * 8 + j] = dw[h][j];
-    red[threadIdx.x][24 + h] = db[h];
+    for (int j = 0; j < 4; ++j) red[threadIdx.x][h * 4 + j] = dw[h][j];
+    red[threadIdx.x][12 + h] = db[h];
   }
   __syncthreads();
   // partial row layout per block: [3][65] = 64 weight grads + bias grad
@@ -298,26 +293,26 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
     const int h = o / 65, c = o % 65;
     float s = 0.f;
     if (c < 64) {
-      const int sb = c >> 3, j = c & 7;
-      for (int r = 0; r < 32; ++r) s += red[r * 8 + sb][h * 8 + j];
+      const int sb = c >> 2, j = c & 3;
+      for (int r = 0; r < 16; ++r) s += red[r * 16 + sb][h * 4 + j];
     } else {
-      for (int r = 0; r < 32; ++r) s += red[r * 8][24 + h];
+      for (int r = 0; r < 16; ++r) s += red[r * 16][12 + h];
     }
     partials[(size_t)blockIdx.x * 195 + o] = s;
   }
   if (BN) {
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       red[threadIdx.x][j] = sg[j];
-      red[threadIdx.x][8 + j] = sgy[j];
+      red[threadIdx.x][4 + j] = sgy[j];
     }
     __syncthreads();
     if (threadIdx.x < 128) {
       const int c = threadIdx.x >> 1, which = threadIdx.x & 1;       // channel, (sum g | sum g*(y-mean))
-      const int sb = c >> 3, j = c & 7;
+      const int sb = c >> 2, j = c & 3;
       float s = 0.f;
-      for (int r = 0; r < 32; ++r) s += red[r * 8 + sb][which * 8 + j];
+      for (int r = 0; r < 16; ++r) s += red[r * 16 + sb][which * 4 + j];
       if (which) s *= __ldg(bn.invstd + c);
       bn.partials[((size_t)blockIdx.x * 64 + c) * 2 + which] = s;
     }
@@ -710,7 +705,7 @@ extern "C" int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float*
 
 static int heads_bwd_blocks(long long pixels, bool bn) {
   (void)bn;
-  return grid_for(pixels * 8, 256, 4);
+  return grid_for(pixels * 16, 256, 3);      // 16 lanes per pixel; 3 resident blocks per SM (80 registers)
 }
 
 extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,

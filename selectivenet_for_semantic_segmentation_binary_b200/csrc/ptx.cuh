@@ -191,6 +191,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A-operand collector reuse (SASS: UTCHMMA ... .A_KEEP / .A_REUSE): consecutive MMAs of one thread that share the SAME
+// A descriptor can keep A in the tensor core's collector buffer instead of re-reading it from shared memory.
+//   COL = 0: default (discard)   1: fill (read A, keep it)   2: use (A from the collector, keep it)   3: lastuse
+template <int COL, bool PAIR>
+__device__ __forceinline__ void umma_bf16_col(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+#define SUNET_UMMA(CG, Q)                                                                         \
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"                                       \
+               "tcgen05.mma.cta_group::" CG ".kind::f16" Q " [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), \
+               "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)                               \
+               : "memory")
+  if (PAIR) {
+    if (COL == 1) SUNET_UMMA("2", ".collector::a::fill");
+    else if (COL == 2) SUNET_UMMA("2", ".collector::a::use");
+    else if (COL == 3) SUNET_UMMA("2", ".collector::a::lastuse");
+    else SUNET_UMMA("2", "");
+  } else {
+    if (COL == 1) SUNET_UMMA("1", ".collector::a::fill");
+    else if (COL == 2) SUNET_UMMA("1", ".collector::a::use");
+    else if (COL == 3) SUNET_UMMA("1", ".collector::a::lastuse");
+    else SUNET_UMMA("1", "");
+  }
+#undef SUNET_UMMA
+}
 // Arrive on `bar` once every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

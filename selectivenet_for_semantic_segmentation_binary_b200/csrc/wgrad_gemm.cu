@@ -48,6 +48,7 @@ struct WgradParams {
   int bboxes;      // B boxes per stage
   int stages;
   int kp;          // pixels per stage
+  int a_reuse;     // keep A in the tensor core's collector across the taps of a K step (SUNET_WGRAD_A_REUSE, default 1)
   int abox;        // bytes of one A box = kp * 128
   float* out;      // [splits][taps_total][Ca][Nb]
 };
@@ -56,32 +57,47 @@ constexpr int MAX_STAGES = 12;
 // MMA issue for one pipeline stage, taps unrolled at compile time.  The generic (runtime T) loop spent ~25 SASS
 // instructions of the single issuing thread per UTCHMMA — more than the 64 tensor-core cycles an N=128 MMA takes,
 // which capped these kernels at ~67 % tensor-pipe utilisation (profiles/r01/ncu_full_r01g.md).
-template <int T, bool PAIR>
-__device__ __forceinline__ void wg_issue_stage(uint32_t tmem_base, uint32_t bnw, uint64_t adesc, uint64_t bdesc,
-                                               uint32_t tstep16, uint32_t idesc, int nkk, uint32_t acc_first) {
+// The T taps of one K step multiply the SAME A tile (dY, or the ConvT input) with shifted B windows: the first MMA
+// fills the tensor core's A collector, the others reuse it (UTCHMMA .A_KEEP / .A_REUSE), so A crosses the shared-memory
+// port once per K step instead of T times — these kernels sit on that port (profiles/r01/ncu_full_r01g.md:
+// smem->tensor wavefronts 64-69 % with the tensor pipe at 33-58 %).  REUSE = false restores the plain form (A/B timing).
+template <int T, bool PAIR, bool REUSE>
+__device__ __forceinline__ void wg_issue_taps(uint32_t tmem_base, uint32_t bnw, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t tstep16, uint32_t idesc, uint32_t acc) {
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    if (PAIR) umma_bf16_pair(tmem_base + t * bnw, adesc, bdesc + t * tstep16, idesc, acc_first);
-    else umma_bf16(tmem_base + t * bnw, adesc, bdesc + t * tstep16, idesc, acc_first);
+    const uint32_t d = tmem_base + t * bnw;
+    const uint64_t b = bdesc + t * tstep16;
+    if (!REUSE || T == 1) umma_bf16_col<0, PAIR>(d, adesc, b, idesc, acc);
+    else if (t == 0) umma_bf16_col<1, PAIR>(d, adesc, b, idesc, acc);
+    else if (t == T - 1) umma_bf16_col<3, PAIR>(d, adesc, b, idesc, acc);
+    else umma_bf16_col<2, PAIR>(d, adesc, b, idesc, acc);
   }
+}
+template <int T, bool PAIR, bool REUSE>
+__device__ __forceinline__ void wg_issue_stage(uint32_t tmem_base, uint32_t bnw, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t tstep16, uint32_t idesc, int nkk, uint32_t acc_first) {
+  wg_issue_taps<T, PAIR, REUSE>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, acc_first);
 #pragma unroll 1
   for (int kk = 1; kk < nkk; ++kk) {
     adesc += 2048 >> 4;               // next 16 pixels (16 rows of 128 B)
     bdesc += 2048 >> 4;
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      if (PAIR) umma_bf16_pair(tmem_base + t * bnw, adesc, bdesc + t * tstep16, idesc, 1u);
-      else umma_bf16(tmem_base + t * bnw, adesc, bdesc + t * tstep16, idesc, 1u);
-    }
+    wg_issue_taps<T, PAIR, REUSE>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, 1u);
   }
 }
 template <bool PAIR>
-__device__ __forceinline__ void wg_issue_stage_T(int T, uint32_t tmem_base, uint32_t bnw, uint64_t adesc,
+__device__ __forceinline__ void wg_issue_stage_T(int T, bool reuse, uint32_t tmem_base, uint32_t bnw, uint64_t adesc,
                                                  uint64_t bdesc, uint32_t tstep16, uint32_t idesc, int nkk,
                                                  uint32_t acc_first) {
-  if (T == 3) wg_issue_stage<3, PAIR>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
-  else if (T == 4) wg_issue_stage<4, PAIR>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
-  else wg_issue_stage<1, PAIR>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+  if (reuse) {
+    if (T == 3) wg_issue_stage<3, PAIR, true>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+    else if (T == 4) wg_issue_stage<4, PAIR, true>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+    else wg_issue_stage<1, PAIR, false>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+  } else {
+    if (T == 3) wg_issue_stage<3, PAIR, false>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+    else if (T == 4) wg_issue_stage<4, PAIR, false>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+    else wg_issue_stage<1, PAIR, false>(tmem_base, bnw, adesc, bdesc, tstep16, idesc, nkk, acc_first);
+  }
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -201,8 +217,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           bdesc0 |= static_cast<uint64_t>(p.dbg_boff & 7) << 49;                  // experiment hook, 0 in production
           // taps: shifted windows of one box (or consecutive box groups), tstep bytes apart
           if (nkk > 0)
-            wg_issue_stage_T<false>(p.T, tmem_base, (uint32_t)BNW, adesc, bdesc0, tstep >> 4, idesc, nkk,
-                                    kb > kb0 ? 1u : 0u);
+            wg_issue_stage_T<false>(p.T, p.a_reuse != 0, tmem_base, (uint32_t)BNW, adesc, bdesc0, tstep >> 4, idesc,
+                                    nkk, kb > kb0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -347,7 +363,7 @@ wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         if (elect_one()) {
           uint64_t adesc = make_smem_desc_sw128(sa, p.abox, 1024);
           uint64_t bdesc0 = make_smem_desc_sw128(sb, p.bslot, 1024);
-          wg_issue_stage_T<true>(p.T, tmem_base, (uint32_t)BNW, adesc, bdesc0, tstep >> 4, idesc, nkk,
+          wg_issue_stage_T<true>(p.T, p.a_reuse != 0, tmem_base, (uint32_t)BNW, adesc, bdesc0, tstep >> 4, idesc, nkk,
                                  kb > kb0 ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage]);
         }
@@ -732,6 +748,10 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     const char* b = getenv("SUNET_DBG_BOFF");
     p.dbg_shift = s ? atoi(s) : 0;
     p.dbg_boff = b ? atoi(b) : 0;
+  }
+  {
+    const char* r = getenv("SUNET_WGRAD_A_REUSE");
+    p.a_reuse = r ? atoi(r) : 1;
   }
   p.tmem_cols = 32;
   while (p.tmem_cols < w.T * w.BNW) p.tmem_cols *= 2;
