@@ -45,6 +45,11 @@ struct Halo2Params {
 // nothing: 0.550 vs 0.548 ms for 128 x 256^2 x 64->64, 33.06 vs 33.18 ms per step (profiles/r02/halo_stages_ab.log) —
 // the N = 64 kernel is bound by the shared-memory port (operand reads 65 % + epilogue 27 % of its wavefronts), not
 // by the latency of the halo load.  Two stages stay the default.
+// Also measured and rejected (profiles/r02/epilogue_groups_ab.log): EIGHT epilogue warps in two groups that take the
+// 64-channel output chunks alternately (own staging tile, y pipeline, store thread and named barrier each).  Parity
+// green, but 0.713 vs 0.736 ms for the level-1 BNB dgrad, 0.479 vs 0.463 at level 2, 0.403 vs 0.381 at level 3 and
+// 32.65 vs 32.52 ms per step: the cost of the BNB epilogue is its extra traffic through the shared-memory port
+// (y tile in, statistics loop out), not the latency of four warps — more warps only contend harder.
 template <int BN, bool BNB = false, int AST = 2>
 struct H2Cfg {
   static constexpr int TILES = (BN == 256) ? 1 : 2;

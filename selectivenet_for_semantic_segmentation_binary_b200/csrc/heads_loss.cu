@@ -189,8 +189,10 @@ struct HeadBN {
 // memory for every pixel because 48 constants + 43 accumulators did not fit: 24 broadcast loads per lane and pixel put it
 // on the shared-memory port (ncu, profiles/r02/ncu_full_small_kernels.md: LSU wavefronts 82-83 % of peak, DRAM 31 %,
 // 0.85-0.89 ms for 2.25 GB), and wider loads do not help — a broadcast only merges lanes of one 128-byte wavefront.
+// Now 0.75 ms, LSU wavefronts 4 %, issue slots 59 % busy at 16 resident warps; 2 pixels in flight with 24 resident warps
+// (80 registers, small spills) measured slower (0.98 ms).
 template <bool BN>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int as, HeadW hw, int nheads,
                  __nv_bfloat16* __restrict__ dA, int das, float* __restrict__ partials, long long P, HeadBN bn) {
   pdl_wait();
@@ -216,7 +218,7 @@ heads_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__
     for (int h = 0; h < 3; ++h) dw[h][j] = 0.f;
   }
   // U pixels per thread per trip: all loads are issued before any is consumed
-  constexpr int U = 2;
+  constexpr int U = 4;
   constexpr long long ppb = 16;                                       // pixels per block per sub-trip
   for (long long p0 = blockIdx.x * ppb * U + pslot; p0 < P; p0 += (long long)gridDim.x * ppb * U) {
     float g[U][3];
@@ -705,7 +707,7 @@ extern "C" int sunet_bn_relu_heads(const void* y, int y_pix_stride, const float*
 
 static int heads_bwd_blocks(long long pixels, bool bn) {
   (void)bn;
-  return grid_for(pixels * 16, 256, 3);      // 16 lanes per pixel; 3 resident blocks per SM (80 registers)
+  return grid_for(pixels * 16, 256, 2);      // 16 lanes per pixel; 2 resident blocks per SM (128 registers)
 }
 
 extern "C" int sunet_heads_bwd(const float* dlogits, const void* a, int a_pix_stride, const float* w0, const float* w1,
