@@ -16,6 +16,11 @@ build/%.o: $(PKG)/csrc/%.cu $(HDR)
 $(LIB): $(OBJ)
 	$(NVCC) -shared -o $@ $(OBJ) -cudart static
 
+# development probes (MMA-rate microbenchmark): NOT part of the product library
+probes: scripts/probes/libsunet_probe.so
+scripts/probes/libsunet_probe.so: scripts/probes/mma_probe.cu $(PKG)/csrc/common.cu $(HDR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ scripts/probes/mma_probe.cu $(PKG)/csrc/common.cu -cudart static
+
 clean:
-	rm -rf build $(LIB)
-.PHONY: all clean
+	rm -rf build $(LIB) scripts/probes/libsunet_probe.so
+.PHONY: all clean probes

@@ -671,11 +671,29 @@ def run_ours(args):
         line["kernel_sha"] = kernel_source_sha()
         print(json.dumps(line), flush=True)
     if world > 1:
-        # CUDA graphs that captured NCCL collectives keep the communicator busy: destroy_process_group()
-        # was observed to hang after such a run.  Everything is flushed and synchronised, so leave directly.
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        sys.stdout.flush()
+        leave_process_group(torch, dist, dev, [tr, net])
+
+
+def leave_process_group(torch, dist, dev, holders):
+    """Drop every CUDA graph that captured NCCL collectives, then destroy the process group.  With the graphs still
+    alive destroy_process_group() was observed to hang (round 1 left with os._exit); it gets 20 s on a helper thread
+    and the hard exit remains only as the fallback, reported on stderr."""
+    import gc
+    for h in holders:
+        if hasattr(h, "_graphs"):
+            h._graphs.clear()
+        if hasattr(h, "_plans"):
+            h._plans.clear()
+    gc.collect()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20.0)
+    if t.is_alive():
+        sys.stderr.write("bench.py: destroy_process_group() did not return within 20 s; leaving with os._exit(0)\n")
         sys.stderr.flush()
         os._exit(0)
 

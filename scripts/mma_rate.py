@@ -6,7 +6,9 @@ import torch
 from selectivenet_for_semantic_segmentation_binary_b200 import _lib
 
 lib = _lib.load()
-raw = C.CDLL(_lib.LIB_PATH)
+# the probe kernels are a development tool and live outside the product library:
+#   make probes   ->  scripts/probes/libsunet_probe.so
+raw = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "probes", "libsunet_probe.so"))
 raw.sunet_dbg_mma_probe.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
 grid = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 iters = 4000

@@ -2,8 +2,8 @@
 // shared-memory-resident operands, for each combination of K-major / MN-major A and B.  No TMA, no
 // epilogue: it isolates "tensor pipe + shared-memory operand fetch".  Used by scripts/mma_rate.py to
 // decide operand layouts.
-#include "common.h"
-#include "ptx.cuh"
+#include "../../selectivenet_for_semantic_segmentation_binary_b200/csrc/common.h"
+#include "../../selectivenet_for_semantic_segmentation_binary_b200/csrc/ptx.cuh"
 
 namespace sunet {
 

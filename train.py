@@ -312,11 +312,8 @@ def train_worker(rank, world, args, ckpt_dir, log_dir):
                           % (va[2], va[0], (c_va[5] - c_va[4]) / max(c_va[5], 1)))
             net_save(ckpt_dir=ckpt_dir, net=net, optim=optim, epoch=epoch)
     if world > 1:
-        # graphs that captured NCCL collectives make destroy_process_group() hang: synchronise and leave
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        sys.stdout.flush()
-        os._exit(0)
+        from bench import leave_process_group      # graphs that captured NCCL collectives go first (bench.py)
+        leave_process_group(torch, dist, dev, [h for h in (trainer, net) if h is not None])
 
 
 def train(args, ckpt_dir, log_dir=None):
