@@ -369,7 +369,20 @@ class SUNetPlan:
                 training: bool) -> torch.Tensor:
         """x: fp32 NCHW on this plan's device, or None when the caller has already filled ``self.col`` (the uint8
         input pipeline, kernels.pack_input_u8_im2col32).  Returns the plan-owned logits buffer [nheads, P]."""
-        self.pack_weights(params)
+        # the weight repack (one launch, ~70 us) does not depend on the input: it runs on the side stream beside the
+        # input im2col and is joined before the first conv (inside a captured graph this is a fork / join)
+        cur = torch.cuda.current_stream()
+        overlap_pack = self.overlap_wgrad and x is not None
+        if overlap_pack:
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            self.side.wait_event(fork)
+            with torch.cuda.stream(self.side):
+                self.pack_weights(params)
+                packed = torch.cuda.Event()
+                packed.record(self.side)
+        else:
+            self.pack_weights(params)
         if x is None:
             if not self.first_pair:
                 raise RuntimeError("the uint8 input pipeline needs the paired-pixel first layer (SUNET_FIRST_PAIR=1)")
@@ -379,6 +392,8 @@ class SUNetPlan:
                 K.pack_input_im2col32(x, self.col)
             else:
                 K.pack_input_im2col(x, self.col)
+        if overlap_pack:
+            cur.wait_event(packed)
         L = self.layers
         for name in ("encoder_layer_1_1", "encoder_layer_1_2", "encoder_layer_2_1", "encoder_layer_2_2",
                      "encoder_layer_3_1", "encoder_layer_3_2", "decoder_layer_4_2", "decoder_layer_4_1"):
