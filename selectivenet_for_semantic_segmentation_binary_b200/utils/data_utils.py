@@ -16,37 +16,35 @@ import numpy as np
 import torch
 
 
-def split_train_valid(TRAIN_list, valid_ratio=0.2, rng=None):
-    """data_utils.py:49-53; `rng` is the stream np.random.seed(42) started at import time in the reference."""
+def _fold_rows(data_dir, folds, kind):
+    """All (input_file, label_file) rows of `kind` ('tumorable' | 'non_tumorable') over the given folds, in fold order."""
+    return np.concatenate([np.load(os.path.join(data_dir, f'{k}-fold_{kind}_data.npy'), allow_pickle=True)
+                           for k in folds])
+
+
+def split_train_valid(rows, valid_ratio=0.2, rng=None):
+    """Hold out int(n * valid_ratio) rows drawn without replacement (data_utils.py:49-53); the kept rows stay in their
+    original order.  `rng` is the stream that np.random.seed(42) starts at import time in the reference."""
     rng = np.random if rng is None else rng
-    total_n = len(TRAIN_list)
-    valid_idx = rng.choice(total_n, size=int(total_n * valid_ratio), replace=False)
-    train_idx = np.setdiff1d([i for i in range(total_n)], valid_idx)
-    return TRAIN_list[train_idx], TRAIN_list[valid_idx]
+    n = len(rows)
+    held_out = rng.choice(n, size=int(n * valid_ratio), replace=False)
+    keep = np.ones(n, dtype=bool)
+    keep[held_out] = False
+    return rows[keep], rows[held_out]
 
 
 def construct_train_valid(data_dir, test_fold=5):
-    """data_utils.py:55-76: all folds except `test_fold`, tumorable and non-tumorable lists split 80/20 separately
-    (tumorable first — the order fixes the random stream), then stacked."""
-    folds = [1, 2, 3, 4, 5]
-    folds.remove(test_fold)
-    tumorable, non_tumorable = [], []
-    for i in folds:
-        tumorable.append(np.load(f'{data_dir}/{i}-fold_tumorable_data.npy', allow_pickle=True))
-        non_tumorable.append(np.load(f'{data_dir}/{i}-fold_non_tumorable_data.npy', allow_pickle=True))
-    tumorable = np.concatenate(tumorable)
-    non_tumorable = np.concatenate(non_tumorable)
+    """Train / valid lists of the four folds that are not `test_fold` (data_utils.py:55-76): the tumorable and the
+    non-tumorable rows are split 80/20 separately — tumorable first, which fixes the random stream — and stacked."""
+    folds = [k for k in (1, 2, 3, 4, 5) if k != test_fold]
     rng = np.random.RandomState(42)          # == the global stream right after the reference's np.random.seed(42)
-    t_train, t_valid = split_train_valid(tumorable, 0.2, rng)
-    n_train, n_valid = split_train_valid(non_tumorable, 0.2, rng)
-    return np.vstack([t_train, n_train]), np.vstack([t_valid, n_valid])
+    parts = [split_train_valid(_fold_rows(data_dir, folds, kind), 0.2, rng) for kind in ('tumorable', 'non_tumorable')]
+    return np.vstack([tr for tr, _ in parts]), np.vstack([va for _, va in parts])
 
 
 def construct_test(data_dir, test_fold=1):
-    """data_utils.py:78-90."""
-    tumorable = np.array(np.load(f'{data_dir}/{test_fold}-fold_tumorable_data.npy', allow_pickle=True))
-    non_tumorable = np.array(np.load(f'{data_dir}/{test_fold}-fold_non_tumorable_data.npy', allow_pickle=True))
-    return np.vstack([tumorable, non_tumorable])
+    """Test list = both row kinds of `test_fold`, tumorable first (data_utils.py:78-90)."""
+    return np.vstack([np.asarray(_fold_rows(data_dir, [test_fold], kind)) for kind in ('tumorable', 'non_tumorable')])
 
 
 class PatchArrays:

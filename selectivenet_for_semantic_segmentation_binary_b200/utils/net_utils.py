@@ -1,59 +1,53 @@
-"""Checkpoint helpers with the reference's names and file layout.
+"""Checkpoint helpers with the reference's names, signatures and file layout.
 
-Mirrors /root/reference/utils/net_utils.py:5-52: ``{'net': state_dict, 'optim': state_dict}``
-saved as ``model_epoch%d.pth``; loaders accept keys with or without DataParallel's ``module.``
-prefix.  The 110-key fp32 state_dict of ``UNet_B`` is the checkpoint contract.
+Contract (from /root/reference/utils/net_utils.py:5-52 and its callers train.py:357, eval.py:139-147): a checkpoint is
+``{'net': state_dict, 'optim': state_dict}`` written to ``<ckpt_dir>/model_epoch<N>.pth``; the newest file of a directory
+is the one with the largest number in its name; ``'net'`` keys may carry DataParallel's ``module.`` prefix.  The
+110-key fp32 state_dict of ``UNet_B`` is the model half of that contract; the optimizer half is
+``optim.Adam.state_dict()``, which has ``torch.optim.Adam``'s own layout.
 """
 import os
+import re
 from collections import OrderedDict
 
 import torch
 
+_FILE = 'model_epoch{}.pth'
+
 
 def net_save(ckpt_dir, net, optim, epoch):
-    if not os.path.exists(ckpt_dir):
-        os.makedirs(ckpt_dir)
-    torch.save({'net': net.state_dict(), 'optim': optim.state_dict()}, '%s/model_epoch%d.pth' % (ckpt_dir, epoch))
+    os.makedirs(ckpt_dir, exist_ok=True)
+    torch.save({'net': net.state_dict(), 'optim': optim.state_dict()}, os.path.join(ckpt_dir, _FILE.format(epoch)))
 
 
 def remove_module(ckpt):
-    net_state_dict = OrderedDict()
-    for k, v in ckpt['net'].items():
-        net_state_dict[k.replace("module.", "")] = v
-    return net_state_dict
+    """'net' state_dict of a checkpoint without the ``module.`` that nn.DataParallel adds to every key."""
+    return OrderedDict((key.replace('module.', ''), value) for key, value in ckpt['net'].items())
 
 
-def _latest(ckpt_dir):
-    ckpt_lst = os.listdir(ckpt_dir)
-    ckpt_lst.sort(key=lambda f: int(''.join(filter(str.isdigit, f))))
-    return ckpt_lst[-1]
+def _number_in(name):
+    return int(''.join(re.findall(r'\d', name)))
+
+
+def _read(path, device):
+    ckpt = torch.load(path, map_location=device) if device is not None else torch.load(path)
+    if isinstance(ckpt, dict) and isinstance(ckpt.get('net'), dict):
+        ckpt['net'] = remove_module(ckpt)
+    return ckpt
 
 
 def net_train_load(ckpt_dir, net, optim, device=None):
+    """Resume from the newest checkpoint of `ckpt_dir`: returns (net, optim, epoch); epoch 0 if there is none."""
     if not os.path.exists(ckpt_dir):
-        epoch = 0
-        return net, optim, epoch
-    last = _latest(ckpt_dir)
-    print('model: ', last)
-    ckpt = torch.load('%s/%s' % (ckpt_dir, last), map_location=device if device is not None else 'cpu')
-    try:
-        ckpt['net'] = remove_module(ckpt)
-    except Exception:
-        pass
+        return net, optim, 0
+    newest = max(os.listdir(ckpt_dir), key=_number_in)
+    print('model: ', newest)
+    ckpt = _read(os.path.join(ckpt_dir, newest), device if device is not None else 'cpu')
     net.load_state_dict(ckpt['net'])
     optim.load_state_dict(ckpt['optim'])
-    epoch = int(last.split('epoch')[1].split('.pth')[0])
-    return net, optim, epoch
+    return net, optim, int(newest.split('epoch')[1].split('.pth')[0])
 
 
 def net_test_load(model_path, net, device=None):
-    if device is not None:
-        ckpt = torch.load(model_path, map_location=device)
-    else:
-        ckpt = torch.load(model_path)
-    try:
-        ckpt['net'] = remove_module(ckpt)
-    except Exception:
-        pass
-    net.load_state_dict(ckpt['net'])
+    net.load_state_dict(_read(model_path, device)['net'])
     return net
