@@ -728,14 +728,14 @@ def tensor_core_roofline(tr, x, label, K, torch, steps):
         DESC[0] = f"mode{a_mode} grid{tuple(grid)} C{src0.shape[3]}{'+' + str(kw['src1'].shape[3]) if kw.get('src1') is not None else ''} N{n} K{k}"
         return timed("conv_gemm", 2.0 * m * n * k, orig_conv, a_mode, grid, src0, weights, dst, **kw)
 
-    def wgrad_gemm(grid, a, b_mode, b0, partials, b1=None):
+    def wgrad_gemm(grid, a, b_mode, b0, partials, b1=None, **kw):
         m = grid[0] * grid[1] * grid[2]
         taps = {K.A_CONV3X3: 9, K.A_PLAIN: 1, K.A_GATHER2X2: 4}[b_mode]
         nb = b0.shape[3] + (b1.shape[3] if b1 is not None else 0)
         if b_mode == K.A_PLAIN:
             nb = 27
         DESC[0] = f"mode{b_mode} grid{tuple(grid)} A{a.shape[3]} B{nb} taps{taps}"
-        return timed("wgrad_gemm", 2.0 * m * taps * a.shape[3] * nb, orig_wgrad, grid, a, b_mode, b0, partials, b1)
+        return timed("wgrad_gemm", 2.0 * m * taps * a.shape[3] * nb, orig_wgrad, grid, a, b_mode, b0, partials, b1, **kw)
 
     use_graph = tr.use_graph
     tr.use_graph = False

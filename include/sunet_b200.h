@@ -81,6 +81,14 @@ typedef struct sunet_conv_gemm_args {
   const float* ep_shift;
   int bnb_col0;                /* the reduction covers output columns [bnb_col0, n_total) (multiple of 64; y and the  */
                                /* bnb_* vectors then have n_total - bnb_col0 channels); lower columns keep (sum, sq)   */
+  /* Optional TRAINING prologue (CBR_2D forward, model.py:11-13 with BatchNorm in training mode): the source(s) flagged
+   * in pro_mask (bit 0: src0, bit 1: src1) hold the RAW conv output y of the producer block; every landed operand tile
+   * is transformed in place to relu(y * pro_scale[c] + pro_shift[c]) rounded to bf16 — bit-identical to what
+   * sunet_bn_relu_pool would have materialised — so that pass and the activation tensor disappear.  fp32 vectors over
+   * the concatenated input channels (src0 first).  Only where sunet_conv_gemm_pro_supported() != 0. */
+  const float* pro_scale;
+  const float* pro_shift;
+  int pro_mask;
 } sunet_conv_gemm_args;
 
 int sunet_conv_gemm(const sunet_conv_gemm_args* args, sunet_stream_t stream);
@@ -88,6 +96,8 @@ int sunet_conv_gemm(const sunet_conv_gemm_args* args, sunet_stream_t stream);
 int sunet_conv_gemm_stat_rows(const sunet_conv_gemm_args* args);
 /* 1 if the kernel variant this shape dispatches to implements the bnb_* epilogue, else 0 */
 int sunet_conv_gemm_bnb_supported(const sunet_conv_gemm_args* args);
+/* 1 if the kernel variant this shape dispatches to implements the pro_* prologue, else 0 */
+int sunet_conv_gemm_pro_supported(const sunet_conv_gemm_args* args);
 
 /* ------------------------------------------------------------------------------------------
  * G2: weight-gradient GEMM over pixels, split-K with fp32 partials.
@@ -105,10 +115,17 @@ typedef struct sunet_wgrad_gemm_args {
   int b1_channels, b1_pix_stride;
   float* partials;             /* fp32 [splits][taps][a_channels][b0+b1 channels]                  */
   size_t partials_bytes;
+  /* Optional training prologue on the B operand (the layer input): b0 holds the raw conv output y of the producer
+   * block and every landed tile is transformed to relu(y * b_pro_scale[c] + b_pro_shift[c]) (bf16) in place, as in
+   * sunet_conv_gemm's pro_*.  Only where sunet_wgrad_gemm_pro_supported() != 0 (conv3x3, one B source, >= 256 A
+   * channels: the CTA-pair kernel with the shifted-window B box). */
+  const float* b_pro_scale;
+  const float* b_pro_shift;
 } sunet_wgrad_gemm_args;
 
 int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* args, sunet_stream_t stream);
 int sunet_wgrad_gemm_splits(const sunet_wgrad_gemm_args* args); /* how many splits it will write */
+int sunet_wgrad_gemm_pro_supported(const sunet_wgrad_gemm_args* args);
 
 /* sum the split-K partials into the reference's parameter-gradient layout.
  *   layout 0: conv3x3  grad[co][ci][3][3]   from P[s][r*3+q][co][ci]

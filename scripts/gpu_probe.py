@@ -300,6 +300,84 @@ def g1_eval_epilogue(K):
     return ok
 
 
+def g1_prologue(K):
+    """Training prologue: conv(relu(scale*y + shift)) computed from the RAW y with the transform applied to the staged
+    halo tiles must be BIT-IDENTICAL (outputs and statistics rows) to the conv of the materialised activation."""
+    dev = "cuda"
+    ok = True
+    seen = 0
+    for (B, H, W, Cin, Cout, dual) in [(4, 64, 64, 256, 256, False), (2, 32, 32, 512, 512, False),
+                                       (3, 16, 16, 128, 64, False), (2, 64, 64, 64, 128, False),
+                                       (1, 16, 48, 256, 256, True), (5, 16, 16, 64, 64, False)]:
+        g = torch.Generator().manual_seed(B + Cin + Cout)
+        y = nhwc(torch.randn(B, Cin, H, W, generator=g).to(dev))
+        w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(dev)
+        scale = ((torch.rand(Cin, generator=g) + 0.5) * torch.where(torch.rand(Cin, generator=g) < 0.1, -1.0, 1.0)).to(dev)
+        shift = (torch.randn(Cin, generator=g) * 0.3).to(dev)
+        wf = torch.empty(Cout, 9 * Cin, dtype=torch.bfloat16, device=dev)
+        K.pack_conv3x3_weights(w, wf, None)
+        out_a = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
+        out_p = torch.full_like(out_a, float("nan"))
+        c0 = Cin // 2 if dual else Cin
+        y0 = y[..., :c0].contiguous()
+        s1 = y[..., c0:].contiguous() if dual else None          # second source: already an activation
+        if not K.conv_gemm_pro_supported(K.A_CONV3X3, (B, H, W), y0, wf, out_a, src1=s1):
+            print(f"  [skip]   prologue B{B} {H}x{W} {Cin}->{Cout}: not served by the halo kernel")
+            continue
+        seen += 1
+        a0 = torch.empty_like(y0)
+        K.bn_relu_pool(y0, scale[:c0].contiguous(), shift[:c0].contiguous(), a0)
+        rows = K.conv_gemm_stat_rows(B, H, W, Cout)
+        st_a = torch.zeros(rows, Cout, 2, device=dev)
+        st_p = torch.zeros(rows, Cout, 2, device=dev)
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), a0, wf, out_a, src1=s1, stats=st_a)
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), y0, wf, out_p, src1=s1, stats=st_p, pro=(scale, shift, 1))
+        torch.cuda.synchronize()
+        same = bool(torch.equal(out_a.view(torch.int16), out_p.view(torch.int16))) and bool(torch.equal(st_a, st_p))
+        print(f"  [{'OK ' if same else 'BAD'}]    prologue conv B{B} {H}x{W} {Cin}->{Cout}{' dual' if dual else ''} bit-identical"
+              f" (max diff {float((out_a.float() - out_p.float()).abs().max()):.3g})")
+        ok &= same
+        src = torch.cat([a0, s1], dim=3) if dual else a0
+        ref = F.conv2d(nchw(src), w.to(torch.bfloat16).float(), padding=1)
+        ok &= report(f"prologue conv vs torch B{B} {H}x{W} {Cin}->{Cout}", nchw(out_p), ref)
+    return ok and seen >= 4
+
+
+def g2_wgrad_prologue(K):
+    """Weight gradient with the B-operand prologue: partial slabs bit-identical to the materialised-activation launch."""
+    dev = "cuda"
+    ok = True
+    seen = 0
+    for (B, H, W, Cin, Cout) in [(4, 64, 64, 256, 256), (2, 64, 64, 128, 256), (1, 16, 64, 256, 512), (3, 8, 128, 128, 256)]:
+        g = torch.Generator().manual_seed(11 + B)
+        y = nhwc(torch.randn(B, Cin, H, W, generator=g).to(dev))
+        dyb = nhwc(torch.randn(B, Cout, H, W, generator=g).to(dev))
+        scale = ((torch.rand(Cin, generator=g) + 0.5) * torch.where(torch.rand(Cin, generator=g) < 0.1, -1.0, 1.0)).to(dev)
+        shift = (torch.randn(Cin, generator=g) * 0.3).to(dev)
+        if not K.wgrad_pro_supported((B, H, W), dyb, K.A_CONV3X3, y):
+            print(f"  [skip]   wgrad prologue B{B} {H}x{W} {Cin}->{Cout}: not served by the CTA-pair shifted-window kernel")
+            continue
+        seen += 1
+        a = torch.empty_like(y)
+        K.bn_relu_pool(y, scale, shift, a)
+        splits = K.wgrad_splits((B, H, W), dyb, K.A_CONV3X3, a)
+        part_a = torch.full((splits, 9, Cout, Cin), float("nan"), device=dev)
+        part_p = torch.full_like(part_a, float("nan"))
+        K.wgrad_gemm((B, H, W), dyb, K.A_CONV3X3, a, part_a)
+        K.wgrad_gemm((B, H, W), dyb, K.A_CONV3X3, y, part_p, b_pro=(scale, shift))
+        torch.cuda.synchronize()
+        same = bool(torch.equal(part_a.view(torch.int32), part_p.view(torch.int32)))
+        print(f"  [{'OK ' if same else 'BAD'}]    wgrad prologue B{B} {H}x{W} {Cin}->{Cout} splits={splits} bit-identical"
+              f" (max diff {float((part_a - part_p).abs().max()):.3g})")
+        ok &= same
+        grad = torch.empty(Cout, Cin, 3, 3, device=dev)
+        K.wgrad_reduce(part_p, splits, 9, Cout, Cin, 0, grad)
+        wref = torch.zeros(Cout, Cin, 3, 3, device=dev, requires_grad=True)
+        F.conv2d(nchw(a), wref, padding=1).backward(nchw(dyb))
+        ok &= report(f"wgrad prologue vs torch B{B} {H}x{W} {Cin}->{Cout}", grad, wref.grad, 1e-2)
+    return ok and seen >= 2
+
+
 def g1_big(K):
     # many tiles per CTA: exercises the persistent schedule, phase wrap-around, TMEM double buffering
     ok = conv3x3_case(K, 8, 128, 128, 64, 64)
@@ -673,7 +751,7 @@ def swizzle_exp(K):
 
 
 GROUPS = {"swizzle_exp": swizzle_exp, "g1_plain": g1_plain, "g1_conv": g1_conv, "g1_convT": g1_convT, "g1_big": g1_big, "g1_eval_epilogue": g1_eval_epilogue, "g1_bnb": g1_bnb, "g1_bnb_convT": g1_bnb_convT, "g1_bnb_pool": g1_bnb_pool, "g2_wgrad": g2_wgrad,
-          "ew_bn": ew_bn, "ew_heads_loss": ew_heads_loss}
+          "g1_prologue": g1_prologue, "g2_wgrad_prologue": g2_wgrad_prologue, "ew_bn": ew_bn, "ew_heads_loss": ew_heads_loss}
 
 
 def main():

@@ -35,6 +35,7 @@ class ConvGemmArgs(C.Structure):
         ("bnb_scale", C.c_void_p), ("bnb_shift", C.c_void_p), ("bnb_mean", C.c_void_p), ("bnb_invstd", C.c_void_p),
         ("ep_scale", C.c_void_p), ("ep_shift", C.c_void_p),
         ("bnb_col0", C.c_int),
+        ("pro_scale", C.c_void_p), ("pro_shift", C.c_void_p), ("pro_mask", C.c_int),
     ]
 
 
@@ -46,6 +47,7 @@ class WgradGemmArgs(C.Structure):
         ("b0", C.c_void_p), ("b0_channels", C.c_int), ("b0_pix_stride", C.c_int),
         ("b1", C.c_void_p), ("b1_channels", C.c_int), ("b1_pix_stride", C.c_int),
         ("partials", C.c_void_p), ("partials_bytes", C.c_size_t),
+        ("b_pro_scale", C.c_void_p), ("b_pro_shift", C.c_void_p),
     ]
 
 
@@ -74,6 +76,8 @@ SIGNATURES = {
     "sunet_conv_gemm":[C.POINTER(ConvGemmArgs), _vp],
     "sunet_conv_gemm_stat_rows": [C.POINTER(ConvGemmArgs)],
     "sunet_conv_gemm_bnb_supported": [C.POINTER(ConvGemmArgs)],
+    "sunet_conv_gemm_pro_supported": [C.POINTER(ConvGemmArgs)],
+    "sunet_wgrad_gemm_pro_supported": [C.POINTER(WgradGemmArgs)],
     "sunet_wgrad_gemm": [C.POINTER(WgradGemmArgs), _vp],
     "sunet_wgrad_gemm_splits": [C.POINTER(WgradGemmArgs)],
     "sunet_wgrad_reduce": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],

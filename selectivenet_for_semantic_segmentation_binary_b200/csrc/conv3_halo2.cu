@@ -34,34 +34,44 @@ struct Halo2Params {
   const float* ep_scale;     // inference epilogue: dst = relu(acc * ep_scale[n] + ep_shift[n]) (nullptr = off)
   const float* ep_shift;
   int bnb_col0;              // BNB covers output columns [bnb_col0, n_total); lower columns get (sum, sum sq)
+  // PRO (training prologue): the source tensor holds the RAW conv output y of the producer block; every landed halo
+  // tile is transformed in place to relu(y * pro_scale[c] + pro_shift[c]) (bf16) before the MMAs read it.  Indexed by
+  // concatenated input channel (source 0 first); pro_mask bit s = transform the chunks of source s.
+  const float* pro_scale;
+  const float* pro_shift;
+  int pro_mask;
 };
 
 // TILES = M=128 tiles per CTA and block: 2 (16x16 block) for BN <= 128, 1 (8 wide x 16 tall) for BN = 256
 // BNB = fused BN-backward reduction in the epilogue: two extra 16 KB slots hold the matching tiles of y (the
 // conv output the BN normalised), paid for with one or two weight stages.
-// AST = halo (A) stages.  With 2 stages the TMA load of the next halo tile has exactly one chunk of MMAs (72 x N/2
-// tensor cycles: 2 304 cycles = 1.3 us for N = 64) to arrive, and the level-1 layers have ONE 64-channel chunk per
-// block.  A third stage (SUNET_HALO2_AST=3, paid for with weight stages and y slots) was measured on B200 and changes
+// Two halo (A) stages.  A third stage (paid for with weight stages and y slots) was measured on B200 and changes
 // nothing: 0.550 vs 0.548 ms for 128 x 256^2 x 64->64, 33.06 vs 33.18 ms per step (profiles/r02/halo_stages_ab.log) —
 // the N = 64 kernel is bound by the shared-memory port (operand reads 65 % + epilogue 27 % of its wavefronts), not
-// by the latency of the halo load.  Two stages stay the default.
+// by the latency of the halo load.
 // Also measured and rejected (profiles/r02/epilogue_groups_ab.log): EIGHT epilogue warps in two groups that take the
 // 64-channel output chunks alternately (own staging tile, y pipeline, store thread and named barrier each).  Parity
 // green, but 0.713 vs 0.736 ms for the level-1 BNB dgrad, 0.479 vs 0.463 at level 2, 0.403 vs 0.381 at level 3 and
 // 32.65 vs 32.52 ms per step: the cost of the BNB epilogue is its extra traffic through the shared-memory port
 // (y tile in, statistics loop out), not the latency of four warps — more warps only contend harder.
-template <int BN, bool BNB = false, int AST = 2>
+//
+// PRO = training-mode prologue fusion (north_star: "BatchNorm ... scale/shift and ReLU fused into the ... prologue"):
+// four extra warps transform every landed halo tile from the producer's raw conv output y to relu(bn(y)) in place.
+// Each CTA's halo load then completes on a barrier of its OWN (the transform warps of that CTA wait on it) and the
+// leader's MMA warp waits on a second barrier that both CTAs' transform warps arrive on.
+template <int BN, bool BNB = false, bool PRO = false>
 struct H2Cfg {
   static constexpr int TILES = (BN == 256) ? 1 : 2;
   static constexpr int PITCH = 8 * TILES + 2;
   static constexpr int A_TX = 18 * PITCH * 128;
   static constexpr int A_SLOT = (A_TX + 1023) / 1024 * 1024;
-  static constexpr int A_STAGES = AST;
+  static constexpr int A_STAGES = 2;
   static constexpr int B_HALF = (BN / 2) * 128;      // this CTA's half of one weight tile
-  static constexpr int B_STAGES = (AST == 3) ? ((BN == 64) ? (BNB ? 8 : 10) : 8)
-                                             : ((BN == 256) ? (BNB ? 7 : 8) : ((BNB && BN == 128) ? 9 : 10));
+  static constexpr int B_STAGES = (BN == 256) ? (BNB ? 7 : 8) : ((BNB && BN == 128) ? 9 : 10);
   static constexpr int STG_BYTES = 128 * 128;
-  static constexpr int Y_SLOTS = BNB ? ((BN == 64 && AST == 2) ? 4 : 2) : 0;      // power of two
+  static constexpr int Y_SLOTS = BNB ? ((BN == 64) ? 4 : 2) : 0;      // power of two
+  static constexpr int THREADS = PRO ? 320 : 192;    // warp 0 TMA, 1 MMA, 2-5 epilogue, (PRO) 6-9 prologue transform
+  static_assert(!(PRO && BNB), "the prologue transform is a forward-pass feature");
   static constexpr int EP_BYTES = BNB ? 0 : 2 * BN * 4;   // inference epilogue: this CTA's scale / shift columns
   static constexpr int SMEM =
       A_STAGES * A_SLOT + B_STAGES * B_HALF + (2 + Y_SLOTS) * STG_BYTES + 1024 + 512 + EP_BYTES;
@@ -69,16 +79,15 @@ struct H2Cfg {
   static constexpr int TMEM_COLS = 2 * TILES * BN;   // TILES x BN columns x 2 accumulator stages
 };
 
-constexpr int kH2Threads = 192;
-
-template <int BN, bool BNB, int AST>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
+template <int BN, bool BNB, bool PRO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((H2Cfg<BN, BNB, PRO>::THREADS), 1)
 conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
                    const __grid_constant__ CUtensorMap mapY, const Halo2Params p) {
   pdl_wait();
   pdl_trigger();
-  using C = H2Cfg<BN, BNB, AST>;
+  using C = H2Cfg<BN, BNB, PRO>;
+  constexpr int kH2Threads = C::THREADS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -93,7 +102,9 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   uint64_t* tfull = bempty + C::B_STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* yfull = tempty + 2;                           // [4], BNB only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 4);
+  uint64_t* alocal = yfull + 4;                           // [A_STAGES], PRO only: this CTA's own halo tile has landed
+  uint64_t* aready = alocal + C::A_STAGES;                // [A_STAGES], PRO only (leader's copy): both tiles transformed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready + C::A_STAGES);
   float* sEp = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);      // [2][BN], !BNB only
 
   const int warp = threadIdx.x >> 5;
@@ -114,6 +125,10 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       mbar_init(&tempty[i], 8);     // 4 epilogue warps x 2 CTAs (only the leader's copy is waited on)
     }
     for (int i = 0; i < 4; ++i) mbar_init(&yfull[i], 1);
+    for (int i = 0; i < C::A_STAGES; ++i) {
+      mbar_init(&alocal[i], 1);
+      mbar_init(&aready[i], 2);     // one arrival per CTA of the pair
+    }
     fence_barrier_init();
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapB);
@@ -156,10 +171,16 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const int c0 = ((cc < p.cpt0) ? cc : cc - p.cpt0) * 64;
         mbar_wait(&aempty[as], aph ^ 1);
         if (elect_one()) {
-          // Only the leader arrives.  The peer cannot run a phase ahead: it refills slot s only after the
-          // leader's MMAs that consumed the previous contents have committed to its aempty[s].
-          if (rank == 0) mbar_arrive_expect_tx(&afull[as], 2 * C::A_TX);
-          tma_load_5d_pair(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * (8 * C::TILES) - 1, by * 16 - 1, n, 0);
+          if (PRO) {
+            // each CTA's tile completes on its own barrier: its transform warps take it from there
+            mbar_arrive_expect_tx(&alocal[as], C::A_TX);
+            tma_load_5d(sA + as * C::A_SLOT, mapA, &alocal[as], c0, bx * (8 * C::TILES) - 1, by * 16 - 1, n, 0);
+          } else {
+            // Only the leader arrives.  The peer cannot run a phase ahead: it refills slot s only after the
+            // leader's MMAs that consumed the previous contents have committed to its aempty[s].
+            if (rank == 0) mbar_arrive_expect_tx(&afull[as], 2 * C::A_TX);
+            tma_load_5d_pair(sA + as * C::A_SLOT, mapA, &afull[as], c0, bx * (8 * C::TILES) - 1, by * 16 - 1, n, 0);
+          }
         }
         __syncwarp();
         if (++as == C::A_STAGES) {
@@ -195,7 +216,7 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acs * (C::TILES * BN);
         for (int cc = 0; cc < cpt; ++cc) {
-          mbar_wait(&afull[as], aph);
+          mbar_wait(PRO ? &aready[as] : &afull[as], aph);
           tc_fence_after_sync();
           const uint32_t a_base = smem_u32(sA + as * C::A_SLOT);
           for (int tap = 0; tap < 9; ++tap) {
@@ -229,6 +250,75 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         }
         if (elect_one()) umma_commit_pair(&tfull[acs]);
         __syncwarp();
+      }
+    }
+  } else if (PRO && warp >= 6) {
+    // ------------------------------------------------------------- prologue transform (both CTAs, 128 threads each)
+    // y -> relu(y * scale + shift), bf16, in place on the landed halo tile: the same fmaf / max / round-to-nearest as
+    // bn_relu_flat_kernel, so the MMA operands are bit-identical to the materialised activation.  Pixels outside the
+    // image are TMA zero fill = the conv's zero padding and stay zero (relu(shift) != 0 in general).
+    const int tt = threadIdx.x - 192;            // 0..127
+    const int j = tt & 7;                        // logical 16-byte chunk of a pixel row: channels 8j .. 8j+7
+    const int r_first = tt >> 3;                 // rows r_first, r_first + 16, ...
+    const int Himg = p.blocks_y * 16, Wimg = p.blocks_x * (8 * C::TILES);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int mp = m_first; mp < m_pairs; mp += m_step) {
+      const int mb = 2 * mp + (int)rank;
+      const int bx = mb % p.blocks_x;
+      const int by = (mb / p.blocks_x) % p.blocks_y;
+      const bool block_valid = mb < p.m_blocks;
+      for (int cc = 0; cc < cpt; ++cc) {
+        const int src = (cc < p.cpt0) ? 0 : 1;
+        const bool active = ((p.pro_mask >> src) & 1) && block_valid;
+        float sc[8], sh[8];
+        if (active) {
+          const float4* ps = reinterpret_cast<const float4*>(p.pro_scale + cc * 64 + j * 8);
+          const float4* ph = reinterpret_cast<const float4*>(p.pro_shift + cc * 64 + j * 8);
+          const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), h0 = __ldg(ph), h1 = __ldg(ph + 1);
+          sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+          sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+        }
+        mbar_wait(&alocal[as], aph);
+        if (active) {
+          uint8_t* tile = sA + as * C::A_SLOT;
+          // four rows per pass, loads first: the LDS -> FMA -> STS chains of one thread overlap
+          for (int rb = r_first; rb < 18 * C::PITCH; rb += 64) {
+            uint4 v[4];
+            bool on[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = rb + 16 * i;
+              const int ry = r / C::PITCH, rx = r - ry * C::PITCH;
+              const int yy = by * 16 - 1 + ry, xx = bx * (8 * C::TILES) - 1 + rx;
+              on[i] = r < 18 * C::PITCH && yy >= 0 && yy < Himg && xx >= 0 && xx < Wimg;
+              if (on[i]) v[i] = *reinterpret_cast<const uint4*>(tile + r * 128 + ((j ^ (r & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (!on[i]) continue;
+              const int r = rb + 16 * i;
+              uint32_t* ww = reinterpret_cast<uint32_t*>(&v[i]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float lo = fmaxf(fmaf(bf16lo(ww[k]), sc[2 * k], sh[2 * k]), 0.f);
+                const float hi = fmaxf(fmaf(bf16hi(ww[k]), sc[2 * k + 1], sh[2 * k + 1]), 0.f);
+                ww[k] = pack_bf16x2(lo, hi);
+              }
+              *reinterpret_cast<uint4*>(tile + r * 128 + ((j ^ (r & 7)) << 4)) = v[i];
+            }
+          }
+          fence_proxy_async_smem();               // generic-proxy writes -> visible to the tensor core's async proxy
+        }
+        named_bar_sync(4, 128);
+        if (tt == 0) {
+          if (rank == 0) mbar_arrive(&aready[as]);
+          else mbar_arrive_remote(&aready[as], 0);
+        }
+        if (++as == C::A_STAGES) {
+          as = 0;
+          aph ^= 1;
+        }
       }
     }
   } else {
@@ -473,30 +563,20 @@ static int halo2_map(CUtensorMap* m, const void* base, int C, int S, int B, int 
   return make_tmap_bf16_5d(m, base, dims, str, box);
 }
 
-template <int BN, bool BNB, int AST>
+template <int BN, bool BNB, bool PRO>
 static int halo2_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& d,
                           const CUtensorMap& y, const Halo2Params& p, int grid, cudaStream_t stream) {
+  using C = H2Cfg<BN, BNB, PRO>;
   static bool attr_set = false;
   if (!attr_set) {
-    int e = check_cuda(cudaFuncSetAttribute(conv3_halo2_kernel<BN, BNB, AST>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<BN, BNB, AST>::SMEM),
+    int e = check_cuda(cudaFuncSetAttribute(conv3_halo2_kernel<BN, BNB, PRO>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
                        "cudaFuncSetAttribute(conv3_halo2)");
     if (e) return e;
     attr_set = true;
   }
-  launch_k(conv3_halo2_kernel<BN, BNB, AST>, dim3(grid), dim3(kH2Threads), H2Cfg<BN, BNB, AST>::SMEM, stream, a0, a1, b,
-           d, y, p);
+  launch_k(conv3_halo2_kernel<BN, BNB, PRO>, dim3(grid), dim3(C::THREADS), C::SMEM, stream, a0, a1, b, d, y, p);
   return check_launch("conv3_halo2_kernel");
-}
-
-// halo stages: 2 (default); SUNET_HALO2_AST=3 selects the three-stage variants where shared memory allows them
-// (N = 64 both forms, N = 128 without the BNB y slots) — an A/B timing knob, see H2Cfg
-static int halo2_ast() {
-  static const int v = [] {
-    const char* e = getenv("SUNET_HALO2_AST");
-    return (e && atoi(e) == 3) ? 3 : 2;
-  }();
-  return v;
 }
 
 bool conv3_halo2_eligible(const sunet_conv_gemm_args* a) {
@@ -573,21 +653,26 @@ int conv3_halo2_launch(const sunet_conv_gemm_args* a, cudaStream_t stream) {
   p.bnb_col0 = bnb ? a->bnb_col0 : 0;
   p.ep_scale = a->ep_scale;
   p.ep_shift = a->ep_shift;
+  p.pro_scale = a->pro_scale;
+  p.pro_shift = a->pro_shift;
+  p.pro_mask = a->pro_mask;
   const int grid = halo2_slots(B, H, W, p.n_tiles, bw) * p.n_tiles * 2;
-  const bool a3 = halo2_ast() == 3;
+  const bool pro = a->pro_scale != nullptr;
+  if (pro) {
+    if (bnb || a->ep_scale || !a->pro_shift || !(a->pro_mask & 3))
+      return set_error(SUNET_ERR_INVALID, "conv_gemm: pro_* needs both vectors, a source mask, and no bnb_* / ep_* epilogue");
+    if (bn == 256) return halo2_launch_t<256, false, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    if (bn == 128) return halo2_launch_t<128, false, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    return halo2_launch_t<64, false, true>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  }
   if (bnb) {
-    if (bn == 256) return halo2_launch_t<256, true, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
-    if (bn == 128) return halo2_launch_t<128, true, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
-    if (a3) return halo2_launch_t<64, true, 3>(mA0, mA1, mB, mD, mY, p, grid, stream);
-    return halo2_launch_t<64, true, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    if (bn == 256) return halo2_launch_t<256, true, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    if (bn == 128) return halo2_launch_t<128, true, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+    return halo2_launch_t<64, true, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
   }
-  if (bn == 256) return halo2_launch_t<256, false, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
-  if (bn == 128) {
-    if (a3) return halo2_launch_t<128, false, 3>(mA0, mA1, mB, mD, mY, p, grid, stream);
-    return halo2_launch_t<128, false, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
-  }
-  if (a3) return halo2_launch_t<64, false, 3>(mA0, mA1, mB, mD, mY, p, grid, stream);
-  return halo2_launch_t<64, false, 2>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  if (bn == 256) return halo2_launch_t<256, false, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  if (bn == 128) return halo2_launch_t<128, false, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
+  return halo2_launch_t<64, false, false>(mA0, mA1, mB, mD, mY, p, grid, stream);
 }
 
 }  // namespace sunet

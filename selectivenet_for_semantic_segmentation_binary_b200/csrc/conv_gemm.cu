@@ -519,6 +519,11 @@ extern "C" int sunet_conv_gemm_bnb_supported(const sunet_conv_gemm_args* a) {
   return (!conv3_halo_eligible(a) && a->d_mode == SUNET_D_NHWC && a->bias == nullptr && a->n_total % 128 == 0) ? 1 : 0;
 }
 
+extern "C" int sunet_conv_gemm_pro_supported(const sunet_conv_gemm_args* a) {
+  if (!a || a->batch <= 0 || a->height <= 0 || a->width <= 0 || a->n_total <= 0 || a->n_total % 64) return 0;
+  return conv3_halo2_eligible(a) ? 1 : 0;          // the prologue transform lives in the CTA-pair halo kernel
+}
+
 extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!a) return set_error(SUNET_ERR_INVALID, "conv_gemm: null args");
@@ -553,6 +558,9 @@ extern "C" int sunet_conv_gemm(const sunet_conv_gemm_args* a, sunet_stream_t str
   if (a->ep_scale && (a->stats || a->bias || a->bnb_y || a->d_mode != SUNET_D_NHWC))
     return set_error(SUNET_ERR_INVALID, "conv_gemm: the inference epilogue excludes stats / bias / bnb / scatter store");
   if (conv3_halo2_eligible(a)) return conv3_halo2_launch(a, stream);
+  if (a->pro_scale != nullptr)
+    return set_error(SUNET_ERR_INVALID, "conv_gemm: the training prologue (pro_scale) is not available for this "
+                                        "shape/mode; check sunet_conv_gemm_pro_supported()");
   const bool bnb = a->bnb_y != nullptr;
   if (bnb && !sunet_conv_gemm_bnb_supported(a))
     return set_error(SUNET_ERR_INVALID, "conv_gemm: the fused BN-backward epilogue (bnb_y) is not available for this "

@@ -62,6 +62,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Cluster-scope acquire: pairs with mbar_arrive_remote (release.cluster) when the data the barrier guards was written
+// by the PEER CTA's threads (the PRO transforms), not by TMA.
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > SUNET_WAIT_LIMIT_CYCLES) {
+      printf("sunet: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x,
+             parity);
+      __trap();
+    }
+  }
+}
+
 // One lane of a fully converged warp.  The producer / MMA warps run their loops warp-uniformly and only
 // predicate the issuing instruction on this: descriptors and addresses then stay in uniform registers
 // (a `if (lane == 0)` body forces an R2UR.BROADCAST chain in front of every UTCHMMA / UTMALDG).
@@ -254,6 +282,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// ... with cluster-scope release: the arriving CTA's own shared-memory writes (the PRO transforms) are what the
+// barrier publishes to the leader.  Costs a cluster-wide fence, so the TMEM hand-back above does not use it.
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");

@@ -51,8 +51,14 @@ struct WgradParams {
   int a_reuse;     // keep A in the tensor core's collector across the taps of a K step (SUNET_WGRAD_A_REUSE, default 1)
   int abox;        // bytes of one A box = kp * 128
   float* out;      // [splits][taps_total][Ca][Nb]
+  // training prologue on B (CTA-pair kernel, shifted-window box only): B holds the producer block's raw conv output y;
+  // the four epilogue warps, idle during the main loop, turn every landed box into relu(y * scale + shift) in place
+  const float* b_pro_scale;
+  const float* b_pro_shift;
+  int W;           // image width (p.H is the height)
 };
 constexpr int MAX_STAGES = 12;
+constexpr int WG_BAR_BYTES = (4 * MAX_STAGES + 2) * 8;   // full, empty, done, tmem slot, (pair + prologue) blocal, bready
 
 // MMA issue for one pipeline stage, taps unrolled at compile time.  The generic (runtime T) loop spent ~25 SASS
 // instructions of the single issuing thread per UTCHMMA — more than the 64 tensor-core cycles an N=128 MMA takes,
@@ -278,6 +284,9 @@ wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* done_bar = bars + 2 * MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  uint64_t* blocal = bars + 2 * MAX_STAGES + 2;       // prologue: this CTA's own B box has landed
+  uint64_t* bready = blocal + MAX_STAGES;             // prologue (leader's copy): both CTAs' boxes are transformed
+  const bool pro = p.b_pro_scale != nullptr;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -286,6 +295,8 @@ wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);      // leader's arrive.expect_tx covers both CTAs' bytes
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&blocal[i], 1);
+      mbar_init(&bready[i], 2);        // one arrival per CTA of the pair
     }
     mbar_init(done_bar, 1);
     fence_barrier_init();
@@ -324,10 +335,15 @@ wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       uint8_t* sb = st + 2 * p.abox;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
-        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (2 * p.abox + p.bboxes * p.b_tx));
+        if (rank == 0)
+          mbar_arrive_expect_tx(&full_bar[stage], pro ? 2 * (2 * p.abox) : 2 * (2 * p.abox + p.bboxes * p.b_tx));
         tma_load_5d_pair(st, &mapA, &full_bar[stage], a_base, x0, y0, n0, 0);
         tma_load_5d_pair(st + p.abox, &mapA, &full_bar[stage], a_base + 64, x0, y0, n0, 0);
-        if (p.shifted) {
+        if (pro) {
+          // the B box completes on this CTA's own barrier: its transform warps take it from there (shifted box only)
+          mbar_arrive_expect_tx(&blocal[stage], p.b_tx);
+          tma_load_5d(sb, mapB, &blocal[stage], cB, x0 - 1, y0 + tg - 1, n0, 0);
+        } else if (p.shifted) {
           tma_load_5d_pair(sb, mapB, &full_bar[stage], cB, x0 - 1, y0 + tg - 1, n0, 0);
         } else {
           for (int t = 0; t < p.T; ++t) {
@@ -355,6 +371,7 @@ wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
+        if (pro) mbar_wait(&bready[stage], phase);
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + 2 * p.abox;
@@ -377,6 +394,72 @@ wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       __syncwarp();
     }
   } else {
+    if (pro) {
+      // -------- prologue transform of the B boxes (both CTAs; these four warps have nothing else to do until the
+      // accumulators are complete): same fmaf / max / round as bn_relu_flat_kernel; pixels outside the image are TMA
+      // zero fill (the conv's padding) and stay zero.  Each WARP owns every fourth stage, so four boxes are in
+      // flight per CTA and the wait -> LDS -> FMA -> STS -> fence -> arrive chain of one box hides behind the
+      // others (one 128-thread group per box measured 0.503 ms against 0.376 ms unfused at 128 x 64^2 x 256).
+      const int pw = warp - 2;                     // 0..3
+      const int j = lane & 7, r_first = lane >> 3;
+      const int cB = n_tile * BNW + (int)rank * 64;          // one B source only (checked by the launcher)
+      float sc[8], sh[8];
+      {
+        const float4* ps = reinterpret_cast<const float4*>(p.b_pro_scale + cB + j * 8);
+        const float4* ph = reinterpret_cast<const float4*>(p.b_pro_shift + cB + j * 8);
+        const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), h0 = __ldg(ph), h1 = __ldg(ph + 1);
+        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+        sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (((kb - kb0) & 3) == pw) {
+          const int xt = kb % p.tiles_x;
+          const int yt = (kb / p.tiles_x) % p.tiles_y;
+          const int x0 = xt * p.tw, yy = yt * p.th + tg - 1;
+          uint8_t* sbp = smem + stage * stage_bytes + 2 * p.abox;
+          mbar_wait(&blocal[stage], phase);
+          if (yy >= 0 && yy < p.H && !(p.dbg_boff & 64)) {     // bit 6: timing experiment, no transform
+            // nine rows per pass, loads first: the LDS -> FMA -> STS chains of one thread overlap
+            for (int rb = r_first; rb < p.kp + 2; rb += 36) {
+              uint4 v[9];
+              bool on[9];
+#pragma unroll
+              for (int i = 0; i < 9; ++i) {
+                const int r = rb + 4 * i;
+                const int xx = x0 - 1 + r;
+                on[i] = r < p.kp + 2 && xx >= 0 && xx < p.W;
+                if (on[i]) v[i] = *reinterpret_cast<const uint4*>(sbp + r * 128 + ((j ^ (r & 7)) << 4));
+              }
+#pragma unroll
+              for (int i = 0; i < 9; ++i) {
+                if (!on[i]) continue;
+                const int r = rb + 4 * i;
+                uint32_t* ww = reinterpret_cast<uint32_t*>(&v[i]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float lo = fmaxf(fmaf(bf16lo(ww[k]), sc[2 * k], sh[2 * k]), 0.f);
+                  const float hi = fmaxf(fmaf(bf16hi(ww[k]), sc[2 * k + 1], sh[2 * k + 1]), 0.f);
+                  ww[k] = pack_bf16x2(lo, hi);
+                }
+                *reinterpret_cast<uint4*>(sbp + r * 128 + ((j ^ (r & 7)) << 4)) = v[i];
+              }
+            }
+            if (!(p.dbg_boff & 128)) fence_proxy_async_smem();     // bit 7: timing experiment, no proxy fence
+          }
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&bready[stage]);
+            else mbar_arrive_remote(&bready[stage], 0);
+          }
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
     const int quad = warp & 3;
     const int mrow = a_base + quad * 32 + lane;
     mbar_wait(done_bar, 0);
@@ -670,6 +753,12 @@ static int make_map(CUtensorMap* m, const void* base, int gs, int C, int S, int 
 
 using namespace sunet;
 
+extern "C" int sunet_wgrad_gemm_pro_supported(const sunet_wgrad_gemm_args* a) {
+  WgPlan w{};
+  if (!a || a->batch <= 0 || a->height <= 0 || a->width <= 0 || plan_wgrad(a, &w)) return 0;
+  return (w.pair && w.shifted && !w.stacked && a->b1 == nullptr && a->b_mode == SUNET_A_CONV3X3) ? 1 : 0;
+}
+
 extern "C" int sunet_wgrad_gemm_splits(const sunet_wgrad_gemm_args* a) {
   WgPlan w{};
   if (!a || plan_wgrad(a, &w)) return -1;
@@ -689,6 +778,10 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
   if (a->partials_bytes < need)
     return set_error(SUNET_ERR_WORKSPACE, "wgrad_gemm: partials buffer %zu < %zu bytes", (size_t)a->partials_bytes, need);
   if (a->b1 && (a->b0_channels % w.BNW)) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: b0 channels vs tile");
+  const bool pro = a->b_pro_scale != nullptr;
+  if (pro && (!a->b_pro_shift || !sunet_wgrad_gemm_pro_supported(a)))
+    return set_error(SUNET_ERR_INVALID, "wgrad_gemm: the B prologue (b_pro_*) needs both vectors and a shape served by the "
+                                        "CTA-pair kernel; check sunet_wgrad_gemm_pro_supported()");
 
   CUtensorMap mA, mB0, mB1;
   const int B = a->batch, H = a->height, W = a->width;
@@ -753,6 +846,9 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     const char* r = getenv("SUNET_WGRAD_A_REUSE");
     p.a_reuse = r ? atoi(r) : 1;
   }
+  p.b_pro_scale = pro ? a->b_pro_scale : nullptr;
+  p.b_pro_shift = pro ? a->b_pro_shift : nullptr;
+  p.W = W;
   p.tmem_cols = 32;
   while (p.tmem_cols < w.T * w.BNW) p.tmem_cols *= 2;
   p.shifted = w.shifted;
@@ -769,7 +865,7 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     p.bboxes = w.T * nb64_cta;
   }
   const int stage_bytes = 2 * p.abox + p.bboxes * p.bslot;
-  const int bar_bytes = (2 * MAX_STAGES + 2) * 8;
+  const int bar_bytes = WG_BAR_BYTES;
   int stages = (227 * 1024 - 1024 - bar_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: stage of %d bytes does not fit", stage_bytes);

@@ -39,6 +39,9 @@ _ENC = [("encoder_layer_1_1", 1, "first"), ("encoder_layer_1_2", 1, "conv"),
 _CH = {1: 64, 2: 128, 3: 256, 4: 512}
 
 
+_FUSE_PROLOGUE_DEFAULT = "1"
+
+
 def kind_first(ly) -> bool:
     return ly.kind == "first"
 
@@ -221,6 +224,23 @@ class SUNetPlan:
             last.bnb_stats = torch.zeros(last.bnb_rows, last.cout, 2, device=dev)
             last.a = None
         self.eval_fused = os.environ.get("SUNET_EVAL_FUSED", "1") != "0"
+        # Training PROLOGUE fusion (SUNET_FUSE_PROLOGUE=1): for conv -> BN -> ReLU -> conv chains with no pool, skip or
+        # ConvT in between, the consumer's forward conv and its weight-gradient GEMM read the producer's RAW conv output
+        # y and apply relu(scale * y + shift) to each staged tile in shared memory, so the producer's activation is
+        # never written to or read from HBM.  Only where both kernels have the variant (CTA-pair halo conv and CTA-pair
+        # shifted-window wgrad: the level-3 blocks at 256^2).  pro_of: consumer name -> producer layer.
+        self.pro_of: Dict[str, _Layer] = {}
+        if os.environ.get("SUNET_FUSE_PROLOGUE", _FUSE_PROLOGUE_DEFAULT) != "0":
+            for pn, cn in (("encoder_layer_1_1", "encoder_layer_1_2"), ("encoder_layer_2_1", "encoder_layer_2_2"),
+                           ("encoder_layer_3_1", "encoder_layer_3_2"), ("decoder_layer_4_2", "decoder_layer_4_1"),
+                           ("decoder_layer_3_2", "decoder_layer_3_1"), ("decoder_layer_2_2", "decoder_layer_2_1")):
+                pl, cl = self.layers[pn], self.layers[cn]
+                h, w = self.hw[cl.level]
+                dy = self.gB[cl.level][0]
+                if K.conv_gemm_pro_supported(K.A_CONV3X3, (B, h, w), pl.y, cl.wf, cl.y) and \
+                        K.wgrad_pro_supported((B, h, w), dy, K.A_CONV3X3, pl.y):
+                    self.pro_of[cn] = pl
+        self._pro_producers = {pl.name for pl in self.pro_of.values()}
         self.ws = K.new_workspace(dev)
         self.partials = None      # sized lazily from the wgrad split plan
         self._partials_bytes = 0
@@ -342,6 +362,9 @@ class SUNetPlan:
             K.conv_gemm(K.A_PLAIN, grid, self.col, ly.wf, ly.y, stats=stats)
         elif ly.kind == "cat":
             K.conv_gemm(K.A_CONV3X3, grid, self.up[ly.level], ly.wf, ly.y, src1=self._skip(ly.level), stats=stats)
+        elif training and ly.name in self.pro_of:
+            pl = self.pro_of[ly.name]
+            K.conv_gemm(K.A_CONV3X3, grid, pl.y, ly.wf, ly.y, stats=stats, pro=(pl.scale, pl.shift))
         else:
             K.conv_gemm(K.A_CONV3X3, grid, self._conv_src(ly), ly.wf, ly.y, stats=stats)
         n = ly.name
@@ -361,6 +384,8 @@ class SUNetPlan:
                 K.bn_relu_heads(ly.y, ly.scale, ly.shift, ly.a if c == 0 else None,
                                 [params[f"{h}.weight"][c] for h in heads], [params[f"{h}.bias"][c:c + 1] for h in heads],
                                 self.logits[c * self.nheads:(c + 1) * self.nheads])
+        elif training and n in self._pro_producers:
+            pass        # relu(bn(y)) is applied by the consumer's prologue; the activation is never materialised
         else:
             K.bn_relu_pool(ly.y, ly.scale, ly.shift, ly.a, self.pool[ly.level] if ly.pool else None,
                            ywin=self.ywin.get(ly.level) if (ly.pool and training) else None)
@@ -469,6 +494,10 @@ class SUNetPlan:
                 K.wgrad_reduce(self.partials, s, 1, ly.cout, 64, 2, gw, real_cin=ly.cin)
             elif ly.kind == "cat":
                 s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self.up[ly.level], self.partials, self._skip(ly.level))
+                K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
+            elif n in self.pro_of:
+                pl = self.pro_of[n]
+                s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, pl.y, self.partials, b_pro=(pl.scale, pl.shift))
                 K.wgrad_reduce(self.partials, s, 9, ly.cout, ly.cin, 0, gw)
             else:
                 s = K.wgrad_gemm(grid, dy, K.A_CONV3X3, self._conv_src(ly), self.partials)

@@ -82,12 +82,23 @@ def conv_gemm_bnb_supported(a_mode: int, grid, src0, weights, dst, *, src1=None,
     return bool(_lib.load().sunet_conv_gemm_bnb_supported(C.byref(a)))
 
 
+def conv_gemm_pro_supported(a_mode: int, grid, src0, weights, dst, *, src1=None, bias=None,
+                            d_mode: int = D_NHWC) -> bool:
+    """True if conv_gemm(..., pro=...) is available for this shape (the CTA-pair halo kernel serves it)."""
+    a = _conv_gemm_args(a_mode, grid, src0, weights, dst, src1, bias, d_mode)
+    return bool(_lib.load().sunet_conv_gemm_pro_supported(C.byref(a)))
+
+
 def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst: torch.Tensor, *,
               src1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-              stats: Optional[torch.Tensor] = None, d_mode: int = D_NHWC, bnb=None, ep=None) -> None:
+              stats: Optional[torch.Tensor] = None, d_mode: int = D_NHWC, bnb=None, ep=None, pro=None) -> None:
     """grid = (batch, height, width) of the GEMM-M pixel grid.
     bnb = (y, scale, shift, mean, invstd): fuse the BatchNorm-backward reduction of the block whose input
-    gradient this launch produces into the epilogue; `stats` then receives (sum g, sum g*xhat) rows."""
+    gradient this launch produces into the epilogue; `stats` then receives (sum g, sum g*xhat) rows.
+    pro = (scale, shift[, mask]): the sources in `mask` (bit 0 src0, bit 1 src1; default src0) hold the RAW conv output
+    of the previous block, scale/shift are indexed by concatenated input channel; the kernel applies
+    relu(scale*y + shift) (BatchNorm(train) + ReLU) to each staged tile in shared memory before the MMAs read it,
+    so the activation is never written to HBM."""
     lib = _lib.load()
     a = _conv_gemm_args(a_mode, grid, src0, weights, dst, src1, bias, d_mode)
     if stats is not None:
@@ -103,6 +114,9 @@ def conv_gemm(a_mode: int, grid, src0: torch.Tensor, weights: torch.Tensor, dst:
         a.bnb_scale, a.bnb_shift, a.bnb_mean, a.bnb_invstd = _f32(scale), _f32(shift), _f32(mean), _f32(invstd)
     if ep is not None:               # inference: dst = relu(acc * scale + shift), BatchNorm(eval) + ReLU folded in
         a.ep_scale, a.ep_shift = _f32(ep[0]), _f32(ep[1])
+    if pro is not None:
+        a.pro_scale, a.pro_shift = _f32(pro[0]), _f32(pro[1])
+        a.pro_mask = int(pro[2]) if len(pro) > 2 else 1       # bit s: source s holds a raw conv output
     _lib.check(lib.sunet_conv_gemm(C.byref(a), _stream()), "sunet_conv_gemm")
 
 
@@ -130,9 +144,17 @@ def wgrad_splits(grid, a, b_mode, b0, b1=None) -> int:
     return r
 
 
-def wgrad_gemm(grid, a, b_mode, b0, partials, b1=None) -> int:
-    """Returns the number of split-K partial slabs written."""
+def wgrad_pro_supported(grid, a, b_mode, b0, b1=None) -> bool:
+    w = _wgrad_args(grid, a, b_mode, b0, b1, None)
+    return bool(_lib.load().sunet_wgrad_gemm_pro_supported(C.byref(w)))
+
+
+def wgrad_gemm(grid, a, b_mode, b0, partials, b1=None, b_pro=None) -> int:
+    """Returns the number of split-K partial slabs written.
+    b_pro = (scale, shift): b0 holds a RAW conv output; relu(scale*y + shift) is applied to each staged B tile."""
     w = _wgrad_args(grid, a, b_mode, b0, b1, partials)
+    if b_pro is not None:
+        w.b_pro_scale, w.b_pro_shift = _f32(b_pro[0]), _f32(b_pro[1])
     lib = _lib.load()
     splits = lib.sunet_wgrad_gemm_splits(C.byref(w))
     _lib.check(lib.sunet_wgrad_gemm(C.byref(w), _stream()), "sunet_wgrad_gemm")

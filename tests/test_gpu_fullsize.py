@@ -14,7 +14,7 @@ B, S = 16, 256
 FUSED_OFF = {"SUNET_FUSE_BNB": "0", "SUNET_FUSE_BNB_POOL": "0", "SUNET_FUSE_HEADS_BN": "0", "SUNET_FIRST_PAIR": "0", "SUNET_OVERLAP_WGRAD": "0"}
 
 
-def _step(monkeypatch, env):
+def _step(monkeypatch, env, batch=B):
     """One SUNet_B forward/backward on seeded inputs with the given environment; returns logits + gradients."""
     from selectivenet_for_semantic_segmentation_binary_b200.model import UNet_B
     from selectivenet_for_semantic_segmentation_binary_b200.selective_loss import (BCEWithLogitsLoss,
@@ -26,7 +26,7 @@ def _step(monkeypatch, env):
     torch.manual_seed(0)
     net = UNet_B("RGB", selective=True).cuda()
     net.train()
-    x, label = O.synthetic_batch(B, S, seed=3)
+    x, label = O.synthetic_batch(batch, S, seed=3)
     x, label = x.cuda(), label.cuda()
     out, sel, aux = net(x)
     loss = BCEWithLogitsLoss()(aux, label)
@@ -35,6 +35,9 @@ def _step(monkeypatch, env):
     torch.cuda.synchronize()
     grads = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
     bufs = {n: b.detach().clone() for n, b in net.named_buffers()}
+    net._plans.clear()               # the plan owns ~230 MB of buffers per patch: free it before the next model
+    del net
+    torch.cuda.empty_cache()
     return dict(out=out.detach(), sel=sel.detach(), aux=aux.detach(), loss=float((loss + s_loss).detach()), cov=float(cov.detach()),
                 grads=grads, bufs=bufs, label=label)
 
@@ -43,12 +46,14 @@ def _rel_l2(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-def test_fused_and_unfused_steps_agree_at_full_size(monkeypatch):
+@pytest.mark.parametrize("batch", [16, 128])
+def test_fused_and_unfused_steps_agree_at_full_size(monkeypatch, batch):
     """Fused BN-backward reductions (dgrad / ConvT-dgrad / heads epilogues), the paired-pixel first layer and the
     side-stream weight gradients are re-associations of the same arithmetic: logits must agree to fp32
-    round-off, gradients to a small fraction of the bf16 noise floor."""
-    a = _step(monkeypatch, {})
-    b = _step(monkeypatch, FUSED_OFF)
+    round-off, gradients to a small fraction of the bf16 noise floor.  batch 16 = one 8-GPU shard, batch 128 = the
+    headline single-GPU configuration of BASELINE.json (8.4 M pixels per level-1 tensor)."""
+    a = _step(monkeypatch, {}, batch)
+    b = _step(monkeypatch, FUSED_OFF, batch)
     for k in ("out", "sel", "aux"):
         assert _rel_l2(a[k], b[k]) < 1e-5, k             # forward differs only in the first layer's K order
     assert abs(a["loss"] - b["loss"]) < 1e-5 * abs(b["loss"]) and abs(a["cov"] - b["cov"]) < 1e-6

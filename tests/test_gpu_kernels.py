@@ -13,7 +13,7 @@ probe = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(probe)
 
 
-@pytest.mark.parametrize("group", ["g1_plain", "g1_conv", "g1_convT", "g1_big", "g1_eval_epilogue", "g1_bnb", "g1_bnb_convT", "g1_bnb_pool", "g2_wgrad", "ew_bn", "ew_heads_loss"])
+@pytest.mark.parametrize("group", ["g1_plain", "g1_conv", "g1_convT", "g1_big", "g1_eval_epilogue", "g1_bnb", "g1_bnb_convT", "g1_bnb_pool", "g2_wgrad", "g1_prologue", "g2_wgrad_prologue", "ew_bn", "ew_heads_loss"])
 def test_kernel_group(group):
     from selectivenet_for_semantic_segmentation_binary_b200 import kernels as K
     assert probe.GROUPS[group](K), f"kernel group {group} failed parity (see captured output)"
