@@ -637,6 +637,146 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ 64-output-channel variant, N = 192
+// Same problem as wgrad64_kernel with the roles arranged so that the MMAs are wide instead of tall.  An M=128 x N=64
+// MMA reads 4 KB of A and 2 KB of B from shared memory for 32 cycles of math: the 128 B/clk port caps it at 62 % of
+// the tensor rate (profiles/r01/mma_rate.log: 51.5 cycles), and five of them per K step leave wgrad64_kernel at
+// ~45 % of peak.  Here a stage is ONE row segment of the layer input (KP+2 pixels, 64 channels) and the THREE dY row
+// segments above / at / below it:
+//   B (N = 192) = the three column taps as shifted windows of the input row   (leading-dimension stride 128 B)
+//   A (M = 128) = two dY rows stacked                                          (leading-dimension stride one row slot)
+// MMA 1 = rows (y, y+1) -> taps dr = 1 (lanes 0-63) and dr = 0 (lanes 64-127); MMA 2 = rows (y-1, y) -> tap dr = 2 in
+// lanes 0-63 (lanes 64-127 repeat dr = 1 and are dropped: M = 64 would run at the same 96 cycles).  Two 96-cycle MMAs
+// per 16 pixels against 10 KB of operand reads each: math-bound at 75 % of the tensor rate by construction.
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad64n_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX0,
+                const __grid_constant__ CUtensorMap mapX1, const WgradParams p, const int stage_bytes) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* done_bar = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapDy);
+    tma_prefetch_desc(&mapX0);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tile = blockIdx.x % p.n_tiles;       // which 64-channel block of the (concatenated) input
+  const int split = blockIdx.x / p.n_tiles;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  const int TH = p.th;                             // input rows per stage; dY rows y0-1 .. y0+TH come as one TMA box
+  const int dy_bytes = (TH + 2) * p.abox;
+
+  if (warp == 0) {
+    const CUtensorMap* mapX = (n_tile < p.c0_blocks) ? &mapX0 : &mapX1;
+    const int cX = ((n_tile < p.c0_blocks) ? n_tile : (n_tile - p.c0_blocks)) * 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int xt = kb % p.tiles_x;
+      const int y = ((kb / p.tiles_x) % p.tiles_y) * TH;   // first row of the layer INPUT (zero fill outside the image)
+      const int n = kb / (p.tiles_x * p.tiles_y);
+      const int x0 = xt * p.kp;
+      uint8_t* st = smem + stage * stage_bytes;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[stage], dy_bytes + TH * p.b_tx);
+        tma_load_5d(st, &mapDy, &full_bar[stage], 0, x0, y - 1, n, 0);
+        tma_load_5d(st + dy_bytes, mapX, &full_bar[stage], cX, x0 - 1, y, n, 0);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(128, 192, true, true);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after_sync();
+      const uint32_t sdy = smem_u32(smem + stage * stage_bytes);
+      const uint32_t sx = sdy + dy_bytes;
+      if (elect_one()) {
+        uint32_t acc = kb > kb0 ? 1u : 0u;
+#pragma unroll 1
+        for (int r = 0; r < TH; ++r) {          // input row y0 + r against dY rows y0 + r - 1 .. y0 + r + 1
+          uint64_t a1 = make_smem_desc_sw128(sdy + (r + 1) * p.abox, p.abox, 1024);     // dY rows (y, y+1)
+          uint64_t a2 = make_smem_desc_sw128(sdy + r * p.abox, p.abox, 1024);           // dY rows (y-1, y)
+          uint64_t bd = make_smem_desc_sw128(sx + r * p.b_tx, 128, 1024);    // column taps 0, 1, 2: one pixel apart
+#pragma unroll 1
+          for (int kk = 0; kk < p.kp / 16; ++kk) {
+            umma_bf16(tmem_base, a1, bd, idesc, acc);
+            umma_bf16(tmem_base + 192, a2, bd, idesc, acc);
+            acc = 1u;
+            a1 += 2048 >> 4;
+            a2 += 2048 >> 4;
+            bd += 2048 >> 4;
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int co = (quad & 1) * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after_sync();
+    // accumulator 0: lanes 0-63 tap row 1, lanes 64-127 tap row 0; accumulator 1: lanes 0-63 tap row 2
+    for (int acc = 0; acc < (quad < 2 ? 2 : 1); ++acc) {
+      const int dr = acc ? 2 : (quad < 2 ? 1 : 0);
+      for (int dc = 0; dc < 3; ++dc) {
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 192 + dc * 64;
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_32x32b_x32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        // out[split][tap][co][ci]: this lane owns 64 consecutive input channels of its output channel
+        float4* o = reinterpret_cast<float4*>(p.out + ((static_cast<size_t>(split) * 9 + dr * 3 + dc) * 64 + co) * p.Nb +
+                                              n_tile * 64);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          o[c] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                             __uint_as_float(v[4 * c + 3]));
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int pow2_div(int v, int cap) {
   int t = 1;
   while (t < cap && (v % (t * 2)) == 0) t *= 2;
@@ -652,6 +792,14 @@ struct WgPlan {
   int stacked;     // wgrad64_kernel
   int pair;        // wgrad_gemm_pair_kernel (cta_group::2)
 };
+
+static bool wgrad64_wide() {
+  static const bool wide = [] {
+    const char* e = getenv("SUNET_WGRAD64_WIDE");     // 0: the tall (M = two taps, N = 64) form, wgrad64_kernel
+    return e ? atoi(e) != 0 : true;
+  }();
+  return wide;
+}
 
 static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   switch (a->b_mode) {
@@ -676,16 +824,26 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   if (w->stacked) {
     w->kp = 64;
     w->tw = 64; w->th = 1; w->nb = 1;
-    w->tiles_x = W / 64; w->tiles_y = H; w->tiles_n = B;
-    w->kb_total = w->tiles_x * H * B;
+    if (wgrad64_wide()) {
+      // input rows per stage: the TH + 2 dY rows of a stage serve TH input rows, so dY is fetched (TH+2)/TH times
+      // instead of three (shared-memory fill traffic is what the N = 192 form has left to give)
+      int th = 4;
+      if (const char* e = getenv("SUNET_WGRAD64_TH")) th = atoi(e);
+      if (th != 1 && th != 2 && th != 4) th = 4;
+      while (H % th) th >>= 1;
+      w->th = th;
+    }
+    w->tiles_x = W / 64; w->tiles_y = H / w->th; w->tiles_n = B;
+    w->kb_total = w->tiles_x * w->tiles_y * B;
     w->n_tiles = w->Nb / 64;
     w->m_tiles = 1;
     w->shifted = 1;
     int want = (2 * num_sms()) / w->n_tiles;
     // short problems: one wave of longer CTAs (prologue + partial-store epilogue cost ~10 us per CTA)
-    if (want > 1 && w->kb_total / want < 48) want = num_sms() / w->n_tiles;
+    if (want > 1 && w->kb_total * w->th / want < 48) want = num_sms() / w->n_tiles;
     if (want < 1) want = 1;
-    int max_splits = (w->kb_total + 7) / 8;
+    int max_splits = (w->kb_total * w->th + 7) / 8;
+    if (max_splits > w->kb_total) max_splits = w->kb_total;
     if (want > max_splits) want = max_splits;
     w->kb_per_split = (w->kb_total + want - 1) / want;
     w->splits = (w->kb_total + w->kb_per_split - 1) / w->kb_per_split;
@@ -810,6 +968,29 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     q.kp = w.kp; q.abox = w.kp * 128;
     q.b_tx = (w.kp + 2) * 128;
     q.bslot = (q.b_tx + 1023) / 1024 * 1024;
+    if (wgrad64_wide()) {
+      // TH input rows (B, N = 192 as three shifted windows each) against TH + 2 dY rows (A, stacked in pairs)
+      CUtensorMap mDy3;
+      WgPlan w3 = w;
+      w3.th = w.th + 2;
+      if ((e = make_map(&mDy3, a->a, 0, a->a_channels, a->a_pix_stride, B, H, W, w3))) return e;
+      q.th = w.th;
+      const int sbytes = ((w.th + 2) * q.abox + w.th * q.b_tx + 1023) / 1024 * 1024;
+      const int bbytes = (2 * MAX_STAGES + 2) * 8;
+      int st = (227 * 1024 - 1024 - bbytes) / sbytes;
+      if (st > MAX_STAGES) st = MAX_STAGES;
+      q.stages = st;
+      static bool attr64n = false;
+      if (!attr64n) {
+        if ((e = check_cuda(cudaFuncSetAttribute(wgrad64n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024), "cudaFuncSetAttribute(wgrad64n)")))
+          return e;
+        attr64n = true;
+      }
+      launch_k(wgrad64n_kernel, dim3(w.n_tiles * w.splits), dim3(WG_THREADS), st * sbytes + 1024 + bbytes, stream, mDy3,
+               mB0, mB1, q, sbytes);
+      return check_launch("wgrad64n_kernel");
+    }
     const int sbytes = q.abox + 3 * q.bslot;
     const int bbytes = (2 * MAX_STAGES + 2) * 8;
     int st = (227 * 1024 - 1024 - bbytes) / sbytes;
