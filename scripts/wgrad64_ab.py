@@ -24,19 +24,21 @@ def timed(fn, n=10):
 
 def main():
     dev = "cuda"
-    B, H, W = 128, 256, 256
-    g = torch.Generator().manual_seed(1)
-    dy = torch.randn(B, H, W, 64, generator=g).to(torch.bfloat16).to(dev)
-    x0 = torch.randn(B, H, W, 64, generator=g).to(torch.bfloat16).to(dev)
-    x1 = torch.randn(B, H, W, 64, generator=g).to(torch.bfloat16).to(dev)
-    for name, b1 in (("64->64", None), ("(64+64)->64", x1)):
+    tag = f"WIDE={os.environ.get('SUNET_WGRAD64_WIDE', '1')} MAXC={os.environ.get('SUNET_WGRAD64_MAXC', '128')}"
+    for (B, H, W, cout, c0, c1) in [(128, 256, 256, 64, 64, 0), (128, 256, 256, 64, 64, 64), (128, 128, 128, 128, 128, 0),
+                                    (128, 128, 128, 128, 128, 128)]:
+        g = torch.Generator().manual_seed(1)
+        dy = torch.randn(B, H, W, cout, generator=g).to(torch.bfloat16).to(dev)
+        x0 = torch.randn(B, H, W, c0, generator=g).to(torch.bfloat16).to(dev)
+        b1 = torch.randn(B, H, W, c1, generator=g).to(torch.bfloat16).to(dev) if c1 else None
         splits = K.wgrad_splits((B, H, W), dy, K.A_CONV3X3, x0, b1)
-        cin = 64 if b1 is None else 128
-        part = torch.empty(splits, 9, 64, cin, device=dev)
+        cin = c0 + c1
+        part = torch.empty(splits, 9, cout, cin, device=dev)
         t = timed(lambda: K.wgrad_gemm((B, H, W), dy, K.A_CONV3X3, x0, part, b1))
-        fl = 2.0 * B * H * W * 64 * cin * 9
-        print(f"WIDE={os.environ.get('SUNET_WGRAD64_WIDE', '1')} wgrad {name}: {t:.3f} ms  {fl / t / 1e9:.0f} TFLOP/s  splits {splits}",
+        fl = 2.0 * B * H * W * cout * cin * 9
+        print(f"{tag} wgrad {H}x{W} {c0}{'+' + str(c1) if c1 else ''}->{cout}: {t:.3f} ms  {fl / t / 1e9:.0f} TFLOP/s  splits {splits}",
               flush=True)
+        del dy, x0, b1, part
 
 
 if __name__ == "__main__":

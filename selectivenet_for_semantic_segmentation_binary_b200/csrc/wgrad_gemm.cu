@@ -680,7 +680,8 @@ wgrad64n_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_tile = blockIdx.x % p.n_tiles;       // which 64-channel block of the (concatenated) input
-  const int split = blockIdx.x / p.n_tiles;
+  const int m_tile = (blockIdx.x / p.n_tiles) % p.m_tiles;     // which 64-channel block of dY
+  const int split = blockIdx.x / (p.n_tiles * p.m_tiles);
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
   const int TH = p.th;                             // input rows per stage; dY rows y0-1 .. y0+TH come as one TMA box
@@ -700,7 +701,7 @@ wgrad64n_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[stage], dy_bytes + TH * p.b_tx);
-        tma_load_5d(st, &mapDy, &full_bar[stage], 0, x0, y - 1, n, 0);
+        tma_load_5d(st, &mapDy, &full_bar[stage], m_tile * 64, x0, y - 1, n, 0);
         tma_load_5d(st + dy_bytes, mapX, &full_bar[stage], cX, x0 - 1, y, n, 0);
       }
       __syncwarp();
@@ -760,8 +761,8 @@ wgrad64n_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
         tmem_ld_32x32b_x32(taddr + 32, v + 32);
         tmem_ld_wait();
         // out[split][tap][co][ci]: this lane owns 64 consecutive input channels of its output channel
-        float4* o = reinterpret_cast<float4*>(p.out + ((static_cast<size_t>(split) * 9 + dr * 3 + dc) * 64 + co) * p.Nb +
-                                              n_tile * 64);
+        float4* o = reinterpret_cast<float4*>(p.out + ((static_cast<size_t>(split) * 9 + dr * 3 + dc) * p.Ca + m_tile * 64 + co) *
+                                                  p.Nb + n_tile * 64);
 #pragma unroll
         for (int c = 0; c < 16; ++c)
           o[c] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
@@ -819,8 +820,15 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   w->pair = (a->a_channels % 256 == 0 && w->BNW == 128 && getenv("SUNET_WGRAD_NO_PAIR") == nullptr) ? 1 : 0;
   if (w->pair) w->m_tiles = a->a_channels / 256;
   const int B = a->batch, H = a->height, W = a->width;
-  w->stacked = (a->b_mode == SUNET_A_CONV3X3 && a->a_channels == 64 && W % 64 == 0 &&
-                getenv("SUNET_WGRAD_NO_STACK") == nullptr) ? 1 : 0;
+  // the 64-channel dY-block kernels serve Cout = 64.  The N = 192 form can also take wider dY in 64-channel blocks
+  // (SUNET_WGRAD64_MAXC=128), but its 25 % idle M rows lose to the M = 128 x N = 128 kernel there: 0.506 vs 0.456 ms
+  // for 128 x 128^2 x 128->128 (profiles/r02/wgrad64_wide_ab.log)
+  static const int stack_max = [] {
+    const char* e = getenv("SUNET_WGRAD64_MAXC");
+    return e ? atoi(e) : 64;
+  }();
+  w->stacked = (a->b_mode == SUNET_A_CONV3X3 && W % 64 == 0 && getenv("SUNET_WGRAD_NO_STACK") == nullptr &&
+                (a->a_channels == 64 || (wgrad64_wide() && a->a_channels % 64 == 0 && a->a_channels <= stack_max))) ? 1 : 0;
   if (w->stacked) {
     w->kp = 64;
     w->tw = 64; w->th = 1; w->nb = 1;
@@ -836,11 +844,13 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
     w->tiles_x = W / 64; w->tiles_y = H / w->th; w->tiles_n = B;
     w->kb_total = w->tiles_x * w->tiles_y * B;
     w->n_tiles = w->Nb / 64;
-    w->m_tiles = 1;
+    w->m_tiles = a->a_channels / 64;
+    w->pair = 0;
     w->shifted = 1;
-    int want = (2 * num_sms()) / w->n_tiles;
+    const int items = w->n_tiles * w->m_tiles;
+    int want = (2 * num_sms()) / items;
     // short problems: one wave of longer CTAs (prologue + partial-store epilogue cost ~10 us per CTA)
-    if (want > 1 && w->kb_total * w->th / want < 48) want = num_sms() / w->n_tiles;
+    if (want > 1 && w->kb_total * w->th / want < 48) want = num_sms() / items;
     if (want < 1) want = 1;
     int max_splits = (w->kb_total * w->th + 7) / 8;
     if (max_splits > w->kb_total) max_splits = w->kb_total;
@@ -956,10 +966,11 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
     if (a->b1 && (a->b0_channels % 64)) return set_error(SUNET_ERR_INVALID, "wgrad_gemm: b0 channels vs tile");
     WgradParams q{};
     q.mode = a->b_mode;
-    q.n_tiles = w.n_tiles; q.splits = w.splits; q.kb_total = w.kb_total; q.kb_per_split = w.kb_per_split;
+    q.n_tiles = w.n_tiles; q.m_tiles = w.m_tiles; q.splits = w.splits; q.kb_total = w.kb_total;
+    q.kb_per_split = w.kb_per_split;
     q.tiles_x = w.tiles_x; q.tiles_y = w.tiles_y;
     q.c0_blocks = a->b0_channels / 64;
-    q.Ca = 64; q.Nb = w.Nb; q.taps_total = 9;
+    q.Ca = a->a_channels; q.Nb = w.Nb; q.taps_total = 9;
     q.out = a->partials;
     {
       const char* b = getenv("SUNET_DBG_BOFF");
@@ -987,7 +998,7 @@ extern "C" int sunet_wgrad_gemm(const sunet_wgrad_gemm_args* a, sunet_stream_t s
           return e;
         attr64n = true;
       }
-      launch_k(wgrad64n_kernel, dim3(w.n_tiles * w.splits), dim3(WG_THREADS), st * sbytes + 1024 + bbytes, stream, mDy3,
+      launch_k(wgrad64n_kernel, dim3(w.n_tiles * w.m_tiles * w.splits), dim3(WG_THREADS), st * sbytes + 1024 + bbytes, stream, mDy3,
                mB0, mB1, q, sbytes);
       return check_launch("wgrad64n_kernel");
     }
