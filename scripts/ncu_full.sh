@@ -15,5 +15,7 @@ run conv128 conv3_halo2_kernel
 run conv64 conv3_halo2_kernel
 run wgrad256 wgrad_gemm
 run wgrad128 wgrad_gemm
-run wgrad64 wgrad64_kernel
+run wgrad64 wgrad64
+run conv256pro conv3_halo2_kernel
+run wgrad256pro wgrad_gemm
 run bnbwd bn_bwd_apply_flat_kernel

@@ -1,6 +1,6 @@
 """Small single-kernel workloads for `ncu --set full` (B200_PROFILING.md: keep the profiled command short).
 
-    python scripts/ncu_target.py conv64|conv128|conv256|wgrad128|wgrad256|wgrad64|bnbwd|bnfwd|headsbwd|headsfwd|hist|
+    python scripts/ncu_target.py conv64|conv128|conv256|conv256pro|wgrad256pro|wgrad128|wgrad256|wgrad64|bnbwd|bnfwd|headsbwd|headsfwd|hist|
                                  losssums|lossbwd|adam
 
 Shapes are the bench shapes (batch 128 of 256x256 patches) of the corresponding SUNet_B layer.
@@ -18,22 +18,24 @@ def bf(*shape):
     return torch.randn(*shape, device="cuda").to(torch.bfloat16)
 
 
-def conv(B, H, W, Cin, Cout, iters=3):
+def conv(B, H, W, Cin, Cout, iters=3, pro=False):
     x = bf(B, H, W, Cin)
+    kw = dict(pro=(torch.rand(Cin, device="cuda") + 0.5, torch.randn(Cin, device="cuda") * 0.3)) if pro else {}
     w = (torch.randn(Cout, 9 * Cin, device="cuda") / (3 * Cin ** 0.5)).to(torch.bfloat16)
     y = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
     rows = K.conv_gemm_stat_rows(B, H, W, Cout, K.A_CONV3X3)
     st = torch.zeros(rows, Cout, 2, device="cuda")
     for _ in range(iters):
-        K.conv_gemm(K.A_CONV3X3, (B, H, W), x, w, y, stats=st)
+        K.conv_gemm(K.A_CONV3X3, (B, H, W), x, w, y, stats=st, **kw)
 
 
-def wgrad(B, H, W, Ca, Cb, iters=3):
+def wgrad(B, H, W, Ca, Cb, iters=3, pro=False):
     dy, x = bf(B, H, W, Ca), bf(B, H, W, Cb)
+    kw = dict(b_pro=(torch.rand(Cb, device="cuda") + 0.5, torch.randn(Cb, device="cuda") * 0.3)) if pro else {}
     splits = K.wgrad_splits((B, H, W), dy, K.A_CONV3X3, x)
     part = torch.empty(splits, 9, Ca, Cb, device="cuda")
     for _ in range(iters):
-        K.wgrad_gemm((B, H, W), dy, K.A_CONV3X3, x, part)
+        K.wgrad_gemm((B, H, W), dy, K.A_CONV3X3, x, part, **kw)
 
 
 def bn(B, H, W, C, bwd, iters=3):
@@ -108,6 +110,8 @@ MODES = {
     "conv512": lambda: conv(128, 32, 32, 512, 512),
     "conv128": lambda: conv(128, 128, 128, 128, 128),
     "conv256": lambda: conv(128, 64, 64, 256, 256),
+    "conv256pro": lambda: conv(128, 64, 64, 256, 256, pro=True),
+    "wgrad256pro": lambda: wgrad(128, 64, 64, 256, 256, pro=True),
     "wgrad128": lambda: wgrad(128, 128, 128, 128, 128),
     "wgrad256": lambda: wgrad(128, 64, 64, 256, 256),
     "wgrad64": lambda: wgrad(128, 256, 256, 64, 64),
