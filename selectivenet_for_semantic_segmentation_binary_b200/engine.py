@@ -147,10 +147,56 @@ class SUNetPlan:
         self.logits = torch.empty(self.n_cls * self.nheads, P, device=dev)
 
         # ---- backward scratch
-        self.gA = {L: act(L, _CH[L]) for L in (1, 2, 3, 4)}
+        # Backward scratch of levels 2-4 lives in the storage of level-1 DECODER forward tensors that are dead by the
+        # time it is first written (SUNET_ALIAS_SCRATCH=0: separate allocations).  Backward runs level 1 first, so
+        #   decoder_layer_1_1.y (last read: its own BN backward)          -> dcat[2]
+        #   decoder_layer_1_2.y (last read: its own BN backward)          -> gB[2] (both buffers)
+        #   decoder_layer_1_2.a (last read: wgrad of decoder_layer_1_1)   -> gA[2], dcat[3]
+        #   up[1]               (last read: wgrad of decoder_layer_1_2)   -> gB[3] (both), gA[3], gB[4] (both)
+        # The two wgrads run on the side stream: backward() makes the main stream wait for their events before the
+        # first aliased write.  Sizes match exactly (channels double and pixels quarter per level): 4 of the 26 level-1-
+        # sized units of a plan, 33.5 MB per 256^2 patch.  The next forward rewrites the level-1 tensors only after
+        # backward has joined the side stream.
+        self.alias_scratch = os.environ.get("SUNET_ALIAS_SCRATCH", "1") != "0"
+        # SUNET_LOW_MEM=1: one dY buffer at level 1 instead of two (the level-1 weight-gradient GEMM then no longer
+        # overlaps the next BN backward) -- 8.4 MB per 256^2 patch for ~1 % of the step; for the batch-size sweep's edge
+        self.low_mem = os.environ.get("SUNET_LOW_MEM", "0") != "0"
+
+        def carve(buf, shapes):
+            flat, off, out = buf.view(-1), 0, []
+            for shp in shapes:
+                n = 1
+                for d in shp:
+                    n *= d
+                out.append(flat[off:off + n].view(*shp))
+                off += n
+            assert off <= flat.numel(), (off, flat.numel())
+            return out
+
+        def shp(L, ch):
+            return (B,) + self.hw[L] + (ch,)
+
+        alias = {}
+        if self.alias_scratch:
+            d11, d12 = self.layers["decoder_layer_1_1"], self.layers["decoder_layer_1_2"]
+            alias["dcat2"], = carve(d11.y, [shp(2, 2 * _CH[2])])
+            alias["gB2a"], alias["gB2b"] = carve(d12.y, [shp(2, _CH[2])] * 2)
+            alias["gA2"], alias["dcat3"] = carve(d12.a, [shp(2, _CH[2]), shp(3, 2 * _CH[3])])
+            (alias["gB3a"], alias["gB3b"], alias["gA3"], alias["gB4a"], alias["gB4b"]) = carve(
+                self.up[1], [shp(3, _CH[3])] * 3 + [shp(4, _CH[4])] * 2)
+        self._wgrad_ev: Dict[str, Optional[torch.cuda.Event]] = {}
+        self.gA = {L: alias[f"gA{L}"] if f"gA{L}" in alias else act(L, _CH[L]) for L in (1, 2, 3, 4)}
         # dY buffers, two per level: the weight-gradient GEMM of layer L runs on a side stream while the main
         # stream already produces dY of layer L-1 into the other buffer
-        self.gB = {L: (act(L, _CH[L]), act(L, _CH[L])) for L in (1, 2, 3, 4)}
+        self.gB = {}
+        for L in (1, 2, 3, 4):
+            if f"gB{L}a" in alias:
+                self.gB[L] = (alias[f"gB{L}a"], alias[f"gB{L}b"])
+            elif L == 1 and self.low_mem:
+                one = act(L, _CH[L])
+                self.gB[L] = (one, one)
+            else:
+                self.gB[L] = (act(L, _CH[L]), act(L, _CH[L]))
         self._gB_next = {L: 0 for L in (1, 2, 3, 4)}
         self._gB_busy = {L: [None, None] for L in (1, 2, 3, 4)}      # event: last wgrad that read the buffer
         # SUNET_WGRAD_AFTER_DGRAD=1: the side-stream wgrad of layer l starts when dgrad(l) has finished, so it runs
@@ -158,7 +204,7 @@ class SUNetPlan:
         self.wgrad_after_dgrad = os.environ.get("SUNET_WGRAD_AFTER_DGRAD", "0") != "0"
         self.side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("SUNET_SIDE_PRIO", "0")))
         self.overlap_wgrad = os.environ.get("SUNET_OVERLAP_WGRAD", "1") != "0"
-        self.dcat = {L: act(L, 2 * _CH[L]) for L in (1, 2, 3)}
+        self.dcat = {L: alias[f"dcat{L}"] if f"dcat{L}" in alias else act(L, 2 * _CH[L]) for L in (1, 2, 3)}
         self.dpool = {L: act(L + 1, _CH[L]) for L in (1, 2, 3)}
         self.dcat_stats = {}
         for L in (1, 2, 3):
@@ -465,7 +511,8 @@ class SUNetPlan:
         n = ly.name
         lvl = ly.level
         idx = self._gB_next[lvl]
-        self._gB_next[lvl] = idx ^ 1
+        if self.gB[lvl][0] is not self.gB[lvl][1]:      # (low-memory mode: one buffer, its busy event is always waited on)
+            self._gB_next[lvl] = idx ^ 1
         dy = self.gB[lvl][idx]
         busy = self._gB_busy[lvl][idx]
         if busy is not None:                       # the wgrad that last read this buffer must be finished
@@ -525,6 +572,7 @@ class SUNetPlan:
         else:
             self._gB_busy[lvl][idx] = self._on_side(wgrad)
             dgrad()
+        self._wgrad_ev[n] = self._gB_busy[lvl][idx]
         return nxt is not None
 
     def backward(self, dlogits: torch.Tensor, params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor],
@@ -582,6 +630,12 @@ class SUNetPlan:
 
             cl = self.bnb_convT.get(lvl)
             kw = {} if cl is None else dict(stats=cl.bnb_stats, bnb=(cl.y, cl.scale, cl.shift, cl.mean, cl.invstd))
+            if self.alias_scratch and lvl in (1, 2):
+                # gA[lvl + 1] (and the scratch written after it) shares storage with a tensor that a level-1 weight-
+                # gradient GEMM on the side stream is still allowed to be reading: see __init__
+                ev = self._wgrad_ev.get("decoder_layer_1_1" if lvl == 1 else "decoder_layer_1_2")
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
             if self.wgrad_after_dgrad:
                 K.conv_gemm(K.A_GATHER2X2, (B, hh, ww), dup, self.upw[lvl]["wd"], self.gA[lvl + 1], **kw)
                 self._on_side(wgrad_t)
