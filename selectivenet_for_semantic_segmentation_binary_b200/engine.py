@@ -153,14 +153,20 @@ class SUNetPlan:
         #   decoder_layer_1_2.y (last read: its own BN backward)          -> gB[2] (both buffers)
         #   decoder_layer_1_2.a (last read: wgrad of decoder_layer_1_1)   -> gA[2], dcat[3]
         #   up[1]               (last read: wgrad of decoder_layer_1_2)   -> gB[3] (both), gA[3], gB[4] (both)
+        #   decoder_layer_2_1.y (last read: its own BN backward)          -> dpool[1], dpool[2], gA[4]
+        #   decoder_layer_2_2.y (last read: its own BN backward)          -> dpool[3]
         # The two wgrads run on the side stream: backward() makes the main stream wait for their events before the
-        # first aliased write.  Sizes match exactly (channels double and pixels quarter per level): 4 of the 26 level-1-
-        # sized units of a plan, 33.5 MB per 256^2 patch.  The next forward rewrites the level-1 tensors only after
-        # backward has joined the side stream.
+        # first aliased write (the y tensors are only ever read on the main stream).  Sizes match exactly (channels
+        # double and pixels quarter per level): 4.56 of the 26 level-1-sized units of a plan, 38 MB per 256^2 patch.
+        # The next forward rewrites these tensors only after backward has joined the side stream.
         self.alias_scratch = os.environ.get("SUNET_ALIAS_SCRATCH", "1") != "0"
-        # SUNET_LOW_MEM=1: one dY buffer at level 1 instead of two (the level-1 weight-gradient GEMM then no longer
-        # overlaps the next BN backward) -- 8.4 MB per 256^2 patch for ~1 % of the step; for the batch-size sweep's edge
-        self.low_mem = os.environ.get("SUNET_LOW_MEM", "0") != "0"
+        # One dY buffer at level 1 for large batches (SUNET_LOW_MEM=0: always two, =1: always one).  The second buffer lets
+        # the BN backward of the next layer start while the weight-gradient GEMM of this one still reads dY on the side
+        # stream; at batch 128 that GEMM always finishes before the dgrad conv it runs beside (0.55 vs 0.76 ms, 1.04 vs
+        # 1.20 ms), so the buffer buys nothing (32.33-32.49 vs 32.42-32.49 ms per step) and costs 8.4 MB per 256^2
+        # patch; at batch 16 it is worth 0.03 ms of a 4.3 ms step and 134 MB are no concern.
+        lm = os.environ.get("SUNET_LOW_MEM", "auto")
+        self.low_mem = (batch * height * width >= 32 * 256 * 256) if lm == "auto" else lm != "0"
 
         def carve(buf, shapes):
             flat, off, out = buf.view(-1), 0, []
@@ -184,6 +190,9 @@ class SUNetPlan:
             alias["gA2"], alias["dcat3"] = carve(d12.a, [shp(2, _CH[2]), shp(3, 2 * _CH[3])])
             (alias["gB3a"], alias["gB3b"], alias["gA3"], alias["gB4a"], alias["gB4b"]) = carve(
                 self.up[1], [shp(3, _CH[3])] * 3 + [shp(4, _CH[4])] * 2)
+            d21, d22 = self.layers["decoder_layer_2_1"], self.layers["decoder_layer_2_2"]
+            alias["dpool1"], alias["dpool2"], alias["gA4"] = carve(d21.y, [shp(2, _CH[1]), shp(3, _CH[2]), shp(4, _CH[4])])
+            alias["dpool3"], = carve(d22.y, [shp(4, _CH[3])])
         self._wgrad_ev: Dict[str, Optional[torch.cuda.Event]] = {}
         self.gA = {L: alias[f"gA{L}"] if f"gA{L}" in alias else act(L, _CH[L]) for L in (1, 2, 3, 4)}
         # dY buffers, two per level: the weight-gradient GEMM of layer L runs on a side stream while the main
@@ -205,7 +214,7 @@ class SUNetPlan:
         self.side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("SUNET_SIDE_PRIO", "0")))
         self.overlap_wgrad = os.environ.get("SUNET_OVERLAP_WGRAD", "1") != "0"
         self.dcat = {L: alias[f"dcat{L}"] if f"dcat{L}" in alias else act(L, 2 * _CH[L]) for L in (1, 2, 3)}
-        self.dpool = {L: act(L + 1, _CH[L]) for L in (1, 2, 3)}
+        self.dpool = {L: alias[f"dpool{L}"] if f"dpool{L}" in alias else act(L + 1, _CH[L]) for L in (1, 2, 3)}
         self.dcat_stats = {}
         for L in (1, 2, 3):
             h, w = self.hw[L]

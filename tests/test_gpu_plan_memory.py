@@ -1,5 +1,5 @@
 """Plan footprint options: backward scratch of levels 2-4 aliased onto dead level-1 decoder tensors (default) and the
-single level-1 dY buffer of SUNET_LOW_MEM=1 must not change a single bit of a training step, in eager mode and under
+single level-1 dY buffer (default; SUNET_LOW_MEM=0 restores two) must not change a single bit of a training step, in eager mode and under
 CUDA-graph replay (SUNetTrainer), and must shrink the plan by what DESIGN.md says."""
 import pytest
 import torch
@@ -35,12 +35,12 @@ def _module_step(monkeypatch, env, batch, size):
 def test_aliased_scratch_is_bit_identical_and_smaller(monkeypatch):
     ref, b0 = _module_step(monkeypatch, {"SUNET_ALIAS_SCRATCH": "0", "SUNET_LOW_MEM": "0"}, 3, 128)
     got, b1 = _module_step(monkeypatch, {"SUNET_ALIAS_SCRATCH": "1", "SUNET_LOW_MEM": "0"}, 3, 128)
-    low, b2 = _module_step(monkeypatch, {"SUNET_ALIAS_SCRATCH": "1", "SUNET_LOW_MEM": "1"}, 3, 128)
+    low, b2 = _module_step(monkeypatch, {"SUNET_ALIAS_SCRATCH": "1", "SUNET_LOW_MEM": "1"}, 3, 128)      # the default
     for k in ref:
         assert torch.equal(ref[k], got[k]), (k, float((ref[k].float() - got[k].float()).abs().max()))
         assert torch.equal(ref[k], low[k]), (k, float((ref[k].float() - low[k].float()).abs().max()))
     unit = 3 * 128 * 128 * 64 * 2            # one level-1 activation tensor
-    assert b0 - b1 >= 4 * unit - (1 << 22), (b0, b1)          # four units gone (allocator rounding: 2 MB blocks)
+    assert b0 - b1 >= 4.5 * unit - (1 << 22), (b0, b1)        # 4.56 units gone (allocator rounding: 2 MB blocks)
     assert b1 - b2 >= unit - (1 << 22), (b1, b2)
 
 
