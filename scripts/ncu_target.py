@@ -51,6 +51,17 @@ def bn(B, H, W, C, bwd, iters=3):
             K.bn_relu_pool(y, sc, sh, out, None)
 
 
+def bnpool(B, H, W, C, iters=3):
+    """forward BN + ReLU + 2x2 pool + winner capture, as the three pooled encoder blocks run it"""
+    y = bf(B, H, W, C)
+    sc, sh = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.3
+    a = torch.empty_like(y)
+    pooled = torch.empty(B, H // 2, W // 2, C, dtype=torch.bfloat16, device="cuda")
+    ywin = torch.empty_like(pooled)
+    for _ in range(iters):
+        K.bn_relu_pool(y, sc, sh, a, pooled, ywin=ywin)
+
+
 def heads(bwd, iters=3, B=128):
     P = B * 256 * 256
     y = (torch.randn(B, 256, 256, 64, device="cuda") * 1.5 + 0.3).to(torch.bfloat16)
@@ -116,6 +127,7 @@ MODES = {
     "wgrad256": lambda: wgrad(128, 64, 64, 256, 256),
     "wgrad64": lambda: wgrad(128, 256, 256, 64, 64),
     "bnbwd": lambda: bn(128, 256, 256, 64, True),
+    "bnpool": lambda: bnpool(128, 256, 256, 64),
     "bnfwd": lambda: bn(128, 256, 256, 64, False),
 }
 

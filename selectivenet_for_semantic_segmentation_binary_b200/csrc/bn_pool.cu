@@ -412,6 +412,8 @@ colsum_finalize_kernel(const float* stats, int rows, int n_total, int col_offset
 }
 
 // ------------------------------------------------------------------ BN + ReLU (+ pool) forward
+// POOL: two 2x2 windows x 8 channels per thread and trip, all eight 16-byte loads issued before the first is used
+// (one window per trip left the kernel latency-bound at 80 % of the HBM rate: 24 warps per SM with 64 B in flight each).
 template <bool POOL>
 __global__ void __launch_bounds__(256)
 bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
@@ -424,60 +426,86 @@ bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, int ys, const float* __
   // POOL: one item = one 2x2 window x 8 channels; else one pixel x 8 channels
   const int HW = POOL ? (H >> 1) : H, WW = POOL ? (W >> 1) : W;
   const long long total = (long long)B * HW * WW * G;
+  if (POOL) {
+    constexpr int U = 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+      bf16x8 v[U][4];
+      long long p00[U], ppix[U];
+      int g[U];
+      bool on[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        on[u] = i < total;
+        // item counts fit 32 bits (checked by the launcher): unsigned 32-bit divisions, not 64-bit ones
+        const uint32_t i32 = on[u] ? (uint32_t)i : 0u;
+        const uint32_t wpix32 = i32 / (uint32_t)G;
+        g[u] = (int)(i32 - wpix32 * (uint32_t)G);
+        const uint32_t rowi = wpix32 / (uint32_t)WW;
+        const int wx = (int)(wpix32 - rowi * (uint32_t)WW);
+        const int n = (int)(rowi / (uint32_t)HW);
+        const int wy = (int)(rowi - (uint32_t)n * (uint32_t)HW);
+        p00[u] = ((long long)n * H + wy * 2) * W + wx * 2;
+        ppix[u] = wpix32;
+        if (on[u]) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            v[u][k] = *reinterpret_cast<const bf16x8*>(y + (p00[u] + (k >> 1) * W + (k & 1)) * ys + g[u] * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!on[u]) continue;
+        float sc[8], sh[8];
+        *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g[u] * 8));
+        *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g[u] * 8 + 4));
+        *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g[u] * 8));
+        *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g[u] * 8 + 4));
+        // (best, yb) = fp32 pre-ReLU activation and conv output y of the window's FIRST maximum — the element
+        // MaxPool2d's backward routes the gradient to (same rule as pool_win_chan); the pooled activation is
+        // relu(best): max over the window of relu(raw) = relu(max raw), exactly
+        float best[8], yb[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long long pix = p00[u] + (k >> 1) * W + (k & 1);
+          float f[8];
+          unpack8(v[u][k], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float raw = fmaf(f[j], sc[j], sh[j]);
+            if (k == 0 || raw > best[j]) {
+              best[j] = raw;
+              yb[j] = f[j];
+            }
+            f[j] = fmaxf(raw, 0.f);
+          }
+          *reinterpret_cast<bf16x8*>(a + pix * as + g[u] * 8) = pack8(f);
+        }
+        if (ywin != nullptr) *reinterpret_cast<bf16x8*>(ywin + ppix[u] * yws + g[u] * 8) = pack8(yb);   // exact: y is bf16
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], 0.f);
+        *reinterpret_cast<bf16x8*>(pooled + ppix[u] * ps + g[u] * 8) = pack8(best);
+      }
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    // item counts fit 32 bits (checked by the launcher): unsigned 32-bit divisions, not 64-bit ones
     const uint32_t i32 = (uint32_t)i;
     const uint32_t wpix32 = i32 / (uint32_t)G;
     const int g = (int)(i32 - wpix32 * (uint32_t)G);
-    const long long wpix = wpix32;
-    const uint32_t rowi = wpix32 / (uint32_t)WW;
-    const int wx = (int)(wpix32 - rowi * (uint32_t)WW);
-    const int n = (int)(rowi / (uint32_t)HW);
-    const int wy = (int)(rowi - (uint32_t)n * (uint32_t)HW);
+    const long long pix = wpix32;
     float sc[8], sh[8];
     *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
     *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
     *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
     *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
-    if (POOL) {
-      // mx = pooled activation; (best, yb) = fp32 pre-ReLU activation and conv output y of the window's FIRST
-      // maximum — the element MaxPool2d's backward routes the gradient to (same rule as pool_win_chan)
-      float mx[8], best[8], yb[8];
-      bf16x8 v[4];
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + pix * ys + g * 8), f);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long long pix = ((long long)n * H + (wy * 2 + (k >> 1))) * W + (wx * 2 + (k & 1));
-        v[k] = *reinterpret_cast<const bf16x8*>(y + pix * ys + g * 8);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long long pix = ((long long)n * H + (wy * 2 + (k >> 1))) * W + (wx * 2 + (k & 1));
-        float f[8];
-        unpack8(v[k], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float raw = fmaf(f[j], sc[j], sh[j]);
-          if (k == 0 || raw > best[j]) {
-            best[j] = raw;
-            yb[j] = f[j];
-          }
-          f[j] = fmaxf(raw, 0.f);
-          mx[j] = (k == 0) ? f[j] : fmaxf(mx[j], f[j]);
-        }
-        *reinterpret_cast<bf16x8*>(a + pix * as + g * 8) = pack8(f);
-      }
-      const long long ppix = ((long long)n * HW + wy) * WW + wx;
-      *reinterpret_cast<bf16x8*>(pooled + ppix * ps + g * 8) = pack8(mx);
-      if (ywin != nullptr) *reinterpret_cast<bf16x8*>(ywin + ppix * yws + g * 8) = pack8(yb);   // exact: y is bf16
-    } else {
-      const long long pix = wpix;
-      float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(y + pix * ys + g * 8), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-      *reinterpret_cast<bf16x8*>(a + pix * as + g * 8) = pack8(f);
-    }
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+    *reinterpret_cast<bf16x8*>(a + pix * as + g * 8) = pack8(f);
   }
 }
 
@@ -671,7 +699,7 @@ bn_bwd_apply_flat_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
 // forms of this kernel (bit-mask decisions, 64-bit index math) were instruction-bound at ~45 % of HBM peak.
 struct PoolWin {
   bf16x8 vy[4], vg[4], vp;
-  long long pix[4];
+  long long p00;      // top-left pixel of the window; pixel k = p00 + (k >> 1) * W + (k & 1)
 };
 __device__ __forceinline__ void pool_win_load(PoolWin& w, long long win, int g, const __nv_bfloat16* __restrict__ dA,
                                               int das, const __nv_bfloat16* __restrict__ dP, int dps,
@@ -684,15 +712,12 @@ __device__ __forceinline__ void pool_win_load(PoolWin& w, long long win, int g, 
   const int n = (int)(rowi / HW);
   const int wy = (int)(rowi - (uint32_t)n * HW);
   const long long p00 = ((long long)n * H + wy * 2) * W + wx * 2;
-  w.pix[0] = p00;
-  w.pix[1] = p00 + 1;
-  w.pix[2] = p00 + W;
-  w.pix[3] = p00 + W + 1;
+  w.p00 = p00;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) w.vy[k] = *reinterpret_cast<const bf16x8*>(y + w.pix[k] * ys + g * 8);
+  for (int k = 0; k < 4; ++k) w.vy[k] = *reinterpret_cast<const bf16x8*>(y + (p00 + (k >> 1) * W + (k & 1)) * ys + g * 8);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (dA) w.vg[k] = *reinterpret_cast<const bf16x8*>(dA + w.pix[k] * das + g * 8);
+    if (dA) w.vg[k] = *reinterpret_cast<const bf16x8*>(dA + (p00 + (k >> 1) * W + (k & 1)) * das + g * 8);
     else w.vg[k] = bf16x8{{0u, 0u, 0u, 0u}};
   }
   w.vp = *reinterpret_cast<const bf16x8*>(dP + win * dps + g * 8);
@@ -769,19 +794,38 @@ bn_bwd_pool_reduce_kernel(const __nv_bfloat16* __restrict__ dA, int das, const _
   }
 }
 
-__global__ void __launch_bounds__(256, 2)
+// The five per-channel constant vectors live in shared memory, not in 40 registers per thread: with 9 sixteen-byte loads
+// in flight per thread the kernel is bound by how many threads fit (bytes in flight per SM), and 128 registers allowed
+// only two blocks (82 % of the HBM rate).
+constexpr int kPoolApplyMaxC = 512;
+// volatile: re-read at every use — hoisting the 40 loop-invariant values into registers is exactly what is being avoided
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+  return r;
+}
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_pool_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __nv_bfloat16* __restrict__ dP, int dps,
                          const __nv_bfloat16* __restrict__ y, int ys, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ coef,
                          __nv_bfloat16* __restrict__ dy, int dys, int B, int H, int W, int C) {
   pdl_wait();
   pdl_trigger();
+  __shared__ float cst[5][kPoolApplyMaxC];       // scale, shift, kg, k1, k0
+  for (int c = threadIdx.x; c < C; c += 256) {
+    cst[0][c] = scale[c];
+    cst[1][c] = shift[c];
+    cst[2][c] = coef[c];
+    cst[3][c] = coef[C + c];
+    cst[4][c] = coef[2 * C + c];
+  }
+  __syncthreads();
   const int G = C >> 3;
   const int g = threadIdx.x % G;
   const int lg = __ffs(G) - 1;
   const long long total = (long long)B * (H >> 1) * (W >> 1) * G;
-  const ChanVec sc = load_chan(scale, g), sh = load_chan(shift, g);
-  const ChanVec kg = load_chan(coef, g), k1 = load_chan(coef + C, g), k0 = load_chan(coef + 2 * C, g);
+  const uint32_t cbase = smem_u32(&cst[0][g * 8]);
+  constexpr uint32_t CS = kPoolApplyMaxC * 4;      // bytes between the constant vectors
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     PoolWin w;
@@ -789,25 +833,26 @@ bn_bwd_pool_apply_kernel(const __nv_bfloat16* __restrict__ dA, int das, const __
     bf16x8 o[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
+      const float2 sc = lds_f2(cbase + jj * 8), sh = lds_f2(cbase + CS + jj * 8), kg = lds_f2(cbase + 2 * CS + jj * 8);
+      const float2 k1 = lds_f2(cbase + 3 * CS + jj * 8), k0 = lds_f2(cbase + 4 * CS + jj * 8);
       float lo[4], hi[4];
       {
         float yv[4], gv[4];
-        pool_win_chan(w, 2 * jj, sc.v[2 * jj], sh.v[2 * jj], yv, gv);
+        pool_win_chan(w, 2 * jj, sc.x, sh.x, yv, gv);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) lo[k] = fmaf(kg.v[2 * jj], gv[k], fmaf(k1.v[2 * jj], yv[k], k0.v[2 * jj]));
+        for (int k = 0; k < 4; ++k) lo[k] = fmaf(kg.x, gv[k], fmaf(k1.x, yv[k], k0.x));
       }
       {
         float yv[4], gv[4];
-        pool_win_chan(w, 2 * jj + 1, sc.v[2 * jj + 1], sh.v[2 * jj + 1], yv, gv);
+        pool_win_chan(w, 2 * jj + 1, sc.y, sh.y, yv, gv);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          hi[k] = fmaf(kg.v[2 * jj + 1], gv[k], fmaf(k1.v[2 * jj + 1], yv[k], k0.v[2 * jj + 1]));
+        for (int k = 0; k < 4; ++k) hi[k] = fmaf(kg.y, gv[k], fmaf(k1.y, yv[k], k0.y));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k].w[jj] = pack_bf16x2(lo[k], hi[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) *reinterpret_cast<bf16x8*>(dy + w.pix[k] * dys + g * 8) = o[k];
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<bf16x8*>(dy + (w.p00 + (k >> 1) * W + (k & 1)) * dys + g * 8) = o[k];
   }
 }
 
@@ -1134,6 +1179,8 @@ extern "C" int sunet_bn_relu_pool_bwd(const void* dA, int dA_pix_stride, const v
                                                                       invstd, dgamma, dbeta, coef);
   if ((e = check_launch("bn_bwd_finalize"))) return e;
   const int ablocks = ew_grid(total, 256);
+  if (pool && channels > kPoolApplyMaxC)
+    return set_error(SUNET_ERR_INVALID, "bn_relu_pool_bwd: pooled layers take at most %d channels", kPoolApplyMaxC);
   if (pool)
     launch_k(bn_bwd_pool_apply_kernel, dim3(ablocks), dim3(256), 0, STREAM, dAp, dA_pix_stride, dPp, dPool_pix_stride, yp, y_pix_stride,
                                                             scale, shift, coef, dyp, dy_pix_stride, batch, height,
@@ -1201,6 +1248,8 @@ extern "C" int sunet_bn_pool_bwd_apply(const void* dA, int dA_pix_stride, const 
   launch_k(bn_bwd_finalize2_kernel, dim3((channels + 7) / 8), dim3(256), 0, STREAM, s0, s1, channels, count, scale,
            mean, invstd, dgamma, dbeta, coef);
   if ((e = check_launch("bn_bwd_finalize2"))) return e;
+  if (channels > kPoolApplyMaxC)
+    return set_error(SUNET_ERR_INVALID, "bn_pool_bwd_apply: pooled layers take at most %d channels", kPoolApplyMaxC);
   launch_k(bn_bwd_pool_apply_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, STREAM,
            reinterpret_cast<const __nv_bfloat16*>(dA), dA_pix_stride, reinterpret_cast<const __nv_bfloat16*>(dPool),
            dPool_pix_stride, reinterpret_cast<const __nv_bfloat16*>(y), y_pix_stride, scale, shift, coef,
