@@ -17,3 +17,19 @@ spec.loader.exec_module(probe)
 def test_kernel_group(group):
     from selectivenet_for_semantic_segmentation_binary_b200 import kernels as K
     assert probe.GROUPS[group](K), f"kernel group {group} failed parity (see captured output)"
+
+
+# Kernel variants that are no longer the default but still ship behind an environment switch (read once per process, so
+# each runs in a process of its own): the single-CTA halo conv, the tall Cout = 64 weight gradient, the wide weight
+# gradient on 128 dY channels, the un-paired / un-shifted weight-gradient forms.
+@pytest.mark.parametrize("env,group", [({"SUNET_HALO_2CTA": "0"}, "g1_conv"), ({"SUNET_WGRAD64_WIDE": "0"}, "g2_wgrad"),
+                                       ({"SUNET_WGRAD64_MAXC": "128"}, "g2_wgrad"), ({"SUNET_WGRAD64_TH": "1"}, "g2_wgrad"),
+                                       ({"SUNET_WGRAD_NO_PAIR": "1"}, "g2_wgrad"), ({"SUNET_WGRAD_NO_SHIFT": "1"}, "g2_wgrad")])
+def test_switchable_variants(env, group):
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gpu_probe.py"), group], env=e, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, (env, r.stdout[-2000:], r.stderr[-1000:])
