@@ -7,7 +7,7 @@ echo "# model  size  batch  ms/step  patches/s  256^2-equivalent patches/s  peak
 B="--no-stock --no-eval --no-cpu-baseline --no-u8 --steps 5 --warmup 3"
 for model in SUNet_B UNet_B; do
   flag=""; [ $model = UNet_B ] && flag="--non-selective"
-  for cfg in "256 32" "256 64" "256 128" "256 256" "256 512" "256 768" "256 1024" "512 32" "512 64" "512 128" "512 192" "512 256"; do
+  for cfg in "256 32" "256 64" "256 128" "256 256" "256 512" "256 768" "256 1024" "256 1152" "512 32" "512 64" "512 128" "512 192" "512 256" "512 288"; do
     set -- $cfg
     python - "$model" "$1" "$2" $flag <<'PY' >> $out 2>/dev/null
 import json, subprocess, sys
