@@ -794,6 +794,19 @@ struct WgPlan {
   int pair;        // wgrad_gemm_pair_kernel (cta_group::2)
 };
 
+// Waves of CTAs per launch (one CTA per SM at a time) that the split-K plan aims for.  ONE: a second wave repeats the
+// ~10 us pipeline fill + partial-slab store of every CTA and doubles what wgrad_reduce has to read, and buys nothing —
+// there is no second CTA on the SM to overlap with.  Measured on the whole step (profiles/r02/wgrad_waves_ab.log):
+// 31.88 -> 31.59 ms at batch 128, 4.34 -> 4.26 ms at batch 16.  SUNET_WGRAD_WAVES=2 restores the old plan.
+static int wgrad_waves() {
+  static const int waves = [] {
+    const char* e = getenv("SUNET_WGRAD_WAVES");
+    const int v = e ? atoi(e) : 1;
+    return v == 2 ? 2 : 1;
+  }();
+  return waves;
+}
+
 static bool wgrad64_wide() {
   static const bool wide = [] {
     const char* e = getenv("SUNET_WGRAD64_WIDE");     // 0: the tall (M = two taps, N = 64) form, wgrad64_kernel
@@ -848,7 +861,7 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
     w->pair = 0;
     w->shifted = 1;
     const int items = w->n_tiles * w->m_tiles;
-    int want = (2 * num_sms()) / items;
+    int want = (wgrad_waves() * num_sms()) / items;
     // short problems: one wave of longer CTAs (prologue + partial-store epilogue cost ~10 us per CTA)
     if (want > 1 && w->kb_total * w->th / want < 48) want = num_sms() / items;
     if (want < 1) want = 1;
@@ -885,8 +898,8 @@ static int plan_wgrad(const sunet_wgrad_gemm_args* a, WgPlan* w) {
   w->kb_total = w->tiles_x * w->tiles_y * w->tiles_n;
   w->shifted = (a->b_mode == SUNET_A_CONV3X3 && w->tw == kp && getenv("SUNET_WGRAD_NO_SHIFT") == nullptr) ? 1 : 0;
   const int base_items = w->m_tiles * w->n_tiles * w->tap_groups * (w->pair ? 2 : 1);   // CTAs per split
-  // two full waves of CTAs (one CTA per SM at a time): round DOWN so no third, nearly empty wave appears
-  int want = (2 * num_sms()) / base_items;
+  // full waves of CTAs (one CTA per SM at a time): round DOWN so no extra, nearly empty wave appears
+  int want = (wgrad_waves() * num_sms()) / base_items;
   // short problems: one wave of longer CTAs (prologue + partial-store epilogue cost ~10 us per CTA)
   if (want > 1 && w->kb_total / want < 48) want = num_sms() / base_items;
   if (want < 1) want = 1;
