@@ -24,7 +24,8 @@ def test_kernel_group(group):
 # gradient on 128 dY channels, the un-paired / un-shifted weight-gradient forms.
 @pytest.mark.parametrize("env,group", [({"SUNET_HALO_2CTA": "0"}, "g1_conv"), ({"SUNET_WGRAD64_WIDE": "0"}, "g2_wgrad"),
                                        ({"SUNET_WGRAD64_MAXC": "128"}, "g2_wgrad"), ({"SUNET_WGRAD64_TH": "1"}, "g2_wgrad"),
-                                       ({"SUNET_WGRAD_NO_PAIR": "1"}, "g2_wgrad"), ({"SUNET_WGRAD_NO_SHIFT": "1"}, "g2_wgrad")])
+                                       ({"SUNET_WGRAD_NO_PAIR": "1"}, "g2_wgrad"), ({"SUNET_WGRAD_NO_SHIFT": "1"}, "g2_wgrad"),
+                                       ({"SUNET_WGRAD_WAVES": "2"}, "g2_wgrad")])
 def test_switchable_variants(env, group):
     import subprocess
     import sys
