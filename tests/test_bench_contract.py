@@ -50,3 +50,13 @@ def test_kernel_stamp_guards_traffic(tmp_path, monkeypatch):
         {"dram_bytes_per_launch": 1.25e9, "kernel_sha": sha, "source": "ncu launch list"}))
     val, why = bench.measured_traffic()
     assert val == 1.25e9 and sha in why
+
+
+def test_committed_traffic_is_from_this_build():
+    """The ncu launch list under profiles/ that bench.py takes `roofline.traffic` from was captured on exactly the kernel
+    sources in the tree (otherwise the bench line would say traffic: null — legal, but then the evidence is stale)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    val, why = bench.measured_traffic()
+    assert val is not None and val > 1e8, why
+    assert bench.kernel_source_sha() in why
